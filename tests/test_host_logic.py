@@ -1,0 +1,93 @@
+"""Host decision logic (uq_b200/host.py) driven by the CPU emulation of the device contract,
+checked against the literal oracle - no GPU needed."""
+import random
+
+import pytest
+
+from conftest import golden_case, load_manifest
+from emu import emu_colstats, emu_stats
+from oracle import uq_literal as lit
+from uq_b200 import host
+
+CASES = sorted(load_manifest())
+
+
+def host_decisions(fq, pad=False, notricks=False):
+    st, n = emu_stats(fq)
+    prefix, suffix, seps = host.derive_qname_layout(st, n)
+    dec = host.decide_alphabets(st, notricks=notricks, pad=pad)
+    cols, bad, dicts = emu_colstats(fq, len(prefix), len(suffix), seps)
+    assert bad < 0
+    columns = host.decide_columns(cols, n, lambda i: dicts[i])
+    return prefix, suffix, seps, dec, columns
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_decisions_match_oracle_on_golden(name):
+    fq, _, kw = golden_case(name)
+    stages = {}
+    lit.encode(fq, stages=stages, **kw)
+    prefix, suffix, seps, dec, columns = host_decisions(fq, pad=kw["pad"], notricks=kw["notricks"])
+    assert (prefix, suffix, seps) == (stages["p1"]["prefix"], stages["p1"]["suffix"], stages["dec"]["separators"])
+    for k in ("bases", "qualities", "N_qual", "bits_per_base", "bits_per_quality", "variable_read_lengths",
+              "dna_bytes", "qual_bytes", "dna_max", "base_distribution", "qual_distribution"):
+        assert dec[k] == stages["dec"][k], k
+    assert columns == stages["columns"]
+
+
+def _fastq(names):
+    return b"".join(n + b"\nACGT\n+\nIIII\n" for n in names)
+
+
+def _rand_names(rng, style):
+    n = rng.randint(2, 40)
+    out = []
+    for i in range(n):
+        if style == 0:
+            out.append(b"@M:%d:%d %d/1" % (rng.randint(1, 3), rng.randint(0, 3000), rng.randint(5, 15)))
+        elif style == 1:      # separator-like characters that are only sometimes constant
+            out.append(b"@r%s_%d:%s" % (b"_" * rng.randint(0, 1), rng.randint(0, 99), rng.choice([b"a:b", b"ab", b"a_b"])))
+        elif style == 2:      # shared long prefixes shrinking over time, adversarial for the order dependence
+            out.append(b"@abc:def:" [: rng.randint(3, 9)] + rng.choice([b"x:1", b"y_2:", b":z", b"q"]) + b"#%d" % rng.randint(0, 5))
+        else:
+            out.append(b"@" + bytes(rng.choice(b"ab:_ 12") for _ in range(rng.randint(1, 8))))
+    return out
+
+
+@pytest.mark.parametrize("style", [0, 1, 2, 3])
+def test_separator_logic_equals_sequential_reference(style):
+    """The closed form derived from (first_lcp_eq, last_count_mismatch) reproduces the reference's
+    order-dependent loop (uq.py:395-413) on random, deliberately ill-formed QNAME sets."""
+    rng = random.Random(1234 + style)
+    agree = errors = 0
+    for _ in range(400):
+        names = _rand_names(rng, style)
+        fq = _fastq(names)
+        lines, total = lit.split_lines(fq)
+        try:
+            p1 = lit.pass1(lines, total)
+            want = (p1["prefix"], p1["suffix"], lit.decide(p1)["separators"])
+        except (lit.UQError, IndexError, Exception) as e:   # IndexError = Q8, re.error = Q6/Q11
+            want = type(e)
+        st, n = emu_stats(fq)
+        try:
+            got = host.derive_qname_layout(st, n)
+        except host.UQError:
+            got = host.UQError
+        if isinstance(want, type):
+            assert got is host.UQError, (names, want)
+            errors += 1
+        else:
+            assert got == want, names
+            agree += 1
+    assert agree > (20 if style < 3 else 3) and agree + errors == 400
+
+
+def test_error_messages():
+    with pytest.raises(host.UQError):
+        host.normalise_options(sort="banana")
+    with pytest.raises(host.UQError):
+        host.normalise_options(pattern=["0.1"])
+    assert host.normalise_options(sort="none") == ((None,), (None,), ["0.1", "0.1"])
+    assert host.key_itemsize(1) == 1 and host.key_itemsize(256) == 1 and host.key_itemsize(257) == 2
+    assert host.key_itemsize(65537) == 4

@@ -1,0 +1,266 @@
+// Stage 1: the Pass-1 statistics of the reference (uq.py:342-425) as device reductions.
+//
+//  k_record_stats  one thread per record: FASTQ shape checks, read-length min/max, and the QNAME
+//                  statistics against line 1 from which the host reproduces the order-dependent
+//                  prefix / suffix / separator logic of uq.py:395-413 exactly (see host.py).
+//  k_pair_hist     base and quality byte histograms plus "does this base always carry one single
+//                  quality" (static_qualities, uq.py:369-375, 420-425, read at uq.py:480-494).
+//                  Counters are private per thread (packed 8-bit fields in shared memory, flushed
+//                  before they can overflow) so the hot loop has no atomics.
+#include "common.cuh"
+
+#define AN_THREADS 256
+#define MAXCH 128            // distinct byte values of line 1 tracked for separator counting
+
+struct an_dev {
+    unsigned long long base_count[256];
+    unsigned long long qual_count[256];
+    int first_q[256];
+    int multi[256];
+    unsigned long long dna_min, dna_max;
+    long long bad_plus, bad_len;
+    unsigned int max_name_len;
+    long long last_count_mismatch[256];
+    long long first_lcp_eq[UQB_HDR_MAX + 1];
+    long long first_lcs_eq[UQB_HDR_MAX + 1];
+    long long first_short_prefix[UQB_HDR_MAX + 1];
+    long long first_short_suffix[UQB_HDR_MAX + 1];
+};
+
+__global__ void k_an_init(an_dev* s) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        s->base_count[i] = 0; s->qual_count[i] = 0; s->first_q[i] = -1; s->multi[i] = 0;
+        s->last_count_mismatch[i] = -1;
+    }
+    for (int i = threadIdx.x; i <= UQB_HDR_MAX; i += blockDim.x) {
+        s->first_lcp_eq[i] = LLONG_MAX; s->first_lcs_eq[i] = LLONG_MAX;
+        s->first_short_prefix[i] = LLONG_MAX; s->first_short_suffix[i] = LLONG_MAX;
+    }
+    if (threadIdx.x == 0) {
+        s->dna_min = ~0ull; s->dna_max = 0; s->bad_plus = LLONG_MAX; s->bad_len = LLONG_MAX; s->max_name_len = 0;
+    }
+}
+
+__global__ void __launch_bounds__(AN_THREADS) k_record_stats(const uint8_t* __restrict__ d, const uint64_t* __restrict__ line_off,
+                                                           uint64_t n_reads, uint32_t first_len, an_dev* __restrict__ s) {
+    __shared__ uint8_t first[UQB_HDR_MAX];
+    __shared__ uint8_t slot_of[256];          // byte value -> slot in the distinct-char list of line 1
+    __shared__ uint8_t slot_char[MAXCH];
+    __shared__ uint16_t first_cnt[MAXCH];
+    __shared__ int nslots_s;
+    __shared__ long long blk_last[MAXCH];
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid; i < first_len; i += AN_THREADS) first[i] = d[i];
+    slot_of[tid] = 255;
+    if (tid < MAXCH) { first_cnt[tid] = 0; blk_last[tid] = -1; }
+    __syncthreads();
+    if (tid == 0) {
+        int ns = 0;
+        for (unsigned i = 0; i < first_len; i++) {
+            uint8_t c = first[i];
+            if (slot_of[c] == 255 && ns < MAXCH) { slot_of[c] = (uint8_t)ns; slot_char[ns] = c; ns++; }
+            if (slot_of[c] != 255) first_cnt[slot_of[c]]++;
+        }
+        nslots_s = ns;
+    }
+    __syncthreads();
+    const int nslots = nslots_s;
+
+    const uint64_t r = (uint64_t)blockIdx.x * AN_THREADS + tid;
+    const bool active = r < n_reads;
+    uint64_t dlen = 0;
+    uint16_t cnt[MAXCH];
+    unsigned name_len = 0;
+    if (active) {
+        const uint64_t o0 = line_off[4 * r], o1 = line_off[4 * r + 1], o2 = line_off[4 * r + 2];
+        const uint64_t o3 = line_off[4 * r + 3], o4 = line_off[4 * r + 4];
+        dlen = o2 - o1 - 1;
+        const uint64_t qlen = o4 - o3 - 1;
+        if (o3 - o2 < 2 || d[o2] != '+') atomicMin(&s->bad_plus, (long long)r);     // uq.py:360, 382
+        if (dlen != qlen) atomicMin(&s->bad_len, (long long)r);                     // uq.py:366, 388
+        // ---- QNAME line against line 1 ----
+        const uint8_t* name = d + o0;
+        const uint64_t nl64 = o1 - o0 - 1;
+        name_len = nl64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)nl64;
+        for (int i = 0; i < nslots; i++) cnt[i] = 0;
+        const unsigned lim = name_len < first_len ? name_len : first_len;
+        unsigned lcp = 0;
+        bool run = true;
+        for (unsigned i = 0; i < name_len; i++) {
+            uint8_t c = __ldg(name + i);
+            if (run && i < lim && c == first[i]) lcp = i + 1; else run = false;
+            uint8_t sl = slot_of[c];
+            if (sl != 255) cnt[sl]++;
+        }
+        unsigned lcs = 0;
+        while (lcs < lim && __ldg(name + name_len - 1 - lcs) == first[first_len - 1 - lcs]) lcs++;
+        if (r >= 1) {
+            atomicMin(&s->first_lcp_eq[lcp], (long long)r);
+            atomicMin(&s->first_lcs_eq[lcs], (long long)r);
+            if (lcp == name_len && name_len < first_len) atomicMin(&s->first_short_prefix[name_len], (long long)r);
+            if (lcs == name_len && name_len < first_len) atomicMin(&s->first_short_suffix[name_len], (long long)r);
+        }
+    }
+    // last record (highest index) whose count of a tracked byte differs from line 1's count
+    for (int i = 0; i < nslots; i++) {
+        bool mis = active && cnt[i] != first_cnt[i];
+        unsigned m = __ballot_sync(0xffffffffu, mis);
+        if (m && lane_id() == 0) {
+            long long rr = (long long)((uint64_t)blockIdx.x * AN_THREADS + (tid & ~31u) + (31 - __clz(m)));
+            atomicMax(&blk_last[i], rr);
+        }
+    }
+    // block reductions of min / max read length and max name length
+    unsigned long long mn = active ? dlen : ~0ull, mx = active ? dlen : 0ull;
+    unsigned nm = active ? name_len : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        unsigned c = __shfl_xor_sync(0xffffffffu, nm, o);
+        mn = a < mn ? a : mn; mx = b > mx ? b : mx; nm = c > nm ? c : nm;
+    }
+    if (lane_id() == 0) {
+        atomicMin(&s->dna_min, mn);
+        atomicMax(&s->dna_max, mx);
+        atomicMax(&s->max_name_len, nm);
+    }
+    __syncthreads();
+    if (tid < (unsigned)nslots && blk_last[tid] >= 0) atomicMax(&s->last_count_mismatch[slot_char[tid]], blk_last[tid]);
+}
+
+// ---- base / quality histograms -------------------------------------------------------------------
+// Private counters: word (v >> 2) of a thread holds four 8-bit counters for byte values 4*(v>>2)..+3.
+// Layout priv[word][thread] keeps every access bank-conflict free.  Byte values >= 128 (never seen in
+// real FASTQ) take a slow global-atomic path.
+#define PH_THREADS 256
+#define PH_WORDS 32
+
+__device__ __forceinline__ void ph_flush(unsigned* priv, unsigned* blk_hist, unsigned tid) {
+#pragma unroll 4
+    for (int w = 0; w < PH_WORDS; w++) {
+        unsigned x = priv[w * PH_THREADS + tid];
+        if (x) {
+            priv[w * PH_THREADS + tid] = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                unsigned c = (x >> (8 * b)) & 255u;
+                if (c) atomicAdd(&blk_hist[4 * w + b], c);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PH_THREADS) k_pair_hist(const uint8_t* __restrict__ d, const uint64_t* __restrict__ line_off,
+                                                         uint64_t n_reads, an_dev* __restrict__ s) {
+    extern __shared__ unsigned ph_smem[];
+    unsigned* priv_b = ph_smem;                               // [PH_WORDS][PH_THREADS]
+    unsigned* priv_q = ph_smem + PH_WORDS * PH_THREADS;
+    unsigned* hist_b = priv_q + PH_WORDS * PH_THREADS;        // [256]
+    unsigned* hist_q = hist_b + 256;
+    int* first_q = (int*)(hist_q + 256);                      // [256]
+    int* multi = first_q + 256;
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    for (unsigned i = tid; i < 2 * PH_WORDS * PH_THREADS; i += PH_THREADS) ph_smem[i] = 0;
+    hist_b[tid] = 0; hist_q[tid] = 0; first_q[tid] = -1; multi[tid] = 0;
+    __syncthreads();
+
+    const uint64_t warps_total = (uint64_t)gridDim.x * (PH_THREADS / 32);
+    const uint64_t warp_global = (uint64_t)blockIdx.x * (PH_THREADS / 32) + (tid >> 5);
+    unsigned since_flush = 0;
+    for (uint64_t r = warp_global; r < n_reads; r += warps_total) {
+        const uint64_t o1 = line_off[4 * r + 1], o2 = line_off[4 * r + 2], o3 = line_off[4 * r + 3], o4 = line_off[4 * r + 4];
+        uint64_t len = o2 - o1 - 1;
+        const uint64_t qlen = o4 - o3 - 1;
+        if (qlen < len) len = qlen;            // malformed records are reported by k_record_stats
+        const uint8_t* dna = d + o1;
+        const uint8_t* qual = d + o3;
+        for (uint64_t i = lane; i < len; i += 32) {
+            const unsigned b = __ldg(dna + i), q = __ldg(qual + i);
+            if (b < 128u) priv_b[(b >> 2) * PH_THREADS + tid] += 1u << (8 * (b & 3u));
+            else atomicAdd(&s->base_count[b], 1ull);
+            if (q < 128u) priv_q[(q >> 2) * PH_THREADS + tid] += 1u << (8 * (q & 3u));
+            else atomicAdd(&s->qual_count[q], 1ull);
+            const int f = first_q[b];
+            if (f != (int)q) {
+                if (f < 0) {
+                    int old = atomicCAS(&first_q[b], -1, (int)q);
+                    if (old >= 0 && old != (int)q) multi[b] = 1;
+                } else {
+                    multi[b] = 1;
+                }
+            }
+            if (++since_flush == 255u) {
+                ph_flush(priv_b, hist_b, tid);
+                ph_flush(priv_q, hist_q, tid);
+                since_flush = 0;
+            }
+        }
+    }
+    ph_flush(priv_b, hist_b, tid);
+    ph_flush(priv_q, hist_q, tid);
+    __syncthreads();
+    if (hist_b[tid]) atomicAdd(&s->base_count[tid], (unsigned long long)hist_b[tid]);
+    if (hist_q[tid]) atomicAdd(&s->qual_count[tid], (unsigned long long)hist_q[tid]);
+    const int f = first_q[tid];
+    if (f >= 0) {
+        int old = atomicCAS(&s->first_q[tid], -1, f);
+        if (old >= 0 && old != f) s->multi[tid] = 1;
+    }
+    if (multi[tid]) s->multi[tid] = 1;
+}
+
+extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
+    if (!fq->line_off) return uqb_fail(ctx, "uqb_analyze: call uqb_split first");
+    if (fq->n_reads == 0) return uqb_fail(ctx, "uqb_analyze: no records");
+    memset(out, 0, sizeof(*out));
+    const uint64_t N = fq->n_reads;
+    // line 1 and the last QNAME line
+    uint64_t offs[2], offl[2];
+    UQB_TRY(uqb_readback(ctx, offs, fq->line_off, 16));
+    UQB_TRY(uqb_readback(ctx, offl, fq->line_off + 4 * (N - 1), 16));
+    uint64_t flen = offs[1] - offs[0] - 1, llen = offl[1] - offl[0] - 1;
+    if (flen > UQB_HDR_MAX || llen > UQB_HDR_MAX)
+        return uqb_fail(ctx, "QNAME line longer than %d bytes is not supported by the device path", UQB_HDR_MAX);
+    out->first_len = (uint32_t)flen;
+    out->last_len = (uint32_t)llen;
+    if (flen) UQB_TRY(uqb_readback(ctx, out->first_name, fq->d + offs[0], flen));
+    if (llen) UQB_TRY(uqb_readback(ctx, out->last_name, fq->d + offl[0], llen));
+    out->bad_first_char = (flen >= 1 && out->first_name[0] == '@') ? -1 : 0;
+
+    an_dev* s;
+    UQB_TRY(uqb_dalloc_t(ctx, &s, 1));
+    UQB_LAUNCH(k_an_init, 1, 256, 0, s);
+    UQB_LAUNCH(k_record_stats, uqb_blocks(N, AN_THREADS), AN_THREADS, 0, fq->d, fq->line_off, N, (uint32_t)flen, s);
+    const size_t smem = (2 * PH_WORDS * PH_THREADS + 4 * 256) * sizeof(unsigned);
+    UQB_CUDA(cudaFuncSetAttribute(k_pair_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = uqb_grid(ctx, N, PH_THREADS / 32, 3);
+    UQB_LAUNCH(k_pair_hist, grid, PH_THREADS, smem, fq->d, fq->line_off, N, s);
+    an_dev* h = new an_dev();
+    int rc = uqb_readback(ctx, h, s, sizeof(an_dev));
+    if (rc == 0) rc = uqb_dfree(ctx, s, sizeof(an_dev));
+    if (rc) { delete h; return rc; }
+    for (int i = 0; i < 256; i++) {
+        out->base_count[i] = h->base_count[i];
+        out->qual_count[i] = h->qual_count[i];
+        out->base_single_qual[i] = h->first_q[i] < 0 ? -1 : (h->multi[i] ? 256 : h->first_q[i]);
+        out->last_count_mismatch[i] = h->last_count_mismatch[i];
+    }
+    out->dna_min = h->dna_min;
+    out->dna_max = h->dna_max;
+    out->bad_plus_record = h->bad_plus == LLONG_MAX ? -1 : h->bad_plus;
+    out->bad_len_record = h->bad_len == LLONG_MAX ? -1 : h->bad_len;
+    out->max_name_len = h->max_name_len;
+    uint32_t pl = (uint32_t)flen, sl = (uint32_t)flen;
+    for (uint32_t j = 0; j <= UQB_HDR_MAX; j++) {
+        out->first_lcp_eq[j] = h->first_lcp_eq[j];
+        out->first_lcs_eq[j] = h->first_lcs_eq[j];
+        out->first_short_prefix[j] = h->first_short_prefix[j];
+        out->first_short_suffix[j] = h->first_short_suffix[j];
+        if (h->first_lcp_eq[j] != LLONG_MAX && j < pl) pl = j;
+        if (h->first_lcs_eq[j] != LLONG_MAX && j < sl) sl = j;
+    }
+    out->prefix_len = pl;
+    out->suffix_len = sl;
+    delete h;
+    return 0;
+}

@@ -1,0 +1,318 @@
+// Device-wide primitives: exclusive scan and a stable LSD radix sort of (key64, aux32, val32) records.
+//
+// Both are HBM-bound streaming kernels.  Layout: SoA arrays, 16 items per thread, 256 threads per
+// CTA (4096-item tiles) so that every warp-level access is a run of 128/256 contiguous bytes.
+#include "common.cuh"
+
+#define PR_THREADS 256
+#define PR_ITEMS 16
+#define PR_TILE (PR_THREADS * PR_ITEMS)
+
+// ================================================================================================
+// scan
+// ================================================================================================
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* total_out) {
+    // exclusive scan of one value per thread across a 256-thread CTA
+    __shared__ T warp_tot[PR_THREADS / 32];
+    unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    T incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    T wbase = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < PR_THREADS / 32; i++) {
+        T t = warp_tot[i];
+        if ((unsigned)i < w) wbase += t;
+        tot += t;
+    }
+    __syncthreads();
+    if (total_out) *total_out = tot;
+    return wbase + incl - v;
+}
+
+template <typename Tout>
+__global__ void __launch_bounds__(PR_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, uint64_t n, Tout* __restrict__ block_sums) {
+    uint64_t base = (uint64_t)blockIdx.x * PR_TILE + (uint64_t)threadIdx.x * PR_ITEMS;
+    Tout s = 0;
+    if (base + PR_ITEMS <= n) {
+        const uint4* p = reinterpret_cast<const uint4*>(in + base);
+#pragma unroll
+        for (int i = 0; i < PR_ITEMS / 4; i++) {
+            uint4 q = __ldg(p + i);
+            s += (Tout)q.x + (Tout)q.y + (Tout)q.z + (Tout)q.w;
+        }
+    } else {
+        for (int i = 0; i < PR_ITEMS; i++)
+            if (base + i < n) s += (Tout)in[base + i];
+    }
+    Tout tot;
+    block_exclusive_scan<Tout>(s, &tot);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+template <typename Tout>
+__global__ void __launch_bounds__(1024) k_scan_block_sums(Tout* __restrict__ sums, uint64_t nblocks, Tout* __restrict__ total) {
+    // single CTA: exclusive scan of the per-tile sums, 1024 at a time with a running carry
+    __shared__ Tout warp_tot[32];
+    __shared__ Tout carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    for (uint64_t start = 0; start < nblocks; start += 1024) {
+        uint64_t i = start + threadIdx.x;
+        Tout v = i < nblocks ? sums[i] : (Tout)0;
+        Tout incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            Tout t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) warp_tot[w] = incl;
+        __syncthreads();
+        Tout wbase = 0, tot = 0;
+        for (int k = 0; k < 32; k++) {
+            Tout t = warp_tot[k];
+            if ((unsigned)k < w) wbase += t;
+            tot += t;
+        }
+        Tout carry = carry_s;
+        if (i < nblocks) sums[i] = carry + wbase + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry_s;
+}
+
+template <typename Tout>
+__global__ void __launch_bounds__(PR_THREADS) k_scan_apply(const uint32_t* in, Tout* out, uint64_t n,
+                                                          const Tout* __restrict__ block_offsets) {   // in may alias out
+    uint64_t base = (uint64_t)blockIdx.x * PR_TILE + (uint64_t)threadIdx.x * PR_ITEMS;
+    uint32_t v[PR_ITEMS];
+    Tout s = 0;
+#pragma unroll
+    for (int i = 0; i < PR_ITEMS; i++) {
+        v[i] = (base + i < n) ? in[base + i] : 0u;
+        s += (Tout)v[i];
+    }
+    Tout ex = block_exclusive_scan<Tout>(s, nullptr) + block_offsets[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < PR_ITEMS; i++) {
+        if (base + i < n) out[base + i] = ex;
+        ex += (Tout)v[i];
+    }
+}
+
+template <typename Tout>
+static int scan_impl(uqb_ctx* ctx, const uint32_t* d_in, Tout* d_out, uint64_t n, Tout* d_total) {
+    if (n == 0) {
+        if (d_total) UQB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(Tout), ctx->stream));
+        return 0;
+    }
+    uint64_t nblocks = (n + PR_TILE - 1) / PR_TILE;
+    Tout* sums;
+    UQB_TRY(uqb_dalloc_t(ctx, &sums, nblocks));
+    UQB_LAUNCH(k_scan_reduce<Tout>, (unsigned)nblocks, PR_THREADS, 0, d_in, n, sums);
+    UQB_LAUNCH(k_scan_block_sums<Tout>, 1, 1024, 0, sums, nblocks, d_total);
+    UQB_LAUNCH(k_scan_apply<Tout>, (unsigned)nblocks, PR_THREADS, 0, d_in, d_out, n, sums);
+    UQB_TRY(uqb_dfree(ctx, sums, nblocks * sizeof(Tout)));
+    return 0;
+}
+
+int uqb_scan_u32(uqb_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, uint64_t n, uint32_t* d_total) {
+    return scan_impl<uint32_t>(ctx, d_in, d_out, n, d_total);
+}
+int uqb_scan_u32_to_u64(uqb_ctx* ctx, const uint32_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_total) {
+    return scan_impl<unsigned long long>(ctx, d_in, (unsigned long long*)d_out, n, (unsigned long long*)d_total);
+}
+
+// ================================================================================================
+// radix sort
+// ================================================================================================
+struct bits_summary { unsigned long long or64, and64; unsigned int or32, and32; };
+
+__global__ void __launch_bounds__(256) k_bits_reduce(const uint64_t* __restrict__ key, const uint32_t* __restrict__ aux, uint64_t n,
+                                                     bits_summary* __restrict__ out) {
+    unsigned long long o64 = 0, a64 = ~0ull;
+    unsigned int o32 = 0, a32 = ~0u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long k = key[i];
+        o64 |= k; a64 &= k;
+        if (aux) { unsigned int a = aux[i]; o32 |= a; a32 &= a; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        o64 |= __shfl_xor_sync(0xffffffffu, o64, o);
+        a64 &= __shfl_xor_sync(0xffffffffu, a64, o);
+        o32 |= __shfl_xor_sync(0xffffffffu, o32, o);
+        a32 &= __shfl_xor_sync(0xffffffffu, a32, o);
+    }
+    if (lane_id() == 0) {
+        atomicOr(&out->or64, o64);
+        atomicAnd(&out->and64, a64);
+        atomicOr(&out->or32, o32);
+        atomicAnd(&out->and32, a32);
+    }
+}
+
+template <bool AUXDIGIT>
+__global__ void __launch_bounds__(PR_THREADS) k_radix_hist(const uint64_t* __restrict__ key, const uint32_t* __restrict__ aux, uint64_t n,
+                                                          int shift, uint32_t* __restrict__ ghist, uint32_t nblk) {
+    __shared__ uint32_t hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t tile0 = (uint64_t)blockIdx.x * PR_TILE;
+#pragma unroll 4
+    for (int j = 0; j < PR_ITEMS; j++) {
+        uint64_t idx = tile0 + (uint64_t)j * PR_THREADS + threadIdx.x;
+        if (idx < n) {
+            uint32_t d = AUXDIGIT ? ((aux[idx] >> shift) & 255u) : (uint32_t)((key[idx] >> shift) & 255ull);
+            atomicAdd(&hist[d], 1u);
+        }
+    }
+    __syncthreads();
+    ghist[(uint64_t)threadIdx.x * nblk + blockIdx.x] = hist[threadIdx.x];
+}
+
+// Stable scatter: every warp owns 512 consecutive items of the tile and ranks them 32 at a time
+// with match_any, so the order inside a digit bucket is (CTA, warp, round, lane) = input order.
+template <bool AUXDIGIT, bool HASAUX>
+__global__ void __launch_bounds__(PR_THREADS) k_radix_scatter(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ ain,
+                                                             const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
+                                                             uint32_t* __restrict__ aout, uint32_t* __restrict__ vout, uint64_t n,
+                                                             int shift, const uint32_t* __restrict__ goff, uint32_t nblk) {
+    __shared__ uint32_t whist[PR_THREADS / 32][256];
+    __shared__ uint32_t wbase[PR_THREADS / 32][256];
+    const unsigned tid = threadIdx.x, w = tid >> 5, lane = tid & 31u;
+    for (unsigned i = tid; i < (PR_THREADS / 32) * 256; i += PR_THREADS) (&whist[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t warp0 = (uint64_t)blockIdx.x * PR_TILE + (uint64_t)w * (32 * PR_ITEMS);
+    uint64_t k[PR_ITEMS];
+    uint32_t a[PR_ITEMS], v[PR_ITEMS], rk[PR_ITEMS];
+#pragma unroll
+    for (int j = 0; j < PR_ITEMS; j++) {
+        uint64_t idx = warp0 + (uint64_t)j * 32 + lane;
+        bool valid = idx < n;
+        k[j] = 0; a[j] = 0; v[j] = 0;
+        if (valid) {
+            k[j] = kin[idx];
+            if (HASAUX) a[j] = ain[idx];
+            v[j] = vin[idx];
+        }
+        uint32_t d = 256u;    // sentinel digit for lanes beyond the end
+        if (valid) d = AUXDIGIT ? ((a[j] >> shift) & 255u) : (uint32_t)((k[j] >> shift) & 255ull);
+        unsigned m = __match_any_sync(0xffffffffu, d);
+        unsigned r = __popc(m & ((1u << lane) - 1u));
+        int leader = __ffs(m) - 1;
+        uint32_t old = 0;
+        if (valid && (int)lane == leader) {
+            old = whist[w][d];
+            whist[w][d] = old + __popc(m);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rk[j] = (d << 16) | (old + r);     // old + r < 512
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        uint32_t run = goff[(uint64_t)tid * nblk + blockIdx.x];
+#pragma unroll
+        for (int w2 = 0; w2 < PR_THREADS / 32; w2++) {
+            wbase[w2][tid] = run;
+            run += whist[w2][tid];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PR_ITEMS; j++) {
+        uint64_t idx = warp0 + (uint64_t)j * 32 + lane;
+        if (idx < n) {
+            uint32_t d = rk[j] >> 16;
+            uint32_t pos = wbase[w][d] + (rk[j] & 0xffffu);
+            kout[pos] = k[j];
+            if (HASAUX) aout[pos] = a[j];
+            vout[pos] = v[j];
+        }
+    }
+}
+
+int uqb_sortbuf_alloc(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool with_aux) {
+    sb->cap = n;
+    sb->cur = 0;
+    for (int i = 0; i < 2; i++) {
+        UQB_TRY(uqb_dalloc_t(ctx, &sb->key[i], n));
+        UQB_TRY(uqb_dalloc_t(ctx, &sb->val[i], n));
+        if (with_aux) UQB_TRY(uqb_dalloc_t(ctx, &sb->aux[i], n));
+    }
+    return 0;
+}
+
+int uqb_sortbuf_free(uqb_ctx* ctx, uqb_sortbuf* sb) {
+    for (int i = 0; i < 2; i++) {
+        UQB_TRY(uqb_dfree(ctx, sb->key[i], sb->cap * 8)); sb->key[i] = nullptr;
+        UQB_TRY(uqb_dfree(ctx, sb->val[i], sb->cap * 4)); sb->val[i] = nullptr;
+        if (sb->aux[i]) { UQB_TRY(uqb_dfree(ctx, sb->aux[i], sb->cap * 4)); sb->aux[i] = nullptr; }
+    }
+    return 0;
+}
+
+// digit windows: 8-bit windows that start at the lowest still-uncovered varying bit
+static int plan_windows(uint64_t varying, int nbits, int* shifts) {
+    int cnt = 0;
+    int b = 0;
+    while (b < nbits) {
+        if ((varying >> b) & 1ull) {
+            shifts[cnt++] = b;
+            b += 8;
+        } else {
+            b++;
+        }
+    }
+    return cnt;
+}
+
+int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux) {
+    if (n < 2) return 0;
+    if (n >= (1ull << 32)) return uqb_fail(ctx, "radix sort: %llu items exceed the 32-bit index range", (unsigned long long)n);
+    bits_summary init = {0ull, ~0ull, 0u, ~0u}, got;
+    bits_summary* d_bits;
+    UQB_TRY(uqb_dalloc_t(ctx, &d_bits, 1));
+    UQB_CUDA(cudaMemcpyAsync(d_bits, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    UQB_LAUNCH(k_bits_reduce, uqb_grid(ctx, n, 256 * 8), 256, 0, sb->key[sb->cur], use_aux ? sb->aux[sb->cur] : nullptr, n, d_bits);
+    UQB_TRY(uqb_readback(ctx, &got, d_bits, sizeof(got)));
+    UQB_TRY(uqb_dfree(ctx, d_bits, sizeof(bits_summary)));
+
+    int kshift[16], ashift[8];
+    int nk = plan_windows(got.or64 ^ got.and64, 64, kshift);
+    int na = use_aux ? plan_windows((uint64_t)(got.or32 ^ got.and32), 32, ashift) : 0;
+    if (nk + na == 0) return 0;
+
+    uint32_t nblk = (uint32_t)((n + PR_TILE - 1) / PR_TILE);
+    uint32_t* ghist;
+    uint64_t hist_n = (uint64_t)256 * nblk;
+    UQB_TRY(uqb_dalloc_t(ctx, &ghist, hist_n));
+    const bool has_aux = sb->aux[0] != nullptr;
+    for (int p = 0; p < nk + na; p++) {
+        bool auxd = p >= nk;
+        int shift = auxd ? ashift[p - nk] : kshift[p];
+        int c = sb->cur, o = c ^ 1;
+        if (auxd) UQB_LAUNCH(k_radix_hist<true>, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], n, shift, ghist, nblk);
+        else      UQB_LAUNCH(k_radix_hist<false>, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], n, shift, ghist, nblk);
+        UQB_TRY(uqb_scan_u32(ctx, ghist, ghist, hist_n, nullptr));
+        auto k_radix_scatter_aux = k_radix_scatter<true, true>;
+        auto k_radix_scatter_key_aux = k_radix_scatter<false, true>;
+        auto k_radix_scatter_key = k_radix_scatter<false, false>;
+        if (auxd)         UQB_LAUNCH(k_radix_scatter_aux, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        else if (has_aux) UQB_LAUNCH(k_radix_scatter_key_aux, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        else              UQB_LAUNCH(k_radix_scatter_key, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        sb->cur = o;
+    }
+    UQB_TRY(uqb_dfree(ctx, ghist, hist_n * 4));
+    return 0;
+}

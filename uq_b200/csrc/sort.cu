@@ -1,0 +1,323 @@
+// Stage 3: stable sort / unique of fixed-width byte rows in memcmp order.
+// Replaces numpy.argsort / numpy.unique(return_inverse) / fancy-index gathers in
+// encode_dna_qual (uq.py:765-805) and encode_qname (uq.py:808-851).
+//
+// Algorithm: MSD refinement in 8-byte chunks on top of the stable LSD radix sort of prims.cu.
+//   round 0   sort (be64(row[0:8]), row index) over all rows; mark group heads.
+//   round c   only rows that are still tied with a neighbour AND whose tie group is not made of
+//             identical rows ("all-equal finisher": one compare of the remaining bytes against the
+//             group's first row) stay active; they are compacted, keyed by (group id, be64(row[8c:8c+8]))
+//             and sorted again; results are written back in place.  Groups are contiguous, so a
+//             sort by (group id, chunk) never moves a row out of its group's position range.
+// Stability: the radix sort is stable and every round keeps the previous order for equal keys, so
+// equal rows end in input order (numpy kind='stable').
+#include "common.cuh"
+
+#define ST 256
+
+__global__ void __launch_bounds__(ST) k_chunk0_keys(const uint8_t* __restrict__ rows, uint64_t n, uint32_t width,
+                                                   uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+    uint64_t i = (uint64_t)blockIdx.x * ST + threadIdx.x;
+    if (i >= n) return;
+    key[i] = load_be64(rows + i * width, width < 8 ? width : 8);
+    val[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(ST) k_mark_heads(const uint64_t* __restrict__ key, uint64_t n, uint32_t* __restrict__ head) {
+    uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
+    if (p >= n) return;
+    head[p] = (p == 0 || key[p] != key[p - 1]) ? 1u : 0u;
+}
+
+// gid[p] = excl[p] + head[p] - 1 ; headpos[gid] = p for heads
+__global__ void __launch_bounds__(ST) k_headpos(const uint32_t* __restrict__ head, const uint32_t* __restrict__ excl, uint64_t n,
+                                               uint32_t* __restrict__ headpos) {
+    uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
+    if (p >= n) return;
+    if (head[p]) headpos[excl[p]] = (uint32_t)p;
+}
+
+// a non-head member that differs from its group's first row in bytes [off, width) marks the group
+__global__ void __launch_bounds__(ST) k_group_diff(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
+                                                  const uint32_t* __restrict__ perm, const uint32_t* __restrict__ head,
+                                                  const uint32_t* __restrict__ excl, const uint32_t* __restrict__ headpos,
+                                                  uint64_t n, uint32_t* __restrict__ gdiff) {
+    uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
+    if (p >= n || head[p]) return;
+    uint32_t g = excl[p] - 1;           // inclusive scan - 1 with head[p] == 0
+    if (gdiff[g]) return;
+    const uint8_t* a = rows + (uint64_t)perm[p] * width + off;
+    const uint8_t* b = rows + (uint64_t)perm[headpos[g]] * width + off;
+    for (uint32_t i = 0; i < width - off; i++) {
+        if (__ldg(a + i) != __ldg(b + i)) { gdiff[g] = 1; return; }
+    }
+}
+
+__global__ void __launch_bounds__(ST) k_active_flags(const uint32_t* __restrict__ head, const uint32_t* __restrict__ excl,
+                                                    const uint32_t* __restrict__ gdiff, uint64_t n, uint32_t* __restrict__ act) {
+    uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
+    if (p >= n) return;
+    uint32_t g = excl[p] + head[p] - 1;
+    bool single = head[p] && (p + 1 == n || head[p + 1]);
+    act[p] = (!single && gdiff[g]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(ST) k_compact_active(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
+                                                      const uint32_t* __restrict__ act, const uint32_t* __restrict__ apos,
+                                                      const uint32_t* __restrict__ head, const uint32_t* __restrict__ excl,
+                                                      const uint32_t* __restrict__ perm, uint64_t n, uint32_t* __restrict__ pos_list,
+                                                      uint64_t* __restrict__ key, uint32_t* __restrict__ aux, uint32_t* __restrict__ val) {
+    uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
+    if (p >= n || !act[p]) return;
+    uint32_t j = apos[p];
+    uint32_t row = perm[p];
+    pos_list[j] = (uint32_t)p;
+    uint32_t rem = width - off;
+    key[j] = load_be64(rows + (uint64_t)row * width + off, rem < 8 ? rem : 8);
+    aux[j] = excl[p] + head[p] - 1;
+    val[j] = row;
+}
+
+__global__ void __launch_bounds__(ST) k_write_back(const uint64_t* __restrict__ key, const uint32_t* __restrict__ aux,
+                                                  const uint32_t* __restrict__ val, const uint32_t* __restrict__ pos_list, uint64_t m,
+                                                  uint32_t* __restrict__ perm, uint32_t* __restrict__ head) {
+    uint64_t j = (uint64_t)blockIdx.x * ST + threadIdx.x;
+    if (j >= m) return;
+    uint32_t p = pos_list[j];
+    perm[p] = val[j];
+    head[p] = (j == 0 || aux[j] != aux[j - 1] || key[j] != key[j - 1]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(ST) k_gid_from_scan(const uint32_t* __restrict__ head, uint32_t* __restrict__ excl_inout, uint64_t n) {
+    uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
+    if (p >= n) return;
+    excl_inout[p] = excl_inout[p] + head[p] - 1;
+}
+
+__global__ void __launch_bounds__(ST) k_iota_zero(uint32_t* __restrict__ perm, uint32_t* __restrict__ gid, uint64_t n) {
+    uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
+    if (p >= n) return;
+    perm[p] = (uint32_t)p;
+    gid[p] = 0;
+}
+
+int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t width,
+                       uint32_t** d_perm, uint32_t** d_gid_sorted, uint64_t* n_unique) {
+    *d_perm = nullptr; *d_gid_sorted = nullptr; *n_unique = 0;
+    if (n >= (1ull << 32)) return uqb_fail(ctx, "sort_rows: %llu rows exceed the 32-bit index range", (unsigned long long)n);
+    uint32_t *perm, *head, *excl;
+    UQB_TRY(uqb_dalloc_t(ctx, &perm, n));
+    UQB_TRY(uqb_dalloc_t(ctx, &excl, n));
+    if (n == 0) { *d_perm = perm; *d_gid_sorted = excl; return 0; }
+    const unsigned nb = uqb_blocks(n, ST);
+    if (width == 0) {
+        UQB_LAUNCH(k_iota_zero, nb, ST, 0, perm, excl, n);
+        *d_perm = perm; *d_gid_sorted = excl; *n_unique = 1;
+        return 0;
+    }
+    UQB_TRY(uqb_dalloc_t(ctx, &head, n));
+    uint32_t* d_tot;
+    UQB_TRY(uqb_dalloc_t(ctx, &d_tot, 2));
+
+    // ---- round 0 ----
+    {
+        uqb_sortbuf sb;
+        UQB_TRY(uqb_sortbuf_alloc(ctx, &sb, n, false));
+        UQB_LAUNCH(k_chunk0_keys, nb, ST, 0, rows, n, width, sb.key[0], sb.val[0]);
+        UQB_TRY(uqb_radix_sort(ctx, &sb, n, false));
+        UQB_LAUNCH(k_mark_heads, nb, ST, 0, sb.key[sb.cur], n, head);
+        UQB_CUDA(cudaMemcpyAsync(perm, sb.val[sb.cur], n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        UQB_TRY(uqb_sortbuf_free(ctx, &sb));
+    }
+    // ---- refinement rounds ----
+    const uint32_t nchunks = (width + 7) / 8;
+    if (nchunks > 1) {
+        uint32_t *headpos, *gdiff, *act, *apos;
+        UQB_TRY(uqb_dalloc_t(ctx, &headpos, n));
+        UQB_TRY(uqb_dalloc_t(ctx, &gdiff, n));
+        UQB_TRY(uqb_dalloc_t(ctx, &act, n));
+        UQB_TRY(uqb_dalloc_t(ctx, &apos, n));
+        for (uint32_t c = 1; c < nchunks; c++) {
+            const uint32_t off = 8 * c;
+            UQB_TRY(uqb_scan_u32(ctx, head, excl, n, d_tot));
+            UQB_LAUNCH(k_headpos, nb, ST, 0, head, excl, n, headpos);
+            UQB_CUDA(cudaMemsetAsync(gdiff, 0, n * 4, ctx->stream));
+            UQB_LAUNCH(k_group_diff, nb, ST, 0, rows, width, off, perm, head, excl, headpos, n, gdiff);
+            UQB_LAUNCH(k_active_flags, nb, ST, 0, head, excl, gdiff, n, act);
+            UQB_TRY(uqb_scan_u32(ctx, act, apos, n, d_tot + 1));
+            uint32_t tot[2];
+            UQB_TRY(uqb_readback(ctx, tot, d_tot, 8));
+            const uint64_t m = tot[1];
+            if (tot[0] == n || m == 0) break;      // every row is its own group, or only identical rows remain tied
+            uqb_sortbuf sb;
+            uint32_t* pos_list;
+            UQB_TRY(uqb_sortbuf_alloc(ctx, &sb, m, true));
+            UQB_TRY(uqb_dalloc_t(ctx, &pos_list, m));
+            UQB_LAUNCH(k_compact_active, nb, ST, 0, rows, width, off, act, apos, head, excl, perm, n, pos_list, sb.key[0], sb.aux[0], sb.val[0]);
+            UQB_TRY(uqb_radix_sort(ctx, &sb, m, true));
+            UQB_LAUNCH(k_write_back, uqb_blocks(m, ST), ST, 0, sb.key[sb.cur], sb.aux[sb.cur], sb.val[sb.cur], pos_list, m, perm, head);
+            UQB_TRY(uqb_dfree(ctx, pos_list, m * 4));
+            UQB_TRY(uqb_sortbuf_free(ctx, &sb));
+        }
+        UQB_TRY(uqb_dfree(ctx, headpos, n * 4));
+        UQB_TRY(uqb_dfree(ctx, gdiff, n * 4));
+        UQB_TRY(uqb_dfree(ctx, act, n * 4));
+        UQB_TRY(uqb_dfree(ctx, apos, n * 4));
+    }
+    // ---- group ids in sorted order ----
+    UQB_TRY(uqb_scan_u32(ctx, head, excl, n, d_tot));
+    UQB_LAUNCH(k_gid_from_scan, nb, ST, 0, head, excl, n);
+    uint32_t u;
+    UQB_TRY(uqb_readback(ctx, &u, d_tot, 4));
+    UQB_TRY(uqb_dfree(ctx, d_tot, 8));
+    UQB_TRY(uqb_dfree(ctx, head, n * 4));
+    *d_perm = perm;
+    *d_gid_sorted = excl;
+    *n_unique = u;
+    return 0;
+}
+
+// ---- public entry points -----------------------------------------------------------------------
+__global__ void __launch_bounds__(ST) k_scatter_key(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ gid, uint64_t n,
+                                                   uint32_t* __restrict__ key) {
+    uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
+    if (p >= n) return;
+    key[perm[p]] = gid[p];
+}
+
+__global__ void __launch_bounds__(ST) k_first_of_group(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ gid, uint64_t n,
+                                                      uint32_t* __restrict__ first_row) {
+    uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
+    if (p >= n) return;
+    if (p == 0 || gid[p] != gid[p - 1]) first_row[gid[p]] = perm[p];
+}
+
+// out[i][:] = table[idx[i]][:]; one warp per row: the index is read once per row, the row bytes are
+// contiguous loads and the output rows are contiguous stores
+__global__ void __launch_bounds__(ST) k_gather_rows(const uint8_t* __restrict__ table, uint32_t width, const uint32_t* __restrict__ idx,
+                                                   uint64_t nrows, uint8_t* __restrict__ out) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t wstride = (uint64_t)gridDim.x * (ST / 32);
+    for (uint64_t i = (uint64_t)blockIdx.x * (ST / 32) + (threadIdx.x >> 5); i < nrows; i += wstride) {
+        const uint8_t* src = table + (uint64_t)__ldg(idx + i) * width;
+        uint8_t* dst = out + i * width;
+        for (uint32_t b = lane; b < width; b += 32) dst[b] = __ldg(src + b);
+    }
+}
+
+extern "C" int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** perm, uqb_array** key,
+                             uqb_array** uniq, uint64_t* n_unique) {
+    uint32_t *d_perm, *d_gid;
+    uint64_t u = 0;
+    const uint64_t n = table->n;
+    UQB_TRY(uqb_sort_rows_impl(ctx, (const uint8_t*)table->d, n, table->width, &d_perm, &d_gid, &u));
+    if (n_unique) *n_unique = u;
+    const unsigned nb = uqb_blocks(n, ST);
+    if (key) {
+        UQB_TRY(uqb_new_array(ctx, n, 4, key));
+        if (n) UQB_LAUNCH(k_scatter_key, nb, ST, 0, d_perm, d_gid, n, (uint32_t*)(*key)->d);
+    }
+    if (uniq) {
+        UQB_TRY(uqb_new_array(ctx, u, table->width, uniq));
+        if (n && table->width) {
+            uint32_t* first_row;
+            UQB_TRY(uqb_dalloc_t(ctx, &first_row, u));
+            UQB_LAUNCH(k_first_of_group, nb, ST, 0, d_perm, d_gid, n, first_row);
+            UQB_LAUNCH(k_gather_rows, uqb_grid(ctx, u, ST / 32, 16), ST, 0, (const uint8_t*)table->d, table->width, first_row, u, (uint8_t*)(*uniq)->d);
+            UQB_TRY(uqb_dfree(ctx, first_row, u * 4));
+        }
+    }
+    if (perm) {
+        UQB_TRY(uqb_new_array(ctx, n, 4, perm));
+        if (n) UQB_CUDA(cudaMemcpyAsync((*perm)->d, d_perm, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    UQB_TRY(uqb_dfree(ctx, d_perm, n * 4));
+    UQB_TRY(uqb_dfree(ctx, d_gid, n * 4));
+    return 0;
+}
+
+extern "C" int uqb_gather_rows(uqb_ctx* ctx, const uqb_array* table, const uqb_array* perm, uqb_array** out) {
+    if (perm->width != 4) return uqb_fail(ctx, "gather_rows: index array must be uint32");
+    UQB_TRY(uqb_new_array(ctx, perm->n, table->width, out));
+    if (perm->n && table->width)
+        UQB_LAUNCH(k_gather_rows, uqb_grid(ctx, perm->n, ST / 32, 16), ST, 0, (const uint8_t*)table->d, table->width, (const uint32_t*)perm->d, perm->n, (uint8_t*)(*out)->d);
+    return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ST) k_narrow(const uint32_t* __restrict__ in, uint64_t n, T* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * ST + threadIdx.x; i < n; i += (uint64_t)gridDim.x * ST) out[i] = (T)in[i];
+}
+
+extern "C" int uqb_narrow_u32(uqb_ctx* ctx, const uqb_array* a, uint32_t itemsize, uqb_array** out) {
+    if (a->width != 4) return uqb_fail(ctx, "narrow: input must be uint32");
+    UQB_TRY(uqb_new_array(ctx, a->n, itemsize, out));
+    if (a->n == 0) return 0;
+    unsigned g = uqb_grid(ctx, a->n, ST, 16);
+    const uint32_t* in = (const uint32_t*)a->d;
+    switch (itemsize) {
+        case 1: UQB_LAUNCH(k_narrow<uint8_t>, g, ST, 0, in, a->n, (uint8_t*)(*out)->d); break;
+        case 2: UQB_LAUNCH(k_narrow<uint16_t>, g, ST, 0, in, a->n, (uint16_t*)(*out)->d); break;
+        case 4: UQB_LAUNCH(k_narrow<uint32_t>, g, ST, 0, in, a->n, (uint32_t*)(*out)->d); break;
+        case 8: UQB_LAUNCH(k_narrow<uint64_t>, g, ST, 0, in, a->n, (uint64_t*)(*out)->d); break;
+        default: return uqb_fail(ctx, "narrow: itemsize %u", itemsize);
+    }
+    return 0;
+}
+
+// ---- QNAME columns <-> big-endian key rows -------------------------------------------------------
+struct col_desc { const uint8_t* p[UQB_MAX_COLS]; uint32_t size[UQB_MAX_COLS]; uint32_t off[UQB_MAX_COLS]; uint32_t ncols; uint32_t width; };
+struct col_desc_out { uint8_t* p[UQB_MAX_COLS]; uint32_t size[UQB_MAX_COLS]; uint32_t off[UQB_MAX_COLS]; uint32_t ncols; uint32_t width; };
+
+__global__ void __launch_bounds__(ST) k_cols_to_rows(col_desc cd, uint64_t n, uint8_t* __restrict__ rows) {
+    for (uint64_t t = (uint64_t)blockIdx.x * ST + threadIdx.x; t < n * cd.ncols; t += (uint64_t)gridDim.x * ST) {
+        uint64_t r = t / cd.ncols;
+        uint32_t c = (uint32_t)(t - r * cd.ncols);
+        uint32_t sz = cd.size[c];
+        const uint8_t* src = cd.p[c] + r * sz;
+        uint8_t* dst = rows + r * cd.width + cd.off[c];
+        for (uint32_t b = 0; b < sz; b++) dst[b] = src[sz - 1 - b];      // little-endian value -> big-endian key bytes
+    }
+}
+
+__global__ void __launch_bounds__(ST) k_rows_to_cols(col_desc_out cd, uint64_t n, const uint8_t* __restrict__ rows) {
+    for (uint64_t t = (uint64_t)blockIdx.x * ST + threadIdx.x; t < n * cd.ncols; t += (uint64_t)gridDim.x * ST) {
+        uint64_t r = t / cd.ncols;
+        uint32_t c = (uint32_t)(t - r * cd.ncols);
+        uint32_t sz = cd.size[c];
+        uint8_t* dst = cd.p[c] + r * sz;
+        const uint8_t* src = rows + r * cd.width + cd.off[c];
+        for (uint32_t b = 0; b < sz; b++) dst[b] = src[sz - 1 - b];
+    }
+}
+
+extern "C" int uqb_columns_to_rows(uqb_ctx* ctx, uint32_t ncols, uqb_array* const* cols, uqb_array** rows) {
+    if (ncols == 0 || ncols > UQB_MAX_COLS) return uqb_fail(ctx, "columns_to_rows: bad column count %u", ncols);
+    col_desc cd;
+    cd.ncols = ncols;
+    uint32_t w = 0;
+    uint64_t n = cols[0]->n;
+    for (uint32_t c = 0; c < ncols; c++) {
+        if (cols[c]->n != n) return uqb_fail(ctx, "columns_to_rows: ragged columns");
+        cd.p[c] = (const uint8_t*)cols[c]->d; cd.size[c] = cols[c]->width; cd.off[c] = w; w += cols[c]->width;
+    }
+    cd.width = w;
+    UQB_TRY(uqb_new_array(ctx, n, w, rows));
+    if (n) UQB_LAUNCH(k_cols_to_rows, uqb_grid(ctx, n * ncols, ST, 16), ST, 0, cd, n, (uint8_t*)(*rows)->d);
+    return 0;
+}
+
+extern "C" int uqb_rows_to_columns(uqb_ctx* ctx, const uqb_array* rows, uint32_t ncols, const uint32_t* itemsizes, uqb_array** cols) {
+    if (ncols == 0 || ncols > UQB_MAX_COLS) return uqb_fail(ctx, "rows_to_columns: bad column count %u", ncols);
+    col_desc_out cd;
+    cd.ncols = ncols;
+    uint32_t w = 0;
+    for (uint32_t c = 0; c < ncols; c++) {
+        UQB_TRY(uqb_new_array(ctx, rows->n, itemsizes[c], &cols[c]));
+        cd.p[c] = (uint8_t*)cols[c]->d; cd.size[c] = itemsizes[c]; cd.off[c] = w; w += itemsizes[c];
+    }
+    cd.width = w;
+    if (w != rows->width) return uqb_fail(ctx, "rows_to_columns: widths sum to %u, rows are %u wide", w, rows->width);
+    if (rows->n) UQB_LAUNCH(k_rows_to_cols, uqb_grid(ctx, rows->n * ncols, ST, 16), ST, 0, cd, rows->n, (const uint8_t*)rows->d);
+    return 0;
+}

@@ -1,0 +1,306 @@
+"""Thin object wrappers over the C ABI (include/uqb200.h).  No computation happens here: every method
+is one call into libuqb200.so; numpy is used only as host memory."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+PATTERN_ID = {'0.1': 0, '1.1': 1, '2.1': 2, '3.1': 3, '0.2': 4, '1.2': 5, '2.2': 6, '3.2': 7}
+
+
+class DeviceError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One per host thread.  `stream` may be a raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = L.load()
+        self.h = C.c_void_p()
+        rc = self.lib.uqb_ctx_create(int(device), C.c_void_p(stream or 0), C.byref(self.h))
+        if rc:
+            msg = self.lib.uqb_last_error(self.h).decode() if self.h else "context allocation failed"
+            if self.h:
+                self.lib.uqb_ctx_destroy(self.h)
+                self.h = C.c_void_p()
+            raise DeviceError("uq_b200: cannot create a CUDA context on device %d: %s" % (device, msg))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.uqb_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc:
+            raise DeviceError(self.lib.uqb_last_error(self.h).decode())
+
+    def sync(self):
+        self.check(self.lib.uqb_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.uqb_ctx_launch_count(self.h))
+
+    def timing(self, enable):
+        self.check(self.lib.uqb_ctx_timing(self.h, 1 if enable else 0))
+
+    def timing_reset(self):
+        self.check(self.lib.uqb_ctx_timing_reset(self.h))
+
+    def timing_report(self):
+        cap = 256
+        names = C.create_string_buffer(cap * L.TIMER_NAME)
+        cnt = (C.c_uint64 * cap)()
+        ms = (C.c_double * cap)()
+        n = C.c_int()
+        self.check(self.lib.uqb_ctx_timing_report(self.h, names, cnt, ms, cap, C.byref(n)))
+        out = {}
+        for i in range(n.value):
+            nm = names.raw[i * L.TIMER_NAME:(i + 1) * L.TIMER_NAME].split(b"\0")[0].decode()
+            out[nm] = (int(cnt[i]), float(ms[i]))
+        return out
+
+    def mem_info(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.check(self.lib.uqb_mem_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    # ---- pinned host memory ----
+    def pinned_empty(self, nbytes):
+        p = C.c_void_p()
+        self.check(self.lib.uqb_host_alloc(self.h, int(nbytes), C.byref(p)))
+        buf = (C.c_uint8 * max(int(nbytes), 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8, count=int(nbytes))
+        return PinnedBuffer(self, p, arr)
+
+    # ---- arrays ----
+    def upload(self, arr, width=None):
+        arr = np.ascontiguousarray(arr)
+        if width is None:
+            width = arr.dtype.itemsize if arr.ndim == 1 else arr.shape[1] * arr.dtype.itemsize
+        n = arr.nbytes // width if width else arr.shape[0]
+        h = C.c_void_p()
+        self.check(self.lib.uqb_array_upload(self.h, _ptr(arr), int(n), int(width), C.byref(h)))
+        return DeviceArray(self, h)
+
+    def load_fastq(self, data):
+        """H2D copy of FASTQ bytes (bytes / bytearray / uint8 ndarray / PinnedBuffer)."""
+        if isinstance(data, PinnedBuffer):
+            arr = data.array
+        elif isinstance(data, np.ndarray):
+            arr = np.ascontiguousarray(data, dtype=np.uint8)
+        else:
+            arr = np.frombuffer(data, dtype=np.uint8)
+        h = C.c_void_p()
+        self.check(self.lib.uqb_fastq_load(self.h, _ptr(arr) if arr.size else None, int(arr.size), C.byref(h)))
+        return Fastq(self, h, int(arr.size))
+
+    def adopt_fastq(self, device_array):
+        """Wrap FASTQ bytes that already live in HBM (no copy); the array must outlive the Fastq."""
+        h = C.c_void_p()
+        self.check(self.lib.uqb_fastq_adopt(self.h, device_array.device_ptr, int(device_array.nbytes), C.byref(h)))
+        fq = Fastq(self, h, int(device_array.nbytes))
+        fq._keep = device_array
+        return fq
+
+    def synth(self, kind, n, length, seed, first=0, genome=0, pool=0, len_table=None):
+        kinds = {"illumina": 0, "genome": 1, "casava": 2, "ont": 3}
+        p = L.SynthParams()
+        p.kind = kinds[kind]
+        if kind == "ont":
+            p.len_lo, p.len_hi = int(length[0]), int(length[1])
+            tab = np.ascontiguousarray(len_table, dtype=np.int64)
+            assert tab.size == 4096
+            tp = _ptr(tab)
+        else:
+            p.length = int(length)
+            tp = None
+        p.seed, p.first, p.n, p.genome, p.pool = int(seed), int(first), int(n), int(genome), int(pool)
+        h = C.c_void_p()
+        self.check(self.lib.uqb_synth(self.h, C.byref(p), tp, C.byref(h)))
+        return DeviceArray(self, h)
+
+    # ---- stage 3 / 4 ----
+    def sort_rows(self, table, want_perm=False, want_key=False, want_uniq=False):
+        perm, key, uniq = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nu = C.c_uint64()
+        self.check(self.lib.uqb_sort_rows(self.h, table.h, C.byref(perm) if want_perm else None,
+                                          C.byref(key) if want_key else None, C.byref(uniq) if want_uniq else None, C.byref(nu)))
+        return (DeviceArray(self, perm) if want_perm else None, DeviceArray(self, key) if want_key else None,
+                DeviceArray(self, uniq) if want_uniq else None, int(nu.value))
+
+    def gather_rows(self, table, perm):
+        h = C.c_void_p()
+        self.check(self.lib.uqb_gather_rows(self.h, table.h, perm.h, C.byref(h)))
+        return DeviceArray(self, h)
+
+    def narrow_u32(self, a, itemsize):
+        h = C.c_void_p()
+        self.check(self.lib.uqb_narrow_u32(self.h, a.h, int(itemsize), C.byref(h)))
+        return DeviceArray(self, h)
+
+    def columns_to_rows(self, cols):
+        arr = (C.c_void_p * len(cols))(*[c.h for c in cols])
+        h = C.c_void_p()
+        self.check(self.lib.uqb_columns_to_rows(self.h, len(cols), arr, C.byref(h)))
+        return DeviceArray(self, h)
+
+    def rows_to_columns(self, rows, itemsizes):
+        n = len(itemsizes)
+        sizes = (C.c_uint32 * n)(*[int(s) for s in itemsizes])
+        outs = (C.c_void_p * n)()
+        self.check(self.lib.uqb_rows_to_columns(self.h, rows.h, n, sizes, outs))
+        return [DeviceArray(self, C.c_void_p(outs[i])) for i in range(n)]
+
+    def layout(self, table, pattern):
+        h = C.c_void_p()
+        self.check(self.lib.uqb_layout(self.h, table.h, PATTERN_ID[pattern], C.byref(h)))
+        return DeviceArray(self, h)
+
+    def unlayout(self, stream, n, width, pattern):
+        h = C.c_void_p()
+        self.check(self.lib.uqb_unlayout(self.h, stream.h, int(n), int(width), PATTERN_ID[pattern], C.byref(h)))
+        return DeviceArray(self, h)
+
+
+class PinnedBuffer:
+    def __init__(self, ctx, ptr, array):
+        self.ctx, self.ptr, self.array = ctx, ptr, array
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.ctx.check(self.ctx.lib.uqb_host_free(self.ctx.h, self.ptr))
+            self.ptr = None
+
+
+class DeviceArray:
+    """n rows x width bytes in HBM."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+        n, w = C.c_uint64(), C.c_uint32()
+        ctx.lib.uqb_array_info(handle, C.byref(n), C.byref(w))
+        self.n, self.width = int(n.value), int(w.value)
+
+    @property
+    def nbytes(self):
+        return self.n * self.width
+
+    @property
+    def device_ptr(self):
+        return C.c_void_p(self.ctx.lib.uqb_array_device_ptr(self.h))
+
+    def download(self, dtype=np.uint8, out=None):
+        """-> ndarray: 1-D of `dtype` when itemsize == width, else uint8 [n][width]."""
+        dtype = np.dtype(dtype)
+        if out is None:
+            out = np.empty(self.nbytes, dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.uqb_array_download(self.ctx.h, self.h, _ptr(out), self.nbytes))
+        if dtype.itemsize == self.width and dtype != np.uint8:
+            return out[:self.nbytes].view(dtype)
+        if dtype == np.uint8 and self.width == 1:
+            return out[:self.nbytes]
+        return out[:self.nbytes].reshape(self.n, self.width)
+
+    def free(self):
+        if self.h:
+            self.ctx.check(self.ctx.lib.uqb_array_free(self.ctx.h, self.h))
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+
+class Fastq:
+    """Device-resident FASTQ bytes plus everything later stages cache on it (line offsets, QNAME scan)."""
+
+    def __init__(self, ctx, handle, nbytes):
+        self.ctx, self.h, self.nbytes = ctx, handle, nbytes
+        self.n_reads = None
+        self._keep = None
+
+    def free(self):
+        if self.h:
+            self.ctx.check(self.ctx.lib.uqb_fastq_free(self.ctx.h, self.h))
+            self.h = C.c_void_p()
+            self._keep = None
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+    def download(self, offset=0, nbytes=None):
+        nbytes = self.nbytes - offset if nbytes is None else nbytes
+        out = np.empty(nbytes, dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.uqb_fastq_download(self.ctx.h, self.h, int(offset), _ptr(out), int(nbytes)))
+        return out
+
+    def split(self):
+        info = L.SplitInfo()
+        self.ctx.check(self.ctx.lib.uqb_split(self.ctx.h, self.h, C.byref(info)))
+        self.n_reads = int(info.n_reads)
+        self.n_lines = int(info.n_lines)
+        return info
+
+    def line_offsets(self, first=0, count=None):
+        count = self.n_lines + 1 - first if count is None else count
+        out = np.empty(count, dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.uqb_fastq_line_offsets(self.ctx.h, self.h, int(first), int(count), _ptr(out)))
+        return out
+
+    def analyze(self):
+        st = L.Stats()
+        self.ctx.check(self.ctx.lib.uqb_analyze(self.ctx.h, self.h, C.byref(st)))
+        return st
+
+    def qname_scan(self, prefix_len, suffix_len, separators):
+        seps = np.frombuffer(separators.encode('latin-1'), dtype=np.uint8)
+        ncols = len(seps) + 1
+        cols = (L.ColStats * ncols)()
+        bad = C.c_int64()
+        self.ctx.check(self.ctx.lib.uqb_qname_scan(self.ctx.h, self.h, int(prefix_len), int(suffix_len),
+                                                   _ptr(seps) if len(seps) else None, len(seps), cols, C.byref(bad)))
+        return cols, int(bad.value)
+
+    def qname_dict(self, col):
+        cnt, w = C.c_uint64(), C.c_uint32()
+        self.ctx.check(self.ctx.lib.uqb_qname_dict_info(self.ctx.h, self.h, int(col), C.byref(cnt), C.byref(w)))
+        buf = np.zeros(max(cnt.value * w.value, 1), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.uqb_qname_dict(self.ctx.h, self.h, int(col), _ptr(buf), cnt.value * w.value))
+        rows = buf[:cnt.value * w.value].reshape(cnt.value, w.value) if w.value else np.zeros((cnt.value, 0), np.uint8)
+        return [bytes(r).rstrip(b"\0").decode('latin-1') for r in rows]
+
+    def qname_encode(self, specs):
+        n = len(specs)
+        arr = (L.ColSpec * n)()
+        for i, (fmt, itemsize, offset, mn) in enumerate(specs):
+            arr[i].format, arr[i].itemsize, arr[i].offset, arr[i].min_val = fmt, itemsize, 1 if offset else 0, int(mn)
+        outs = (C.c_void_p * n)()
+        self.ctx.check(self.ctx.lib.uqb_qname_encode(self.ctx.h, self.h, n, arr, outs))
+        return [DeviceArray(self.ctx, C.c_void_p(outs[i])) for i in range(n)]
+
+    def pack(self, params):
+        d, q = C.c_void_p(), C.c_void_p()
+        self.ctx.check(self.ctx.lib.uqb_pack(self.ctx.h, self.h, C.byref(params), C.byref(d), C.byref(q)))
+        return DeviceArray(self.ctx, d), DeviceArray(self.ctx, q)

@@ -1,0 +1,548 @@
+"""Host side of the B200 uQ path: the reference's decision logic re-typed in Python 3 on top of the
+statistics the device returns, and the orchestration of the device stages.
+
+Nothing here touches per-read data on the CPU: the FASTQ bytes go to HBM once, every O(N) step is a
+call into libuqb200.so (uq_b200/device.py), and what comes back is either O(alphabet) statistics or
+the finished output arrays.  There is no CPU fallback and nothing is imported from oracle/.
+
+Reference regions mirrored here (JohnLonginotto/uq, uq.py):
+  option validation ............... uq.py:52-69, 893-894          normalise_options
+  prefix / suffix / separators .... uq.py:395-413, 427-444        derive_qname_layout
+  alphabets, N-trick, bit widths .. uq.py:448-457, 476-545        decide_alphabets
+  Pass-2 column typing ............ uq.py:586-602, 641-676        decide_columns
+  run_mix / encode_* .............. uq.py:739-851                 run_mix
+  config / container .............. uq.py:681-696, 898-912        encode(), container.py
+  decoder ......................... uq.py:939-1058                decode()
+"""
+import re
+
+import numpy as np
+
+from . import _lib as L
+from .device import Context, DeviceArray, PATTERN_ID
+
+PATTERNS = ['0.1', '1.1', '2.1', '3.1', '0.2', '1.2', '2.2', '3.2']
+_DT = [(255, 'uint8', 1), (65535, 'uint16', 2), (4294967295, 'uint32', 4), (18446744073709551615, 'uint64', 8)]
+
+
+class UQError(Exception):
+    """Where the reference prints a message and exit()s (uq.py:48-50) this path raises."""
+
+
+# ------------------------------------------------------------------------------------------------
+# options (uq.py:52-69, 893-894)
+# ------------------------------------------------------------------------------------------------
+def normalise_options(sort=None, raw=None, pattern=None):
+    if pattern is not None:
+        if len(pattern) != 2: raise UQError('ERROR: There must be 2 values for --pattern!')
+        if not all(p in PATTERNS for p in pattern): raise UQError('ERROR: Pattern values are incorrect!')
+    if sort is not None and not isinstance(sort, tuple):
+        if sort.lower() not in ('dna', 'qual', 'qname', 'none'): raise UQError('ERROR: --sort value is incorrect!')
+        if sort.lower() == 'none': sort = (None,)
+    if raw is not None:
+        if not all((x is None) or x.lower() in ('dna', 'qual', 'qname', 'none') for x in raw):
+            raise UQError('ERROR: --raw values are incorrect!')
+        raw = set(raw)
+        if 'none' in raw:
+            raw.add(None); raw.discard('none')
+    if sort is None: sort = (None,)
+    if raw is None: raw = (None,)
+    if pattern is None: pattern = ['0.1', '0.1']
+    return sort, raw, list(pattern)
+
+
+# ------------------------------------------------------------------------------------------------
+# Pass-1 decisions
+# ------------------------------------------------------------------------------------------------
+def _none(v):
+    return v == L.NONE_I64
+
+
+def derive_qname_layout(st, n_reads):
+    """prefix, suffix, ordered separators from the device statistics.
+
+    The reference's loop (uq.py:395-413) is order dependent: a character becomes a separator
+    candidate when the running common prefix first shrinks past its last occurrence in line 1, and
+    from that record on every QNAME must hold as many of it as line 1.  With
+        E[j]  = first record whose common prefix with line 1 is <= j      (from first_lcp_eq)
+        M[c]  = last record whose count of c differs from line 1's        (last_count_mismatch)
+    candidate c (exposed at record E[last position of c in line 1]) survives iff M[c] < E[..]."""
+    first = bytes(st.first_name[:st.first_len]).decode('latin-1')
+    last = bytes(st.last_name[:st.last_len]).decode('latin-1')
+    flen = len(first)
+    lcp_first = [st.first_lcp_eq[j] for j in range(flen + 1)]
+    lcs_first = [st.first_lcs_eq[j] for j in range(flen + 1)]
+
+    def running_first(arr):
+        out, best = [], L.NONE_I64
+        for v in arr:
+            best = min(best, v)
+            out.append(best)
+        return out
+    E = running_first(lcp_first)
+    Es = running_first(lcs_first)
+    # Q8: a QNAME that is a proper prefix (suffix) of the running prefix (suffix) raises IndexError
+    # in the reference (uq.py:397, 405)
+    for j in range(flen):
+        k = st.first_short_prefix[j]
+        if not _none(k) and E[j] == k:
+            raise UQError('ERROR: QNAME of record %d is a proper prefix of the common QNAME prefix (the reference raises IndexError here, Q8)' % k)
+        k = st.first_short_suffix[j]
+        if not _none(k) and Es[j] == k:
+            raise UQError('ERROR: QNAME of record %d is a proper suffix of the common QNAME suffix (the reference raises IndexError here, Q8)' % k)
+
+    plen, slen = int(st.prefix_len), int(st.suffix_len)
+    prefix = first[:plen]
+    suffix = first[flen - slen:] if slen else ''
+    # candidates in the reference's insertion order: by shrink event (in time order), then by position
+    events = []                                    # (new, old): the running prefix shrinks from old to new
+    low = sorted((lcp_first[j], j) for j in range(flen) if not _none(lcp_first[j]))    # by record index
+    cur = flen
+    for _, j in low:
+        if j < cur:
+            events.append((j, cur))                # exposes first[j:cur]
+            cur = j
+    sep_count = {}
+    for new, old in events:
+        for ch in first[new:old]:
+            if ch not in sep_count:
+                sep_count[ch] = None
+    for ch in list(sep_count):
+        k_c = E[first.rindex(ch)]
+        if st.last_count_mismatch[ord(ch)] >= k_c:
+            del sep_count[ch]                      # uq.py:410-413
+        else:
+            sep_count[ch] = first[plen:].count(ch)
+    for ch in list(sep_count):                     # uq.py:428-431
+        k = suffix.count(ch)
+        if k:
+            sep_count[ch] -= k
+            if sep_count[ch] == 0:
+                del sep_count[ch]
+    if len(sep_count) == 0:
+        raise UQError('ERROR: no QNAME separators (the reference crashes on such files, Q6)')
+
+    def order_seps(name):                          # uq.py:433-436
+        return ''.join(re.findall('([' + ''.join(sep_count) + ']+)', name[len(prefix):-1 - len(suffix)]))
+    try:
+        a, b = order_seps(last), order_seps(first)
+    except re.error as e:
+        raise UQError('ERROR: QNAME separators %r break the reference regex (Q11): %s' % (''.join(sep_count), e))
+    if a != b:                                     # uq.py:438-444
+        raise UQError("ERROR: Sorry, the separators used in this file's QNAME/headers are so unusual/improbable that "
+                      "I didn't think it was worth the time to write the code on how to deal with it, only identify it.")
+    return prefix, suffix, a
+
+
+def bits_for(n, pad):
+    """uq.py:497-503 / uq.py:534-540."""
+    if n <= 4: return 2
+    if n <= 8 and not pad: return 3
+    if n <= 16: return 4
+    if n <= 32 and not pad: return 5
+    if n <= 64 and not pad: return 6
+    if n <= 128 and not pad: return 7
+    return 8
+
+
+def decide_alphabets(st, notricks=False, pad=False):
+    base_graph = {chr(i): int(st.base_count[i]) for i in range(256) if st.base_count[i]}
+    qual_graph = {chr(i): int(st.qual_count[i]) for i in range(256) if st.qual_count[i]}
+    bases = sorted(base_graph)                     # uq.py:456-457
+    quals = sorted(qual_graph)
+    n_qual = {}
+    total_quals = len(quals)
+    if not notricks:                               # uq.py:479-494
+        for base in sorted(base_graph):            # py2 dict order in the reference; only matters for >=2 tricked bases (Q10)
+            if len(bases) == 1:
+                continue
+            single = st.base_single_qual[ord(base)]
+            if 0 <= single <= 255:
+                bases.remove(base)
+                q = chr(single)
+                if base_graph[base] == qual_graph[q]:
+                    n_qual[base] = quals.index(q)
+                else:
+                    total_quals += 1
+                    n_qual[base] = total_quals     # Q3
+    bpb = bits_for(len(bases), pad)
+    dna_max = int(st.dna_max)
+    variable = int(st.dna_min) != dna_max
+    bpq = bits_for(total_quals, pad)
+    return dict(bases=''.join(bases), qualities=''.join(quals), N_qual=n_qual, bits_per_base=bpb,
+                bits_per_quality=bpq, variable_read_lengths=variable, dna_max=dna_max,
+                dna_bytes=-(-(bpb * (dna_max + variable)) // 8), qual_bytes=-(-(bpq * (dna_max + variable)) // 8),
+                base_distribution=base_graph, qual_distribution=qual_graph)
+
+
+def pack_params(dec):
+    p = L.PackParams()
+    for i, ch in enumerate(dec['bases']):
+        p.base_code[ord(ch)] = i
+    for i, ch in enumerate(dec['qualities']):
+        p.qual_code[ord(ch)] = i
+    for i in range(256):
+        p.trick_qual[i] = -1
+    for base, code in dec['N_qual'].items():
+        if code >> dec['bits_per_quality']:
+            raise UQError('ERROR: the N-trick quality code %d does not fit %d bits; the reference corrupts its output here (Q4)'
+                          % (code, dec['bits_per_quality']))
+        p.trick_qual[ord(base)] = code
+    p.bits_per_base, p.bits_per_quality = dec['bits_per_base'], dec['bits_per_quality']
+    p.dna_bytes, p.qual_bytes = dec['dna_bytes'], dec['qual_bytes']
+    p.variable, p.dna_max = int(dec['variable_read_lengths']), dec['dna_max']
+    return p
+
+
+# ------------------------------------------------------------------------------------------------
+# Pass-2 decisions (uq.py:586-602, 641-676)
+# ------------------------------------------------------------------------------------------------
+def decide_columns(colstats, n_reads, fetch_dict):
+    columns = []
+    last = n_reads - 1
+    for i, cs in enumerate(colstats):
+        col = {'name': 'QNAME_%d' % (i + 1)}
+        if cs.overflow:
+            raise UQError('ERROR: QNAME column %d holds an integer outside the int64 range' % (i + 1))
+        demoted = False
+        t = 10000
+        for k in range(cs.n_checkpoints):          # uq.py:634-636
+            if cs.distinct_at[k] > t // 10:
+                demoted = True
+                break
+            t *= 2
+        if not demoted and cs.n_distinct > last // 10:       # uq.py:638
+            demoted = True
+        if demoted:
+            if not cs.all_int:                     # 'strings' (uq.py:598-601, 624-630) -> uq.py:672-673
+                raise UQError('I havent implimented this yet')
+            col['format'] = 'integers'
+            col['min'], col['max'] = int(cs.min_val), int(cs.max_val)
+            span = col['max'] - col['min']
+            cap, col['dtype'], _ = next(d for d in _DT if span <= d[0])
+            col['offset'] = bool(col['min'] < 0 or col['max'] > cap)
+        else:
+            n = int(cs.n_distinct)
+            cap, col['dtype'], _ = next(d for d in _DT if n <= d[0])
+            if cs.all_int and int(cs.max_val) - int(cs.min_val) <= cap:     # uq.py:649-658
+                col['format'] = 'integers'
+                col['max'], col['min'] = int(cs.max_val), int(cs.min_val)
+                col['offset'] = bool(col['min'] < 0 or col['max'] > cap)
+            else:
+                col['format'] = 'mapping'
+                col['map'] = fetch_dict(i)         # sorted distinct tokens (uq.py:659-661)
+        if col['format'] == 'integers' and not col['offset'] and col['min'] < 0:
+            raise UQError('ERROR: negative integers in QNAME column %d' % (i + 1))
+        columns.append(col)
+    return columns
+
+
+def column_specs(columns):
+    out = []
+    for c in columns:
+        size = np.dtype(c['dtype']).itemsize
+        if c['format'] == 'mapping':
+            out.append((0, size, False, 0))
+        else:
+            out.append((1, size, c['offset'], c['min'] if c['offset'] else 0))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# run_mix on the device (uq.py:739-851)
+# ------------------------------------------------------------------------------------------------
+def key_itemsize(n_unique):
+    """numpy.min_scalar_type(max(key)) with max(key) = n_unique - 1 (uq.py:790, 832)."""
+    m = max(n_unique - 1, 0)
+    return next(d[2] for d in _DT if m <= d[0])
+
+
+class DeviceMembers:
+    """Output members kept in HBM: name -> (DeviceArray, kind, meta).  download() turns them into the
+    exact ndarray objects the reference hands to numpy.save."""
+
+    def __init__(self):
+        self.items = {}
+
+    def add_table(self, name, stream, n, width, pattern):
+        self.items[name] = (stream, 'table', (n, width, pattern))
+
+    def add_vector(self, name, arr, dtype):
+        self.items[name] = (arr, 'vector', np.dtype(dtype))
+
+    def nbytes(self):
+        return sum(a.nbytes for a, _, _ in self.items.values())
+
+    def download(self, into=None):
+        out = {}
+        for name, (arr, kind, meta) in self.items.items():
+            buf = None if into is None else into(name, arr.nbytes)
+            if kind == 'vector':
+                out[name] = arr.download(dtype=meta, out=buf).reshape(-1)
+                if meta == np.uint8:
+                    out[name] = out[name].reshape(-1)
+            else:
+                n, width, pattern = meta
+                flat = arr.download(dtype=np.uint8, out=buf).reshape(-1)
+                shape = (n, width) if pattern[0] in '02' else (width, n)
+                out[name] = np.ndarray(shape, dtype=np.uint8, buffer=flat, order='C' if pattern[2] == '1' else 'F')
+        return out
+
+    def free(self):
+        for a, _, _ in self.items.values():
+            a.free()
+        self.items = {}
+
+
+def _mix_dna_qual(ctx, out, table, name, order, raw, pattern):
+    """encode_dna_qual (uq.py:765-805).  order: None / False / DeviceArray(uint32 perm)."""
+    if raw:
+        src = table
+        if order is not None:
+            if order is False:
+                order, _, _, _ = ctx.sort_rows(table, want_perm=True)              # uq.py:775
+            src = ctx.gather_rows(table, order)                                    # uq.py:777
+        out.add_table(name + '.raw', ctx.layout(src, pattern), table.n, table.width, pattern)
+        if src is not table:
+            src.free()
+    else:
+        perm, key, uniq, nu = ctx.sort_rows(table, want_perm=(order is False), want_key=True, want_uniq=True)   # uq.py:786
+        size = key_itemsize(nu)
+        if order is not None:
+            if order is False:
+                order = perm                                                       # argsort(key), uq.py:796
+            k2 = ctx.gather_rows(key, order)
+            key.free()
+            key = k2
+        narrow = ctx.narrow_u32(key, size)                                         # uq.py:790
+        key.free()
+        out.add_vector(name + '.key', narrow, 'uint%d' % (8 * size))
+        out.add_table(name, ctx.layout(uniq, pattern), uniq.n, uniq.width, pattern)
+        uniq.free()
+    return order
+
+
+def _mix_qname(ctx, out, cols, columns, order, raw):
+    """encode_qname (uq.py:808-851)."""
+    if raw:
+        if order is False:
+            rows = ctx.columns_to_rows(cols)
+            order, _, _, _ = ctx.sort_rows(rows, want_perm=True)                   # uq.py:816
+            rows.free()
+        for c, meta in zip(cols, columns):
+            if order is not None:
+                out.add_vector(meta['name'] + '.raw', ctx.gather_rows(c, order), meta['dtype'])
+            else:
+                out.add_vector(meta['name'] + '.raw', c, meta['dtype'])
+    else:
+        rows = ctx.columns_to_rows(cols)
+        perm, key, uniq, nu = ctx.sort_rows(rows, want_perm=(order is False), want_key=True, want_uniq=True)    # uq.py:830
+        rows.free()
+        size = key_itemsize(nu)
+        if order is False:
+            order = perm                                                           # uq.py:833
+        if order is not None:
+            k2 = ctx.gather_rows(key, order)
+            key.free()
+            key = k2
+        narrow = ctx.narrow_u32(key, size)
+        key.free()
+        out.add_vector('QNAME.key', narrow, 'uint%d' % (8 * size))
+        ucols = ctx.rows_to_columns(uniq, [np.dtype(m['dtype']).itemsize for m in columns])   # uq.py:842-847
+        uniq.free()
+        for c, meta in zip(ucols, columns):
+            out.add_vector(meta['name'], c, meta['dtype'])
+    return order
+
+
+def run_mix(ctx, dna, qual, cols, columns, sorted_on, raw_tables, pattern):
+    out = DeviceMembers()
+    pd, pq = pattern
+    if sorted_on in ('DNA', 'QUAL'):
+        first = (dna, 'DNA', pd) if sorted_on == 'DNA' else (qual, 'QUAL', pq)
+        second = (qual, 'QUAL', pq) if sorted_on == 'DNA' else (dna, 'DNA', pd)
+        order = _mix_dna_qual(ctx, out, first[0], first[1], False, first[1] in raw_tables, first[2])
+        _mix_dna_qual(ctx, out, second[0], second[1], order, second[1] in raw_tables, second[2])
+        _mix_qname(ctx, out, cols, columns, order, 'QNAME' in raw_tables)
+    elif sorted_on == 'QNAME':
+        order = _mix_qname(ctx, out, cols, columns, False, 'QNAME' in raw_tables)
+        _mix_dna_qual(ctx, out, dna, 'DNA', order, 'DNA' in raw_tables, pd)
+        _mix_dna_qual(ctx, out, qual, 'QUAL', order, 'QUAL' in raw_tables, pq)
+    else:
+        _mix_qname(ctx, out, cols, columns, None, 'QNAME' in raw_tables)
+        _mix_dna_qual(ctx, out, dna, 'DNA', None, 'DNA' in raw_tables, pd)
+        _mix_dna_qual(ctx, out, qual, 'QUAL', None, 'QUAL' in raw_tables, pq)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# encode
+# ------------------------------------------------------------------------------------------------
+def encode_device(ctx, fq, sort=None, raw=None, pattern=None, pad=False, notricks=False, stages=None):
+    """FASTQ already in HBM (device.Fastq) -> (DeviceMembers, config).  All O(N) work is on the GPU."""
+    sort, raw, pattern = normalise_options(sort, raw, pattern)
+    info = fq.split()
+    if info.status == 1:                                                           # uq.py:86-87
+        raise UQError('ERROR: The FASTQ file provided contains' + str(info.n_lines) + 'rows, which is not divisible by 4!')
+    n = int(info.n_reads)
+    if n == 0:
+        raise UQError('ERROR: the FASTQ file holds no records')
+    st = fq.analyze()
+    if st.bad_first_char != -1:                                                    # uq.py:346
+        raise UQError('ERROR: This does not look like a FASTA/FASTQ file! (first line does not start with @)')
+    bad = [(r, w) for r, w in ((st.bad_plus_record, 'plus'), (st.bad_len_record, 'len')) if r >= 0]
+    if bad:
+        r, w = min(bad, key=lambda t: (t[0], t[1] != 'plus'))
+        if w == 'plus':                                                            # uq.py:360, 382
+            raise UQError('ERROR: For entry %d the third line does not start with +' % r)
+        raise UQError('ERROR: Length of DNA does not match the length of the quality scores for entry %d' % (r + 1))   # uq.py:366, 388
+    prefix, suffix, separators = derive_qname_layout(st, n)
+    dec = decide_alphabets(st, notricks=notricks, pad=pad)
+    colstats, bad_rec = fq.qname_scan(len(prefix), len(suffix), separators)
+    if bad_rec >= 0:                                                               # uq.py:609-613, 637
+        raise UQError('Encoding QNAMEs as strings has not been implimented yet. (record %d does not split into %d columns)'
+                      % (bad_rec, len(separators) + 1))
+    columns = decide_columns(colstats, n, fq.qname_dict)
+    dna, qual = fq.pack(pack_params(dec))
+    cols = fq.qname_encode(column_specs(columns))
+    if stages is not None:
+        stages.update(stats=st, dec=dec, columns=columns, dna=dna, qual=qual, cols=cols, prefix=prefix, suffix=suffix,
+                      separators=separators, total=n)
+    members = run_mix(ctx, dna, qual, cols, columns, sort, raw, pattern)
+    if stages is None:
+        keep = {id(a) for a, _, _ in members.items.values()}
+        for a in [dna, qual] + cols:
+            if id(a) not in keep:
+                a.free()
+    config = {
+        'base_distribution': dec['base_distribution'], 'qual_distribution': dec['qual_distribution'],
+        'reads': n, 'bases': dec['bases'], 'qualities': dec['qualities'],
+        'variable_read_lengths': dec['variable_read_lengths'], 'bits_per_base': dec['bits_per_base'],
+        'bits_per_quality': dec['bits_per_quality'], 'N_qual': dec['N_qual'], 'dna_max': dec['dna_max'],
+        'QNAME_prefix': prefix, 'QNAME_suffix': suffix, 'QNAME_separators': separators,
+        'QNAME_columns': columns, 'sort': sort, 'raw': list(raw), 'pattern': pattern,
+    }
+    return members, config
+
+
+def encode(fastq, sort=None, raw=None, pattern=None, pad=False, notricks=False, ctx=None, stages=None):
+    """FASTQ bytes on the host -> (members: name -> ndarray as handed to numpy.save, config)."""
+    own = ctx is None
+    ctx = ctx or Context()
+    fq = ctx.load_fastq(fastq)
+    try:
+        members, config = encode_device(ctx, fq, sort, raw, pattern, pad, notricks, stages)
+        host = members.download()
+        if stages is None:
+            members.free()
+        else:
+            stages['device_members'] = members
+        return host, config
+    finally:
+        fq.free()
+        if own and stages is None:
+            ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# decode (uq.py:939-1058)
+# ------------------------------------------------------------------------------------------------
+def _upload_table(ctx, members, name, pattern):
+    """DNA / QUAL member(s) -> logical DeviceArray [n][width] (load_from_tar + key expansion)."""
+    def logical(arr):
+        n, width = arr.shape if pattern[0] in '02' else arr.shape[::-1]
+        flat = np.ascontiguousarray(arr.ravel(order='K') if (arr.flags.c_contiguous or arr.flags.f_contiguous) else arr.ravel())
+        # numpy.load returns fortran_order arrays F-contiguous: ravel('K') is the file's byte stream
+        stream = ctx.upload(flat, width=1)
+        tab = ctx.unlayout(stream, n, width, pattern)                              # uq.py:943-945
+        stream.free()
+        return tab
+    if name + '.raw' in members:
+        return logical(members[name + '.raw'])
+    if name in members and name + '.key' in members:
+        uniq = logical(members[name])
+        key = ctx.upload(np.ascontiguousarray(members[name + '.key'], dtype=np.uint32))
+        tab = ctx.gather_rows(uniq, key)                                           # uq.py:953, 957
+        uniq.free(); key.free()
+        return tab
+    raise UQError('ERROR: No %s data was found in this uQ file?!' % name)
+
+
+def decode(members, config, ctx=None):
+    """members/config as container.read_container returns them -> FASTQ bytes (ndarray uint8)."""
+    import ctypes as C
+    own = ctx is None
+    ctx = ctx or Context()
+    pat = config['pattern']
+    dna = _upload_table(ctx, members, 'DNA', pat[0])
+    qual = _upload_table(ctx, members, 'QUAL', pat[1])
+    cols_meta = config['QNAME_columns']
+    ncol = len(cols_meta)
+    keyed = 'QNAME.key' in members
+    dcols = []
+    key = ctx.upload(np.ascontiguousarray(members['QNAME.key'], dtype=np.uint32)) if keyed else None
+    for i, meta in enumerate(cols_meta):
+        nm = 'QNAME_%d' % (i + 1) + ('' if keyed else '.raw')
+        if nm not in members:
+            raise UQError('ERROR: No QNAME data exists in this uQ file?')
+        c = ctx.upload(np.ascontiguousarray(members[nm], dtype=meta['dtype']))
+        if keyed:
+            c2 = ctx.gather_rows(c, key)                                           # uq.py:973
+            c.free()
+            c = c2
+        dcols.append(c)
+    if key is not None:
+        key.free()
+
+    p = L.DecodeParams()
+    for i, ch in enumerate(config['bases']):
+        p.base_char[i] = ord(ch)
+    for i, ch in enumerate(config['qualities']):
+        p.qual_char[i] = ord(ch)
+    for i in range(256):
+        p.qual_to_base[i] = -1
+    for base, code in config['N_qual'].items():                                    # qual_N, uq.py:999
+        if code >= len(config['qualities']):
+            raise UQError('ERROR: N_qual code %d has no quality symbol; the reference decoder raises IndexError here (Q3)' % code)
+        p.qual_to_base[code] = ord(base)
+    p.bits_per_base, p.bits_per_quality = config['bits_per_base'], config['bits_per_quality']
+    p.variable, p.dna_max = int(config['variable_read_lengths']), config['dna_max']
+    keep = []
+    def cbuf(s):
+        b = np.frombuffer(s.encode('latin-1'), dtype=np.uint8).copy() if s else np.zeros(1, np.uint8)
+        keep.append(b)
+        return b.ctypes.data_as(C.c_void_p)
+    p.prefix, p.prefix_len = cbuf(config['QNAME_prefix']), len(config['QNAME_prefix'])
+    p.suffix, p.suffix_len = cbuf(config['QNAME_suffix']), len(config['QNAME_suffix'])
+    p.seps, p.nseps = cbuf(config['QNAME_separators']), len(config['QNAME_separators'])
+    p.ncols = ncol
+    carr = (L.DecodeCol * max(ncol, 1))()
+    for i, meta in enumerate(cols_meta):
+        carr[i].itemsize = np.dtype(meta['dtype']).itemsize
+        if meta['format'] == 'mapping':
+            carr[i].format = 0
+            words = [w.encode('latin-1') for w in meta['map']]
+            width = max([len(w) for w in words] + [1])
+            d = np.zeros((max(len(words), 1), width), dtype=np.uint8)
+            for k, w in enumerate(words):
+                d[k, :len(w)] = np.frombuffer(w, dtype=np.uint8)
+            keep.append(d)
+            carr[i].dict = d.ctypes.data_as(C.c_void_p)
+            carr[i].dict_count, carr[i].dict_width = len(words), width
+        elif meta['format'] == 'integers':
+            carr[i].format = 1
+            carr[i].offset = 1 if meta['offset'] else 0
+            carr[i].min_val = int(meta['min']) if meta['offset'] else 0
+        else:
+            raise UQError('ERROR: I dont support string encoding yet.')          # uq.py:1020-1021
+    p.cols = carr
+    h = C.c_void_p()
+    handles = (C.c_void_p * max(ncol, 1))(*[c.h for c in dcols])
+    ctx.check(ctx.lib.uqb_decode(ctx.h, dna.h, qual.h, handles, C.byref(p), C.byref(h)))
+    out = DeviceArray(ctx, h)
+    data = out.download()
+    for a in [dna, qual, out] + dcols:
+        a.free()
+    if own:
+        ctx.close()
+    return data
