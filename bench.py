@@ -1,0 +1,327 @@
+#!/usr/bin/env python3
+"""bench.py - FASTQ->uQ encode throughput of the B200 path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # ours
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on host cores
+
+Workload (BASELINE.json configs[1]): 100 M reads x 150 bp Illumina-style synthetic FASTQ,
+`--sort DNA` with keyed (unique table + index) DNA / QUAL / QNAME tables.  One "step" is one full
+encode of the whole FASTQ: record split -> Pass-1 statistics -> QNAME scan -> pack -> sort/unique ->
+layout, ending with every output array resident in HBM in its final layout.
+
+  value  reads/s with the FASTQ already resident in HBM (CUDA-event time on the context's stream,
+         max over ranks).
+  e2e    the same encode through the public API with HOST buffers: pinned FASTQ -> H2D -> encode ->
+         D2H of every output array into pinned host memory, all inside the timed region.
+  roofline  the kernel with the largest share of the step: algorithmic bytes / event time vs the
+         measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline  the oracle's literal restatement of uq.py (1 core, the reference is single threaded)
+         on a bounded sample of the same FASTQ.
+
+Multi-GPU (torchrun, one process per GPU): every rank encodes its own contiguous range of reads into
+its own container shard (weak scaling, no data-path collective in round 1 - see DESIGN.md (e)).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SORT, RAW, PATTERN = "DNA", None, None          # configs[1]: --sort DNA, keyed tables, default pattern
+READ_LEN = 150
+GENOME = 10_000_000
+SEED = 1002
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median over samples under load (the top half of the samples)
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from uq_b200 import host
+    from uq_b200.device import Context
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ctx = Context(local_rank)
+    n = args.reads
+    pool = max(1, n // 5)
+    dev = ctx.synth("genome", n, READ_LEN, SEED, first=rank * n, genome=GENOME, pool=pool)
+    fbytes = dev.nbytes
+    opts = dict(sort=SORT, raw=RAW, pattern=PATTERN)
+
+    def one_step():
+        fq = ctx.adopt_fastq(dev)
+        members, cfg = host.encode_device(ctx, fq, **opts)
+        out_bytes = members.nbytes()
+        members.free()
+        fq.free()
+        return out_bytes, cfg
+
+    for _ in range(args.warmup):
+        out_bytes, cfg = one_step()
+    ctx.sync()
+    ctx.timing(True)
+    ctx.timing_reset()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    launches0 = ctx.launches
+    ctx.span_begin()
+    for _ in range(args.steps):
+        out_bytes, cfg = one_step()
+    ms = ctx.span_end()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launches - launches0
+    report = ctx.timing_report()
+    ctx.timing(False)
+    ms = max_over_ranks(ms)
+    total_reads = sum_over_ranks(float(n))
+    total_fbytes = sum_over_ranks(float(fbytes))
+    total_out = sum_over_ranks(float(out_bytes))
+    t = ms / 1e3 / args.steps
+    value = total_reads / t
+
+    # ---- roofline of the dominant kernel (rank 0's launches) ----
+    peak, peak_src = peaks()
+    kern = sorted(report.items(), key=lambda kv: -kv[1][1])
+    kernel_ms = sum(v[1] for v in report.values())
+    top_name, (top_cnt, top_ms, top_bytes) = kern[0]
+    # prefer the heaviest kernel that carries an algorithmic byte count
+    for name, (cnt, kms, kb) in kern:
+        if kb > 0:
+            top_name, top_cnt, top_ms, top_bytes = name, cnt, kms, kb
+            break
+    achieved = top_bytes / 1e9 / (top_ms / 1e3) if top_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": top_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "launches_per_step": top_cnt / args.steps, "avg_launch_ms": round(top_ms / max(top_cnt, 1), 4),
+                "share_of_step": round(top_ms / (ms * 1.0), 4), "algorithmic_bytes_per_launch": top_bytes / max(top_cnt, 1)}
+    a_enc = total_fbytes + total_out
+    pipeline = {"algorithmic_bytes_per_step": a_enc, "achieved_GBps": round(a_enc / 1e9 / t, 1),
+                "frac_of_peak": round(a_enc / 1e9 / t / (peak * world), 4),
+                "kernel_time_share": round(kernel_ms / ms, 4)}
+    top5 = [{"kernel": k, "launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / ms, 4),
+             "GBps": round(v[2] / 1e9 / (v[1] / 1e3), 1) if v[1] > 0 and v[2] else None} for k, v in kern[:8]]
+
+    # ---- end to end: host buffers, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        pin_in = ctx.pinned_empty(fbytes)
+        ctx.check(ctx.lib.uqb_array_download(ctx.h, dev.h, pin_in.ptr, fbytes))
+        dev.free()
+        pin_out = ctx.pinned_empty(int(out_bytes * 1.05) + (1 << 20))
+
+        def e2e_step():
+            fq = ctx.load_fastq(pin_in)
+            members, _ = host.encode_device(ctx, fq, **opts)
+            cur = [0]
+
+            def into(name, nbytes):
+                a = pin_out.array[cur[0]:cur[0] + nbytes]
+                cur[0] += (nbytes + 63) & ~63
+                return a
+            members.download(into=into)
+            nb = members.nbytes()
+            members.free()
+            fq.free()
+            return nb
+        e2e_step()
+        ctx.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            d2h = e2e_step()
+        ctx.sync()
+        barrier()
+        te = max_over_ranks(time.perf_counter() - t0) / args.steps
+        e2e = {"value": total_reads / te, "unit": "reads/s", "h2d_bytes_per_step": int(fbytes) * world,
+               "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": round(te * 1e3, 2)}
+        sample_src = pin_in
+    else:
+        sample_src = None
+
+    # ---- CPU baseline: the reference algorithm (oracle port) on a bounded sample, rank 0 at N=1 only ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import uq_literal as lit
+        s_reads = args.cpu_sample
+        if sample_src is not None:
+            head = bytes(sample_src.array[:min(fbytes, s_reads * 420)])
+        else:
+            head = dev.download()[:s_reads * 420].tobytes()
+        lines = head.split(b"\n")
+        sample = b"\n".join(lines[:4 * s_reads]) + b"\n"
+        t0 = time.perf_counter()
+        lit.encode(sample, sort=SORT)
+        dt = time.perf_counter() - t0
+        cpu = {"value": round(s_reads / dt, 1), "unit": "reads/s", "cores": 1, "kind": "port",
+               "sample": "first %d reads of the same FASTQ, full encode incl. --sort DNA (sort is over the sample only), %.1f s; "
+                         "host has %d cores, the reference is single threaded" % (s_reads, dt, os.cpu_count())}
+
+    if rank == 0:
+        line = {
+            "metric": "fastq_to_uq_encode_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: %d reads x %d bp per GPU, --sort DNA, keyed DNA/QUAL/QNAME tables, pattern 0.1 0.1"
+                                   % (n, READ_LEN),
+                       "reads_per_gpu": n, "read_len": READ_LEN, "fastq_bytes_per_gpu": int(fbytes),
+                       "output_bytes_per_gpu": int(out_bytes), "genome": GENOME, "qual_pool": pool,
+                       "l2": "inputs (%.1f GB) far larger than the 126 MB L2; no flush needed" % (fbytes / 1e9),
+                       "bits": [cfg["bits_per_base"], cfg["bits_per_quality"]],
+                       "sharding": "independent read ranges per rank, one container shard per rank"},
+            "gb_per_s": round(total_fbytes / 1e9 / t, 2),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "pipeline_roofline": pipeline, "kernels": top5, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def _ref_worker(job):
+    """One host core: generate its own sample with the host generator, encode it with the oracle port."""
+    idx, s_reads, steps = job
+    from oracle import synth, uq_literal as lit
+    fq = synth.make_fastq(kind="genome", n=s_reads, length=READ_LEN, seed=SEED, first=idx * s_reads,
+                          genome=GENOME, pool=max(1, s_reads // 5))
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        lit.encode(fq, sort=SORT)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    """The reference's own algorithm (py3 restatement of uq.py; the Python-2 original cannot run here) on the
+    host cores: one independent process per core, each encoding its own bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    s_reads = args.ref_sample
+    total_steps = args.warmup + args.steps
+    with mp.Pool(cores) as pool:
+        res = pool.map(_ref_worker, [(i, s_reads, total_steps) for i in range(cores)])
+    per_step = [max(r[k] for r in res) for k in range(args.warmup, total_steps)]
+    t = sum(per_step) / len(per_step)
+    value = cores * s_reads / t
+    line = {
+        "impl": "reference", "metric": "fastq_to_uq_encode_reads_per_s", "value": value, "unit": "reads/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(t * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "configs[1] shape: %d bp reads, --sort DNA, keyed tables; bounded sample of %d reads per core"
+                               % (READ_LEN, s_reads)},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
+                         "sample": "%d processes x %d reads each (reference algorithm is single threaded; one independent "
+                                   "encode per core, sort over the sample only)" % (cores, s_reads)},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("UQ_BENCH_READS", "100000000")), help="reads per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=60000)
+    ap.add_argument("--ref-sample", type=int, default=20000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,11 +44,15 @@ int         uqb_ctx_sync(uqb_ctx* ctx);
 uint64_t    uqb_ctx_launch_count(const uqb_ctx* ctx);
 /* per-kernel device timing (CUDA events around every launch on the context's stream).
  * report: writes up to cap entries "name\0" packed in names (each UQB_TIMER_NAME bytes),
- * launches[i], ms[i]; returns the number of distinct kernels through *n. */
+ * launches[i], ms[i], algorithmic_bytes[i] (compulsory reads+writes summed over the launches; 0 for
+ * kernels that are not annotated); returns the number of distinct kernels through *n. */
 #define UQB_TIMER_NAME 48
 int         uqb_ctx_timing(uqb_ctx* ctx, int enable);
-int         uqb_ctx_timing_report(uqb_ctx* ctx, char* names, uint64_t* launches, double* ms, int cap, int* n);
+int         uqb_ctx_timing_report(uqb_ctx* ctx, char* names, uint64_t* launches, double* ms, uint64_t* algorithmic_bytes, int cap, int* n);
 int         uqb_ctx_timing_reset(uqb_ctx* ctx);
+/* CUDA-event time between two points of the context's stream (device timeline, host gaps included) */
+int         uqb_ctx_span_begin(uqb_ctx* ctx);
+int         uqb_ctx_span_end(uqb_ctx* ctx, double* ms);
 /* pinned host memory for end-to-end paths (cudaHostAlloc / cudaFreeHost) */
 int         uqb_host_alloc(uqb_ctx* ctx, uint64_t nbytes, void** out);
 int         uqb_host_free(uqb_ctx* ctx, void* p);

@@ -80,7 +80,9 @@ SIGNATURES = {
     "uqb_ctx_sync": (C.c_int, [P]),
     "uqb_ctx_launch_count": (C.c_uint64, [P]),
     "uqb_ctx_timing": (C.c_int, [P, C.c_int]),
-    "uqb_ctx_timing_report": (C.c_int, [P, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]),
+    "uqb_ctx_timing_report": (C.c_int, [P, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]),
+    "uqb_ctx_span_begin": (C.c_int, [P]),
+    "uqb_ctx_span_end": (C.c_int, [P, C.POINTER(C.c_double)]),
     "uqb_ctx_timing_reset": (C.c_int, [P]),
     "uqb_host_alloc": (C.c_int, [P, C.c_uint64, PP]),
     "uqb_host_free": (C.c_int, [P, P]),

@@ -239,6 +239,9 @@ extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
     int rc = uqb_readback(ctx, h, s, sizeof(an_dev));
     if (rc == 0) rc = uqb_dfree(ctx, s, sizeof(an_dev));
     if (rc) { delete h; return rc; }
+    fq->total_bases = 0;
+    for (int i = 0; i < 256; i++) fq->total_bases += h->base_count[i];
+    uqb_timer_add_bytes(ctx, 2 * fq->total_bases + 32 * N);     // k_pair_hist: every base + quality byte, 4 offsets per record
     for (int i = 0; i < 256; i++) {
         out->base_count[i] = h->base_count[i];
         out->qual_count[i] = h->qual_count[i];

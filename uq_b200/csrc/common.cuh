@@ -11,7 +11,8 @@
 
 #define UQB_SM_COUNT 148   // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of this
 
-struct uqb_timer_rec { const char* name; cudaEvent_t a, b; };
+struct uqb_timer_rec { const char* name; cudaEvent_t a, b; uint64_t bytes; };
+struct uqb_timer_tot { uint64_t launches = 0; double ms = 0; uint64_t bytes = 0; };
 
 struct uqb_ctx {
     int device = 0;
@@ -28,7 +29,8 @@ struct uqb_ctx {
     bool timing = false;
     std::vector<uqb_timer_rec> pending;
     std::vector<cudaEvent_t> free_events;
-    std::map<std::string, std::pair<uint64_t, double>> totals;
+    std::map<std::string, uqb_timer_tot> totals;
+    cudaEvent_t span_a = nullptr, span_b = nullptr;   // uqb_ctx_span_begin / _end
 };
 
 struct uqb_array {
@@ -54,6 +56,7 @@ struct uqb_fastq {
     bool owned = false;
     uint64_t* line_off = nullptr; // uint64[n_lines + 1]
     uint64_t n_lines = 0, n_reads = 0;
+    uint64_t total_bases = 0;     // sum of read lengths (set by uqb_analyze; bookkeeping for byte counts)
     uint32_t prefix_len = 0, suffix_len = 0, ncols = 0;
     std::vector<uqb_qcol> qcols;
 };
@@ -87,13 +90,17 @@ static inline int uqb_dalloc_t(uqb_ctx* ctx, T** p, size_t count) {
 }
 
 // ---- launches ----------------------------------------------------------------------------------
-void uqb_timer_begin(uqb_ctx* ctx, const char* name);
+void uqb_timer_begin(uqb_ctx* ctx, const char* name, uint64_t bytes);
 void uqb_timer_end(uqb_ctx* ctx);
+void uqb_timer_add_bytes(uqb_ctx* ctx, uint64_t bytes);   // adds to the most recent launch record (when the size is known late)
 
 // Launch a kernel on the context stream, count it, optionally time it, and check the launch.
-#define UQB_LAUNCH(kernel, grid, block, smem, ...)                                           \
+// UQB_LAUNCH_B additionally records the kernel's ALGORITHMIC bytes (compulsory reads + writes) so that
+// bench.py can report achieved bandwidth per kernel from the event timings.
+#define UQB_LAUNCH(kernel, grid, block, smem, ...) UQB_LAUNCH_B(0, kernel, grid, block, smem, __VA_ARGS__)
+#define UQB_LAUNCH_B(abytes, kernel, grid, block, smem, ...)                                 \
     do {                                                                                     \
-        uqb_timer_begin(ctx, #kernel);                                                       \
+        uqb_timer_begin(ctx, #kernel, (uint64_t)(abytes));                                   \
         kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                       \
         uqb_timer_end(ctx);                                                                  \
         ctx->launches++;                                                                     \

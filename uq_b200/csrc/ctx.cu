@@ -52,6 +52,7 @@ extern "C" void uqb_ctx_destroy(uqb_ctx* ctx) {
     for (auto& r : ctx->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->free_events) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->span_a) { cudaEventDestroy(ctx->span_a); cudaEventDestroy(ctx->span_b); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -77,10 +78,11 @@ static cudaEvent_t get_event(uqb_ctx* ctx) {
     return e;
 }
 
-void uqb_timer_begin(uqb_ctx* ctx, const char* name) {
+void uqb_timer_begin(uqb_ctx* ctx, const char* name, uint64_t bytes) {
     if (!ctx->timing) return;
     uqb_timer_rec r;
     r.name = name;
+    r.bytes = bytes;
     r.a = get_event(ctx);
     r.b = get_event(ctx);
     cudaEventRecord(r.a, ctx->stream);
@@ -92,6 +94,11 @@ void uqb_timer_end(uqb_ctx* ctx) {
     cudaEventRecord(ctx->pending.back().b, ctx->stream);
 }
 
+void uqb_timer_add_bytes(uqb_ctx* ctx, uint64_t bytes) {
+    if (!ctx->timing || ctx->pending.empty()) return;
+    ctx->pending.back().bytes += bytes;
+}
+
 static void drain_timers(uqb_ctx* ctx) {
     if (ctx->pending.empty()) return;
     cudaStreamSynchronize(ctx->stream);
@@ -99,8 +106,9 @@ static void drain_timers(uqb_ctx* ctx) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
             auto& t = ctx->totals[r.name];
-            t.first += 1;
-            t.second += ms;
+            t.launches += 1;
+            t.ms += ms;
+            t.bytes += r.bytes;
         }
         ctx->free_events.push_back(r.a);
         ctx->free_events.push_back(r.b);
@@ -120,17 +128,34 @@ extern "C" int uqb_ctx_timing_reset(uqb_ctx* ctx) {
     return 0;
 }
 
-extern "C" int uqb_ctx_timing_report(uqb_ctx* ctx, char* names, uint64_t* launches, double* ms, int cap, int* n) {
+extern "C" int uqb_ctx_timing_report(uqb_ctx* ctx, char* names, uint64_t* launches, double* ms, uint64_t* bytes, int cap, int* n) {
     drain_timers(ctx);
     int i = 0;
     for (auto& kv : ctx->totals) {
         if (i >= cap) break;
         snprintf(names + (size_t)i * UQB_TIMER_NAME, UQB_TIMER_NAME, "%s", kv.first.c_str());
-        launches[i] = kv.second.first;
-        ms[i] = kv.second.second;
+        launches[i] = kv.second.launches;
+        ms[i] = kv.second.ms;
+        bytes[i] = kv.second.bytes;
         i++;
     }
     *n = i;
+    return 0;
+}
+
+// device time between two points of the context's stream (includes host gaps in between)
+extern "C" int uqb_ctx_span_begin(uqb_ctx* ctx) {
+    if (!ctx->span_a) { UQB_CUDA(cudaEventCreate(&ctx->span_a)); UQB_CUDA(cudaEventCreate(&ctx->span_b)); }
+    UQB_CUDA(cudaEventRecord(ctx->span_a, ctx->stream));
+    return 0;
+}
+extern "C" int uqb_ctx_span_end(uqb_ctx* ctx, double* ms) {
+    if (!ctx->span_a) return uqb_fail(ctx, "span_end without span_begin");
+    UQB_CUDA(cudaEventRecord(ctx->span_b, ctx->stream));
+    UQB_CUDA(cudaEventSynchronize(ctx->span_b));
+    float f = 0.f;
+    UQB_CUDA(cudaEventElapsedTime(&f, ctx->span_a, ctx->span_b));
+    *ms = f;
     return 0;
 }
 

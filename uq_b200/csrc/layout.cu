@@ -91,15 +91,15 @@ static int layout_impl(uqb_ctx* ctx, const uint8_t* src, uint8_t* dst, uint64_t 
     if (n == 0 || width == 0) return 0;
     if (!ld.transposed) {
         unsigned g = uqb_grid(ctx, n, LT / 32, 16);
-        if (inverse) UQB_LAUNCH(k_layout_rows<true>, g, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
-        else         UQB_LAUNCH(k_layout_rows<false>, g, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
+        if (inverse) UQB_LAUNCH_B(2 * n * width, k_layout_rows<true>, g, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
+        else         UQB_LAUNCH_B(2 * n * width, k_layout_rows<false>, g, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
     } else {
         uint64_t gx = (n + TILE - 1) / TILE;
         if (gx > 0x7fffffffull) return uqb_fail(ctx, "layout: too many rows");
         dim3 grid((unsigned)gx, (width + TILE - 1) / TILE);
         if (grid.y > 65535) return uqb_fail(ctx, "layout: rows wider than %d bytes are not supported", 65535 * TILE);
-        if (inverse) UQB_LAUNCH(k_layout_transpose<true>, grid, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
-        else         UQB_LAUNCH(k_layout_transpose<false>, grid, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
+        if (inverse) UQB_LAUNCH_B(2 * n * width, k_layout_transpose<true>, grid, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
+        else         UQB_LAUNCH_B(2 * n * width, k_layout_transpose<false>, grid, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
     }
     return 0;
 }

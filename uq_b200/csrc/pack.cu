@@ -110,7 +110,9 @@ extern "C" int uqb_pack(uqb_ctx* ctx, uqb_fastq* fq, const uqb_pack_params* p, u
     unsigned long long* d_err;
     UQB_TRY(uqb_dalloc_t(ctx, &d_err, 1));
     UQB_CUDA(cudaMemsetAsync(d_err, 0xFF, 8, ctx->stream));
-    UQB_LAUNCH(k_pack_rows, uqb_grid(ctx, N, PK_THREADS / 32, 16), PK_THREADS, 0, fq->d, fq->line_off, N, lut,
+    // algorithmic bytes: base + quality bytes in, 4 line offsets per record in, both packed tables out
+    const uint64_t abytes = 2 * fq->total_bases + 32 * N + N * ((uint64_t)p->dna_bytes + p->qual_bytes);
+    UQB_LAUNCH_B(abytes, k_pack_rows, uqb_grid(ctx, N, PK_THREADS / 32, 16), PK_THREADS, 0, fq->d, fq->line_off, N, lut,
                p->bits_per_base, p->bits_per_quality, p->dna_bytes, p->qual_bytes, p->variable, p->dna_max,
                (uint8_t*)(*dna)->d, (uint8_t*)(*qual)->d, d_err);
     unsigned long long err;

@@ -118,9 +118,9 @@ static int scan_impl(uqb_ctx* ctx, const uint32_t* d_in, Tout* d_out, uint64_t n
     uint64_t nblocks = (n + PR_TILE - 1) / PR_TILE;
     Tout* sums;
     UQB_TRY(uqb_dalloc_t(ctx, &sums, nblocks));
-    UQB_LAUNCH(k_scan_reduce<Tout>, (unsigned)nblocks, PR_THREADS, 0, d_in, n, sums);
+    UQB_LAUNCH_B(n * 4, k_scan_reduce<Tout>, (unsigned)nblocks, PR_THREADS, 0, d_in, n, sums);
     UQB_LAUNCH(k_scan_block_sums<Tout>, 1, 1024, 0, sums, nblocks, d_total);
-    UQB_LAUNCH(k_scan_apply<Tout>, (unsigned)nblocks, PR_THREADS, 0, d_in, d_out, n, sums);
+    UQB_LAUNCH_B(n * (4 + sizeof(Tout)), k_scan_apply<Tout>, (unsigned)nblocks, PR_THREADS, 0, d_in, d_out, n, sums);
     UQB_TRY(uqb_dfree(ctx, sums, nblocks * sizeof(Tout)));
     return 0;
 }
@@ -284,7 +284,7 @@ int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux) {
     bits_summary* d_bits;
     UQB_TRY(uqb_dalloc_t(ctx, &d_bits, 1));
     UQB_CUDA(cudaMemcpyAsync(d_bits, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-    UQB_LAUNCH(k_bits_reduce, uqb_grid(ctx, n, 256 * 8), 256, 0, sb->key[sb->cur], use_aux ? sb->aux[sb->cur] : nullptr, n, d_bits);
+    UQB_LAUNCH_B(n * (use_aux ? 12 : 8), k_bits_reduce, uqb_grid(ctx, n, 256 * 8), 256, 0, sb->key[sb->cur], use_aux ? sb->aux[sb->cur] : nullptr, n, d_bits);
     UQB_TRY(uqb_readback(ctx, &got, d_bits, sizeof(got)));
     UQB_TRY(uqb_dfree(ctx, d_bits, sizeof(bits_summary)));
 
@@ -302,15 +302,15 @@ int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux) {
         bool auxd = p >= nk;
         int shift = auxd ? ashift[p - nk] : kshift[p];
         int c = sb->cur, o = c ^ 1;
-        if (auxd) UQB_LAUNCH(k_radix_hist<true>, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], n, shift, ghist, nblk);
-        else      UQB_LAUNCH(k_radix_hist<false>, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], n, shift, ghist, nblk);
+        if (auxd) UQB_LAUNCH_B(n * 4, k_radix_hist<true>, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], n, shift, ghist, nblk);
+        else      UQB_LAUNCH_B(n * 8, k_radix_hist<false>, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], n, shift, ghist, nblk);
         UQB_TRY(uqb_scan_u32(ctx, ghist, ghist, hist_n, nullptr));
         auto k_radix_scatter_aux = k_radix_scatter<true, true>;
         auto k_radix_scatter_key_aux = k_radix_scatter<false, true>;
         auto k_radix_scatter_key = k_radix_scatter<false, false>;
-        if (auxd)         UQB_LAUNCH(k_radix_scatter_aux, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
-        else if (has_aux) UQB_LAUNCH(k_radix_scatter_key_aux, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
-        else              UQB_LAUNCH(k_radix_scatter_key, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        if (auxd)         UQB_LAUNCH_B(n * 32, k_radix_scatter_aux, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        else if (has_aux) UQB_LAUNCH_B(n * 32, k_radix_scatter_key_aux, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        else              UQB_LAUNCH_B(n * 24, k_radix_scatter_key, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
         sb->cur = o;
     }
     UQB_TRY(uqb_dfree(ctx, ghist, hist_n * 4));

@@ -123,7 +123,7 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
     {
         uqb_sortbuf sb;
         UQB_TRY(uqb_sortbuf_alloc(ctx, &sb, n, false));
-        UQB_LAUNCH(k_chunk0_keys, nb, ST, 0, rows, n, width, sb.key[0], sb.val[0]);
+        UQB_LAUNCH_B(n * ((width < 8 ? width : 8) + 12), k_chunk0_keys, nb, ST, 0, rows, n, width, sb.key[0], sb.val[0]);
         UQB_TRY(uqb_radix_sort(ctx, &sb, n, false));
         UQB_LAUNCH(k_mark_heads, nb, ST, 0, sb.key[sb.cur], n, head);
         UQB_CUDA(cudaMemcpyAsync(perm, sb.val[sb.cur], n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -153,9 +153,9 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
             uint32_t* pos_list;
             UQB_TRY(uqb_sortbuf_alloc(ctx, &sb, m, true));
             UQB_TRY(uqb_dalloc_t(ctx, &pos_list, m));
-            UQB_LAUNCH(k_compact_active, nb, ST, 0, rows, width, off, act, apos, head, excl, perm, n, pos_list, sb.key[0], sb.aux[0], sb.val[0]);
+            UQB_LAUNCH_B(n * 8 + m * 32, k_compact_active, nb, ST, 0, rows, width, off, act, apos, head, excl, perm, n, pos_list, sb.key[0], sb.aux[0], sb.val[0]);
             UQB_TRY(uqb_radix_sort(ctx, &sb, m, true));
-            UQB_LAUNCH(k_write_back, uqb_blocks(m, ST), ST, 0, sb.key[sb.cur], sb.aux[sb.cur], sb.val[sb.cur], pos_list, m, perm, head);
+            UQB_LAUNCH_B(m * 28, k_write_back, uqb_blocks(m, ST), ST, 0, sb.key[sb.cur], sb.aux[sb.cur], sb.val[sb.cur], pos_list, m, perm, head);
             UQB_TRY(uqb_dfree(ctx, pos_list, m * 4));
             UQB_TRY(uqb_sortbuf_free(ctx, &sb));
         }
@@ -223,7 +223,7 @@ extern "C" int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** p
             uint32_t* first_row;
             UQB_TRY(uqb_dalloc_t(ctx, &first_row, u));
             UQB_LAUNCH(k_first_of_group, nb, ST, 0, d_perm, d_gid, n, first_row);
-            UQB_LAUNCH(k_gather_rows, uqb_grid(ctx, u, ST / 32, 16), ST, 0, (const uint8_t*)table->d, table->width, first_row, u, (uint8_t*)(*uniq)->d);
+            UQB_LAUNCH_B(u * (2 * (uint64_t)table->width + 4), k_gather_rows, uqb_grid(ctx, u, ST / 32, 16), ST, 0, (const uint8_t*)table->d, table->width, first_row, u, (uint8_t*)(*uniq)->d);
             UQB_TRY(uqb_dfree(ctx, first_row, u * 4));
         }
     }
@@ -240,7 +240,7 @@ extern "C" int uqb_gather_rows(uqb_ctx* ctx, const uqb_array* table, const uqb_a
     if (perm->width != 4) return uqb_fail(ctx, "gather_rows: index array must be uint32");
     UQB_TRY(uqb_new_array(ctx, perm->n, table->width, out));
     if (perm->n && table->width)
-        UQB_LAUNCH(k_gather_rows, uqb_grid(ctx, perm->n, ST / 32, 16), ST, 0, (const uint8_t*)table->d, table->width, (const uint32_t*)perm->d, perm->n, (uint8_t*)(*out)->d);
+        UQB_LAUNCH_B(perm->n * (2 * (uint64_t)table->width + 4), k_gather_rows, uqb_grid(ctx, perm->n, ST / 32, 16), ST, 0, (const uint8_t*)table->d, table->width, (const uint32_t*)perm->d, perm->n, (uint8_t*)(*out)->d);
     return 0;
 }
 

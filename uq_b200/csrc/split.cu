@@ -168,7 +168,7 @@ extern "C" int uqb_split(uqb_ctx* ctx, uqb_fastq* fq, uqb_split_info* info) {
         UQB_TRY(uqb_dalloc_t(ctx, &counts, ntiles));
         UQB_TRY(uqb_dalloc_t(ctx, &bases, ntiles));
         UQB_TRY(uqb_dalloc_t(ctx, &d_total, 1));
-        UQB_LAUNCH(k_newline_count, (unsigned)ntiles, SP_THREADS, 0, fq->d, fq->n, counts);
+        UQB_LAUNCH_B(fq->n, k_newline_count, (unsigned)ntiles, SP_THREADS, 0, fq->d, fq->n, counts);
         UQB_TRY(uqb_scan_u32_to_u64(ctx, counts, bases, ntiles, d_total));
         UQB_TRY(uqb_readback(ctx, &total, d_total, 8));
     }
@@ -177,7 +177,7 @@ extern "C" int uqb_split(uqb_ctx* ctx, uqb_fastq* fq, uqb_split_info* info) {
     UQB_TRY(uqb_dalloc_t(ctx, &fq->line_off, total + 1));
     UQB_LAUNCH(k_set_u64, 1, 1, 0, fq->line_off, 0ull);
     if (ntiles) {
-        UQB_LAUNCH(k_newline_write, (unsigned)ntiles, SP_THREADS, 0, fq->d, fq->n, bases, fq->line_off);
+        UQB_LAUNCH_B(fq->n + 8 * total, k_newline_write, (unsigned)ntiles, SP_THREADS, 0, fq->d, fq->n, bases, fq->line_off);
         UQB_TRY(uqb_dfree(ctx, counts, ntiles * 4));
         UQB_TRY(uqb_dfree(ctx, bases, ntiles * 8));
         UQB_TRY(uqb_dfree(ctx, d_total, 8));

@@ -65,13 +65,22 @@ class Context:
         names = C.create_string_buffer(cap * L.TIMER_NAME)
         cnt = (C.c_uint64 * cap)()
         ms = (C.c_double * cap)()
+        nb = (C.c_uint64 * cap)()
         n = C.c_int()
-        self.check(self.lib.uqb_ctx_timing_report(self.h, names, cnt, ms, cap, C.byref(n)))
+        self.check(self.lib.uqb_ctx_timing_report(self.h, names, cnt, ms, nb, cap, C.byref(n)))
         out = {}
         for i in range(n.value):
             nm = names.raw[i * L.TIMER_NAME:(i + 1) * L.TIMER_NAME].split(b"\0")[0].decode()
-            out[nm] = (int(cnt[i]), float(ms[i]))
+            out[nm] = (int(cnt[i]), float(ms[i]), int(nb[i]))
         return out
+
+    def span_begin(self):
+        self.check(self.lib.uqb_ctx_span_begin(self.h))
+
+    def span_end(self):
+        ms = C.c_double()
+        self.check(self.lib.uqb_ctx_span_end(self.h, C.byref(ms)))
+        return float(ms.value)
 
     def mem_info(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
