@@ -1,0 +1,22 @@
+#!/usr/bin/env python3
+"""Diagnostics: per-phase wall clock and full per-kernel event timing of one encode (not a benchmark)."""
+import json, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from uq_b200 import host
+from uq_b200.device import Context
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
+sort = sys.argv[2] if len(sys.argv) > 2 else "DNA"
+ctx = Context(0)
+dev = ctx.synth("genome", n, 150, 1002, genome=10_000_000, pool=max(1, n // 5))
+def step():
+    fq = ctx.adopt_fastq(dev)
+    m, cfg = host.encode_device(ctx, fq, sort=sort)
+    m.free(); fq.free()
+step(); step()
+ctx.timing(True); ctx.timing_reset()
+host.PHASE_LOG = {}
+step()
+rep = ctx.timing_report()
+print(json.dumps({"phases_ms": host.PHASE_LOG,
+                  "kernels": sorted(([k, v[0], round(v[1], 3), round(v[2] / 1e9 / (v[1] / 1e3), 1) if v[1] > 0 and v[2] else None] for k, v in rep.items()), key=lambda r: -r[2])}, indent=1))

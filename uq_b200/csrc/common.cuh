@@ -14,8 +14,25 @@
 struct uqb_timer_rec { const char* name; cudaEvent_t a, b; uint64_t bytes; };
 struct uqb_timer_tot { uint64_t launches = 0; double ms = 0; uint64_t bytes = 0; };
 
+// Device memory arena: ONE contiguous virtual address range per context, backed on demand by physical
+// chunks (CUDA virtual memory management), with a first-fit free list on top.  All work of a context is
+// on one stream, so a freed block may be handed out again immediately (stream order = program order).
+// Sized for a 180 GB part: nothing is ever returned to the driver before the context dies, so the
+// steady-state cost of an allocation is a map lookup instead of a driver call.
+struct uqb_arena {
+    unsigned long long base = 0;      // CUdeviceptr
+    uint64_t reserved = 0;            // bytes of virtual address space
+    uint64_t mapped = 0;              // bytes backed by physical memory, [base, base + mapped)
+    uint64_t granularity = 0;
+    std::map<uint64_t, uint64_t> free_by_off;           // offset -> size
+    std::map<uint64_t, uint64_t> used;                  // offset -> size
+    std::vector<unsigned long long> handles;            // CUmemGenericAllocationHandle per chunk
+    std::vector<std::pair<uint64_t, uint64_t>> chunks;  // (offset, size) per chunk
+};
+
 struct uqb_ctx {
     int device = 0;
+    uqb_arena arena;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     char err[512] = {0};

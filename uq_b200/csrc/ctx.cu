@@ -1,7 +1,111 @@
 // Context, memory, arrays and the per-kernel timing facility of libuqb200.so.
 #include "common.cuh"
+#include <cuda.h>
 #include <stdarg.h>
 #include <new>
+
+// ---- driver entry points for the VMM arena (resolved at run time: libuqb200.so does not link libcuda) ----
+struct drv_api {
+    CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+    bool ok = false;
+};
+static drv_api g_drv;
+
+static int load_driver(uqb_ctx* ctx) {
+    if (g_drv.ok) return 0;
+    struct { const char* name; void** fn; } tab[] = {
+        {"cuMemGetAllocationGranularity", (void**)&g_drv.GetGranularity}, {"cuMemAddressReserve", (void**)&g_drv.AddressReserve},
+        {"cuMemCreate", (void**)&g_drv.Create}, {"cuMemMap", (void**)&g_drv.Map}, {"cuMemSetAccess", (void**)&g_drv.SetAccess},
+        {"cuMemUnmap", (void**)&g_drv.Unmap}, {"cuMemRelease", (void**)&g_drv.Release}, {"cuMemAddressFree", (void**)&g_drv.AddressFree}};
+    for (auto& t : tab) {
+        cudaDriverEntryPointQueryResult st;
+        cudaError_t e = cudaGetDriverEntryPoint(t.name, t.fn, cudaEnableDefault, &st);
+        if (e != cudaSuccess || st != cudaDriverEntryPointSuccess || !*t.fn)
+            return uqb_fail(ctx, "cannot resolve driver entry point %s", t.name);
+    }
+    g_drv.ok = true;
+    return 0;
+}
+
+static inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+static int arena_init(uqb_ctx* ctx) {
+    UQB_TRY(load_driver(ctx));
+    uqb_arena& A = ctx->arena;
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = ctx->device;
+    size_t gran = 0;
+    if (g_drv.GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0)
+        return uqb_fail(ctx, "cuMemGetAllocationGranularity failed");
+    A.granularity = gran;
+    size_t f = 0, t = 0;
+    UQB_CUDA(cudaMemGetInfo(&f, &t));
+    A.reserved = round_up((uint64_t)t, gran);
+    CUdeviceptr base = 0;
+    if (g_drv.AddressReserve(&base, A.reserved, 0, 0, 0) != CUDA_SUCCESS)
+        return uqb_fail(ctx, "cuMemAddressReserve of %llu bytes failed", (unsigned long long)A.reserved);
+    A.base = base;
+    A.mapped = 0;
+    return 0;
+}
+
+static void arena_destroy(uqb_ctx* ctx) {
+    uqb_arena& A = ctx->arena;
+    if (!g_drv.ok || !A.base) return;
+    for (size_t i = 0; i < A.handles.size(); i++) {
+        g_drv.Unmap(A.base + A.chunks[i].first, A.chunks[i].second);
+        g_drv.Release(A.handles[i]);
+    }
+    g_drv.AddressFree(A.base, A.reserved);
+    A = uqb_arena();
+}
+
+// back [mapped, mapped + at_least) with physical memory
+static int arena_grow(uqb_ctx* ctx, uint64_t at_least) {
+    uqb_arena& A = ctx->arena;
+    const uint64_t min_chunk = 1ull << 30;
+    uint64_t chunk = round_up(at_least > min_chunk ? at_least : min_chunk, A.granularity);
+    if (A.mapped + chunk > A.reserved) chunk = round_up(at_least, A.granularity);
+    if (A.mapped + chunk > A.reserved)
+        return uqb_fail(ctx, "device arena exhausted: %llu bytes mapped, %llu more requested", (unsigned long long)A.mapped, (unsigned long long)at_least);
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = ctx->device;
+    CUmemGenericAllocationHandle h;
+    CUresult r = g_drv.Create(&h, chunk, &prop, 0);
+    if (r != CUDA_SUCCESS && chunk > round_up(at_least, A.granularity)) {
+        chunk = round_up(at_least, A.granularity);
+        r = g_drv.Create(&h, chunk, &prop, 0);
+    }
+    if (r != CUDA_SUCCESS) return uqb_fail(ctx, "out of device memory: cuMemCreate(%llu) failed (%d) with %llu bytes already mapped", (unsigned long long)chunk, (int)r, (unsigned long long)A.mapped);
+    if (g_drv.Map(A.base + A.mapped, chunk, 0, h, 0) != CUDA_SUCCESS) { g_drv.Release(h); return uqb_fail(ctx, "cuMemMap failed"); }
+    CUmemAccessDesc acc = {};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = ctx->device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (g_drv.SetAccess(A.base + A.mapped, chunk, &acc, 1) != CUDA_SUCCESS) return uqb_fail(ctx, "cuMemSetAccess failed");
+    A.handles.push_back(h);
+    A.chunks.push_back({A.mapped, chunk});
+    // append to the free list, merging with a free block that ends at the old frontier
+    uint64_t off = A.mapped, size = chunk;
+    if (!A.free_by_off.empty()) {
+        auto last = std::prev(A.free_by_off.end());
+        if (last->first + last->second == A.mapped) { off = last->first; size += last->second; A.free_by_off.erase(last); }
+    }
+    A.free_by_off[off] = size;
+    A.mapped += chunk;
+    return 0;
+}
 
 int uqb_fail(uqb_ctx* ctx, const char* fmt, ...) {
     va_list ap;
@@ -37,11 +141,8 @@ extern "C" int uqb_ctx_create(int device, void* stream, uqb_ctx** out) {
         UQB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         ctx->own_stream = true;
     }
-    // keep freed blocks in the stream-ordered pool instead of returning them to the OS
-    cudaMemPool_t pool;
-    UQB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thresh = UINT64_MAX;
-    UQB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    UQB_CUDA(cudaFree(0));            // make sure the primary context exists before driver-level calls
+    UQB_TRY(arena_init(ctx));
     return 0;
 }
 
@@ -53,6 +154,7 @@ extern "C" void uqb_ctx_destroy(uqb_ctx* ctx) {
     for (auto e : ctx->free_events) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->span_a) { cudaEventDestroy(ctx->span_a); cudaEventDestroy(ctx->span_b); }
+    arena_destroy(ctx);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -162,23 +264,47 @@ extern "C" int uqb_ctx_span_end(uqb_ctx* ctx, double* ms) {
 // ---- memory ------------------------------------------------------------------------------------
 int uqb_dalloc(uqb_ctx* ctx, void** p, size_t nbytes) {
     *p = nullptr;
-    size_t want = nbytes ? nbytes : 16;
-    want = (want + 255) & ~(size_t)255;
-    cudaError_t e = cudaMallocAsync(p, want, ctx->stream);
-    if (e != cudaSuccess) {
-        *p = nullptr;
-        return uqb_fail(ctx, "device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+    uqb_arena& A = ctx->arena;
+    const uint64_t want = round_up(nbytes ? nbytes : 1, 256);
+    // best fit over the free list (a few hundred blocks at most)
+    auto best = A.free_by_off.end();
+    for (auto it = A.free_by_off.begin(); it != A.free_by_off.end(); ++it)
+        if (it->second >= want && (best == A.free_by_off.end() || it->second < best->second)) best = it;
+    if (best == A.free_by_off.end()) {
+        uint64_t tail = 0;
+        if (!A.free_by_off.empty()) {
+            auto last = std::prev(A.free_by_off.end());
+            if (last->first + last->second == A.mapped) tail = last->second;
+        }
+        UQB_TRY(arena_grow(ctx, want - tail));
+        best = std::prev(A.free_by_off.end());
+        if (best->second < want) return uqb_fail(ctx, "device arena: internal error after growth");
     }
+    const uint64_t off = best->first, size = best->second;
+    A.free_by_off.erase(best);
+    if (size > want) A.free_by_off[off + want] = size - want;
+    A.used[off] = want;
     ctx->bytes_in_use += want;
+    *p = (void*)(uintptr_t)(A.base + off);
     return 0;
 }
 
-int uqb_dfree(uqb_ctx* ctx, void* p, size_t nbytes) {
+int uqb_dfree(uqb_ctx* ctx, void* p, size_t /*nbytes*/) {
     if (!p) return 0;
-    size_t want = nbytes ? nbytes : 16;
-    want = (want + 255) & ~(size_t)255;
-    ctx->bytes_in_use -= want;
-    UQB_CUDA(cudaFreeAsync(p, ctx->stream));
+    uqb_arena& A = ctx->arena;
+    const uint64_t off = (uint64_t)(uintptr_t)p - A.base;
+    auto u = A.used.find(off);
+    if (u == A.used.end()) return uqb_fail(ctx, "device arena: free of an unknown pointer");
+    uint64_t size = u->second, start = off;
+    A.used.erase(u);
+    ctx->bytes_in_use -= size;
+    auto next = A.free_by_off.lower_bound(start);
+    if (next != A.free_by_off.end() && start + size == next->first) { size += next->second; next = A.free_by_off.erase(next); }
+    if (next != A.free_by_off.begin()) {
+        auto prev = std::prev(next);
+        if (prev->first + prev->second == start) { start = prev->first; size += prev->second; A.free_by_off.erase(prev); }
+    }
+    A.free_by_off[start] = size;
     return 0;
 }
 

@@ -29,6 +29,21 @@ class UQError(Exception):
     """Where the reference prints a message and exit()s (uq.py:48-50) this path raises."""
 
 
+PHASE_LOG = None     # set to a dict to collect wall-clock milliseconds per phase (adds stream syncs; diagnostics only)
+
+
+def _timed(ctx, name, fn, *args, **kw):
+    if PHASE_LOG is None:
+        return fn(*args, **kw)
+    import time
+    ctx.sync()
+    t0 = time.perf_counter()
+    out = fn(*args, **kw)
+    ctx.sync()
+    PHASE_LOG[name] = PHASE_LOG.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # options (uq.py:52-69, 893-894)
 # ------------------------------------------------------------------------------------------------
@@ -361,17 +376,17 @@ def run_mix(ctx, dna, qual, cols, columns, sorted_on, raw_tables, pattern):
     if sorted_on in ('DNA', 'QUAL'):
         first = (dna, 'DNA', pd) if sorted_on == 'DNA' else (qual, 'QUAL', pq)
         second = (qual, 'QUAL', pq) if sorted_on == 'DNA' else (dna, 'DNA', pd)
-        order = _mix_dna_qual(ctx, out, first[0], first[1], False, first[1] in raw_tables, first[2])
-        _mix_dna_qual(ctx, out, second[0], second[1], order, second[1] in raw_tables, second[2])
-        _mix_qname(ctx, out, cols, columns, order, 'QNAME' in raw_tables)
+        order = _timed(ctx, 'mix_' + first[1], _mix_dna_qual, ctx, out, first[0], first[1], False, first[1] in raw_tables, first[2])
+        _timed(ctx, 'mix_' + second[1], _mix_dna_qual, ctx, out, second[0], second[1], order, second[1] in raw_tables, second[2])
+        _timed(ctx, 'mix_QNAME', _mix_qname, ctx, out, cols, columns, order, 'QNAME' in raw_tables)
     elif sorted_on == 'QNAME':
-        order = _mix_qname(ctx, out, cols, columns, False, 'QNAME' in raw_tables)
-        _mix_dna_qual(ctx, out, dna, 'DNA', order, 'DNA' in raw_tables, pd)
-        _mix_dna_qual(ctx, out, qual, 'QUAL', order, 'QUAL' in raw_tables, pq)
+        order = _timed(ctx, 'mix_QNAME', _mix_qname, ctx, out, cols, columns, False, 'QNAME' in raw_tables)
+        _timed(ctx, 'mix_DNA', _mix_dna_qual, ctx, out, dna, 'DNA', order, 'DNA' in raw_tables, pd)
+        _timed(ctx, 'mix_QUAL', _mix_dna_qual, ctx, out, qual, 'QUAL', order, 'QUAL' in raw_tables, pq)
     else:
-        _mix_qname(ctx, out, cols, columns, None, 'QNAME' in raw_tables)
-        _mix_dna_qual(ctx, out, dna, 'DNA', None, 'DNA' in raw_tables, pd)
-        _mix_dna_qual(ctx, out, qual, 'QUAL', None, 'QUAL' in raw_tables, pq)
+        _timed(ctx, 'mix_QNAME', _mix_qname, ctx, out, cols, columns, None, 'QNAME' in raw_tables)
+        _timed(ctx, 'mix_DNA', _mix_dna_qual, ctx, out, dna, 'DNA', None, 'DNA' in raw_tables, pd)
+        _timed(ctx, 'mix_QUAL', _mix_dna_qual, ctx, out, qual, 'QUAL', None, 'QUAL' in raw_tables, pq)
     return out
 
 
@@ -381,13 +396,13 @@ def run_mix(ctx, dna, qual, cols, columns, sorted_on, raw_tables, pattern):
 def encode_device(ctx, fq, sort=None, raw=None, pattern=None, pad=False, notricks=False, stages=None):
     """FASTQ already in HBM (device.Fastq) -> (DeviceMembers, config).  All O(N) work is on the GPU."""
     sort, raw, pattern = normalise_options(sort, raw, pattern)
-    info = fq.split()
+    info = _timed(ctx, 'split', fq.split)
     if info.status == 1:                                                           # uq.py:86-87
         raise UQError('ERROR: The FASTQ file provided contains' + str(info.n_lines) + 'rows, which is not divisible by 4!')
     n = int(info.n_reads)
     if n == 0:
         raise UQError('ERROR: the FASTQ file holds no records')
-    st = fq.analyze()
+    st = _timed(ctx, 'analyze', fq.analyze)
     if st.bad_first_char != -1:                                                    # uq.py:346
         raise UQError('ERROR: This does not look like a FASTA/FASTQ file! (first line does not start with @)')
     bad = [(r, w) for r, w in ((st.bad_plus_record, 'plus'), (st.bad_len_record, 'len')) if r >= 0]
@@ -398,13 +413,13 @@ def encode_device(ctx, fq, sort=None, raw=None, pattern=None, pad=False, notrick
         raise UQError('ERROR: Length of DNA does not match the length of the quality scores for entry %d' % (r + 1))   # uq.py:366, 388
     prefix, suffix, separators = derive_qname_layout(st, n)
     dec = decide_alphabets(st, notricks=notricks, pad=pad)
-    colstats, bad_rec = fq.qname_scan(len(prefix), len(suffix), separators)
+    colstats, bad_rec = _timed(ctx, 'qname_scan', fq.qname_scan, len(prefix), len(suffix), separators)
     if bad_rec >= 0:                                                               # uq.py:609-613, 637
         raise UQError('Encoding QNAMEs as strings has not been implimented yet. (record %d does not split into %d columns)'
                       % (bad_rec, len(separators) + 1))
     columns = decide_columns(colstats, n, fq.qname_dict)
-    dna, qual = fq.pack(pack_params(dec))
-    cols = fq.qname_encode(column_specs(columns))
+    dna, qual = _timed(ctx, 'pack', fq.pack, pack_params(dec))
+    cols = _timed(ctx, 'qname_encode', fq.qname_encode, column_specs(columns))
     if stages is not None:
         stages.update(stats=st, dec=dec, columns=columns, dna=dna, qual=qual, cols=cols, prefix=prefix, suffix=suffix,
                       separators=separators, total=n)
