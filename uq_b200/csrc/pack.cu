@@ -9,6 +9,7 @@
 // assembles the (at most 8/bits + 1) symbols that overlap it.  The symbol LUTs live in shared
 // memory.  Output rows are contiguous, so a warp stores runs of consecutive bytes.
 #include "common.cuh"
+#include "tile.cuh"
 
 #define PK_THREADS 256
 
@@ -85,6 +86,113 @@ __global__ void __launch_bounds__(PK_THREADS) k_pack_rows(const uint8_t* __restr
     }
 }
 
+// ================================================================================================
+// v2 (fixed-length reads): record tiles in shared memory (tile.cuh).  One work item = 16 consecutive
+// positions of one read: the thread maps the 16 bases and qualities through the shared-memory LUTs,
+// builds their bit strings most-significant-bit first and ORs them into the tile's output staging
+// area, which holds the packed rows as big-endian 32-bit words.  The staging area is then written out
+// with 128-bit stores: a tile of TL_R = 128 rows starts at a multiple of 16 bytes in both tables.
+// ================================================================================================
+#define PKT_THREADS 256
+#define PKT_STAGE_MAX (64 * 1024)
+
+struct pkt_lut { uint16_t base[256]; uint8_t qual[256]; };      // base: low byte = code, high byte = N-trick quality code or 0xFF
+
+// append `nbits` (<= 32) bits, given right-aligned in `v`, at bit position `gbit` of a big-endian word array
+__device__ __forceinline__ void or_bits(uint32_t* words, uint32_t gbit, uint32_t v, uint32_t nbits) {
+    const uint32_t w = gbit >> 5, o = gbit & 31u;
+    if (o + nbits <= 32u) {
+        atomicOr(&words[w], v << (32u - o - nbits));
+    } else {
+        const uint32_t lo_bits = o + nbits - 32u;
+        atomicOr(&words[w], v >> lo_bits);
+        atomicOr(&words[w + 1], v << (32u - lo_bits));
+    }
+}
+
+__global__ void __launch_bounds__(PKT_THREADS) k_pack_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
+                                                           const uint64_t* __restrict__ line_off, uint64_t n_reads, pack_lut lut_in,
+                                                           uint32_t bb, uint32_t bq, uint32_t wd, uint32_t wq, uint32_t L,
+                                                           uint8_t* __restrict__ dna_out, uint8_t* __restrict__ qual_out,
+                                                           unsigned int* __restrict__ fallback) {
+    extern __shared__ __align__(128) uint8_t pkt_raw[];
+    tile_smem* T = reinterpret_cast<tile_smem*>(pkt_raw);
+    pkt_lut* lut = reinterpret_cast<pkt_lut*>(pkt_raw + sizeof(tile_smem));
+    uint32_t* stage_d = reinterpret_cast<uint32_t*>(pkt_raw + sizeof(tile_smem) + sizeof(pkt_lut));
+    const uint32_t words_d = (TL_R * wd + 3) / 4 + 4, words_q = (TL_R * wq + 3) / 4 + 4;
+    uint32_t* stage_q = stage_d + ((words_d + 3) & ~3u);
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid; i < 256; i += PKT_THREADS) {
+        const int t = lut_in.trick_qual[i];
+        lut->base[i] = (uint16_t)(lut_in.base_code[i] | ((t >= 0 ? (unsigned)t : 0xFFu) << 8));
+        lut->qual[i] = lut_in.qual_code[i];
+    }
+    tile_init(T);
+    __syncthreads();
+    const uint32_t pad_d = wd * 8u - L * bb, pad_q = wq * 8u - L * bq;
+    const uint32_t chunks = (L + 15) / 16;
+    const uint64_t ntiles = (n_reads + TL_R - 1) / TL_R;
+    unsigned phase = 0;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t r0 = t * TL_R, r1 = (r0 + TL_R < n_reads) ? r0 + TL_R : n_reads;
+        uint64_t a0;
+        const uint32_t nrec = tile_load(T, d, n_bytes, line_off, r0, r1, phase, &a0);
+        if (!nrec) { if (tid == 0) atomicOr(fallback, 1u); continue; }
+        phase ^= 1u;
+        for (uint32_t i = tid; i < words_d; i += PKT_THREADS) stage_d[i] = 0;
+        for (uint32_t i = tid; i < words_q; i += PKT_THREADS) stage_q[i] = 0;
+        __syncthreads();
+        for (uint32_t item = tid; item < nrec * chunks; item += PKT_THREADS) {
+            const uint32_t i = item / chunks, c = item - i * chunks;
+            const uint32_t o1 = T->loff[4 * i + 1], o2 = T->loff[4 * i + 2], o3 = T->loff[4 * i + 3];
+            if (o2 - o1 - 1 != L) { atomicOr(fallback, 2u); continue; }      // not a fixed-length file after all
+            const uint8_t* dna = T->bytes + o1;
+            const uint8_t* qual = T->bytes + o3;
+            const uint32_t p0 = c * 16, p1 = (p0 + 16 < L) ? p0 + 16 : L;
+            uint32_t gd = (i * wd) * 8u + pad_d + p0 * bb;      // bit position in the tile's DNA staging area
+            uint32_t gq = (i * wq) * 8u + pad_q + p0 * bq;
+            uint32_t accd = 0, nd = 0, accq = 0, nq = 0;
+            for (uint32_t p = p0; p < p1; p++) {
+                const uint32_t be = lut->base[dna[p]];
+                const uint32_t cd = be & 0xFFu, tq = be >> 8;
+                const uint32_t cq = tq != 0xFFu ? tq : lut->qual[qual[p]];
+                if (nd + bb > 32u) { or_bits(stage_d, gd, accd, nd); gd += nd; accd = 0; nd = 0; }
+                accd = (accd << bb) | cd; nd += bb;
+                if (nq + bq > 32u) { or_bits(stage_q, gq, accq, nq); gq += nq; accq = 0; nq = 0; }
+                accq = (accq << bq) | cq; nq += bq;
+            }
+            if (nd) or_bits(stage_d, gd, accd, nd);
+            if (nq) or_bits(stage_q, gq, accq, nq);
+        }
+        __syncthreads();
+        // staging (big-endian words) -> global bytes
+        {
+            const uint64_t out0 = r0 * wd, nb = (uint64_t)nrec * wd;
+            const uint32_t vec = (uint32_t)(nb / 16);
+            uint4* o = reinterpret_cast<uint4*>(dna_out + out0);
+            for (uint32_t v = tid; v < vec; v += PKT_THREADS) {
+                uint4 x;
+                x.x = __byte_perm(stage_d[4 * v], 0, 0x0123); x.y = __byte_perm(stage_d[4 * v + 1], 0, 0x0123);
+                x.z = __byte_perm(stage_d[4 * v + 2], 0, 0x0123); x.w = __byte_perm(stage_d[4 * v + 3], 0, 0x0123);
+                o[v] = x;
+            }
+            for (uint32_t b = vec * 16 + tid; b < nb; b += PKT_THREADS) dna_out[out0 + b] = (uint8_t)(stage_d[b >> 2] >> (24 - 8 * (b & 3u)));
+        }
+        {
+            const uint64_t out0 = r0 * wq, nb = (uint64_t)nrec * wq;
+            const uint32_t vec = (uint32_t)(nb / 16);
+            uint4* o = reinterpret_cast<uint4*>(qual_out + out0);
+            for (uint32_t v = tid; v < vec; v += PKT_THREADS) {
+                uint4 x;
+                x.x = __byte_perm(stage_q[4 * v], 0, 0x0123); x.y = __byte_perm(stage_q[4 * v + 1], 0, 0x0123);
+                x.z = __byte_perm(stage_q[4 * v + 2], 0, 0x0123); x.w = __byte_perm(stage_q[4 * v + 3], 0, 0x0123);
+                o[v] = x;
+            }
+            for (uint32_t b = vec * 16 + tid; b < nb; b += PKT_THREADS) qual_out[out0 + b] = (uint8_t)(stage_q[b >> 2] >> (24 - 8 * (b & 3u)));
+        }
+    }
+}
+
 extern "C" int uqb_pack(uqb_ctx* ctx, uqb_fastq* fq, const uqb_pack_params* p, uqb_array** dna, uqb_array** qual) {
     if (!fq->line_off) return uqb_fail(ctx, "uqb_pack: call uqb_split first");
     if (p->bits_per_base < 1 || p->bits_per_base > 8 || p->bits_per_quality < 1 || p->bits_per_quality > 8)
@@ -107,11 +215,34 @@ extern "C" int uqb_pack(uqb_ctx* ctx, uqb_fastq* fq, const uqb_pack_params* p, u
     memcpy(lut.base_code, p->base_code, 256);
     memcpy(lut.qual_code, p->qual_code, 256);
     memcpy(lut.trick_qual, p->trick_qual, 512);
+    // algorithmic bytes: base + quality bytes in, 4 line offsets per record in, both packed tables out
+    const uint64_t abytes = 2 * fq->total_bases + 32 * N + N * ((uint64_t)p->dna_bytes + p->qual_bytes);
+    // v2: shared-memory record tiles for fixed-length reads that fit
+    const size_t stage_bytes = (size_t)((((TL_R * p->dna_bytes + 3) / 4 + 4 + 3) & ~3u) + (TL_R * p->qual_bytes + 3) / 4 + 4) * 4;
+    bool trick_ok = true;                       // 0xFF marks "no trick" in the packed LUT
+    for (int i = 0; i < 256; i++) if (p->trick_qual[i] >= 255) trick_ok = false;
+    if (!p->variable && trick_ok && fq->n / N <= (TL_CAP - 64) / TL_R && stage_bytes <= PKT_STAGE_MAX && p->dna_max > 0) {
+        unsigned int* d_fb;
+        UQB_TRY(uqb_dalloc_t(ctx, &d_fb, 1));
+        UQB_CUDA(cudaMemsetAsync(d_fb, 0, 4, ctx->stream));
+        const size_t smem = sizeof(tile_smem) + sizeof(pkt_lut) + stage_bytes;
+        UQB_CUDA(cudaFuncSetAttribute(k_pack_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint64_t ntiles = (N + TL_R - 1) / TL_R;
+        const unsigned per_sm = (unsigned)(220 * 1024 / (smem + 1024)) ? (unsigned)(220 * 1024 / (smem + 1024)) : 1u;
+        const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
+        UQB_LAUNCH_B(abytes, k_pack_tiles, (unsigned)(ntiles < cap ? ntiles : cap), PKT_THREADS, smem, fq->d, fq->n, fq->line_off, N, lut,
+                     p->bits_per_base, p->bits_per_quality, p->dna_bytes, p->qual_bytes, p->dna_max,
+                     (uint8_t*)(*dna)->d, (uint8_t*)(*qual)->d, d_fb);
+        unsigned int fb = 0;
+        UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
+        UQB_TRY(uqb_dfree(ctx, d_fb, 4));
+        if (fb == 0) return 0;
+        if (fb & 2u) return uqb_fail(ctx, "uqb_pack: a record is not dna_max long although variable == 0");
+        // a tile did not fit: fall through to the direct-from-global kernel
+    }
     unsigned long long* d_err;
     UQB_TRY(uqb_dalloc_t(ctx, &d_err, 1));
     UQB_CUDA(cudaMemsetAsync(d_err, 0xFF, 8, ctx->stream));
-    // algorithmic bytes: base + quality bytes in, 4 line offsets per record in, both packed tables out
-    const uint64_t abytes = 2 * fq->total_bases + 32 * N + N * ((uint64_t)p->dna_bytes + p->qual_bytes);
     UQB_LAUNCH_B(abytes, k_pack_rows, uqb_grid(ctx, N, PK_THREADS / 32, 16), PK_THREADS, 0, fq->d, fq->line_off, N, lut,
                p->bits_per_base, p->bits_per_quality, p->dna_bytes, p->qual_bytes, p->variable, p->dna_max,
                (uint8_t*)(*dna)->d, (uint8_t*)(*qual)->d, d_err);

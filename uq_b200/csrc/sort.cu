@@ -35,15 +35,16 @@ __global__ void __launch_bounds__(ST) k_headpos(const uint32_t* __restrict__ hea
     uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
     if (p >= n) return;
     if (head[p]) headpos[excl[p]] = (uint32_t)p;
+    if (p == n - 1) headpos[excl[p] + head[p]] = (uint32_t)n;      // sentinel: headpos[number of groups] = n
 }
 
 // a non-head member that differs from its group's first row in bytes [off, width) marks the group
 __global__ void __launch_bounds__(ST) k_group_diff(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
                                                   const uint32_t* __restrict__ perm, const uint32_t* __restrict__ head,
                                                   const uint32_t* __restrict__ excl, const uint32_t* __restrict__ headpos,
-                                                  uint64_t n, uint32_t* __restrict__ gdiff) {
+                                                  const uint8_t* __restrict__ done, uint64_t n, uint32_t* __restrict__ gdiff) {
     uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
-    if (p >= n || head[p]) return;
+    if (p >= n || head[p] || done[p]) return;
     uint32_t g = excl[p] - 1;           // inclusive scan - 1 with head[p] == 0
     if (gdiff[g]) return;
     const uint8_t* a = rows + (uint64_t)perm[p] * width + off;
@@ -54,12 +55,102 @@ __global__ void __launch_bounds__(ST) k_group_diff(const uint8_t* __restrict__ r
 }
 
 __global__ void __launch_bounds__(ST) k_active_flags(const uint32_t* __restrict__ head, const uint32_t* __restrict__ excl,
-                                                    const uint32_t* __restrict__ gdiff, uint64_t n, uint32_t* __restrict__ act) {
+                                                    const uint32_t* __restrict__ gdiff, const uint8_t* __restrict__ done,
+                                                    uint64_t n, uint32_t* __restrict__ act) {
     uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
     if (p >= n) return;
+    if (done[p]) { act[p] = 0u; return; }       // finished by k_small_groups (its excl / head may be stale)
     uint32_t g = excl[p] + head[p] - 1;
     bool single = head[p] && (p + 1 == n || head[p + 1]);
     act[p] = (!single && gdiff[g]) ? 1u : 0u;
+}
+
+// ---- small tie groups: finished in one pass ------------------------------------------------------
+// After round 0 almost every tie group is small.  A group of 2..32 rows is sorted completely by one
+// warp: lane i holds row i of the group, the remaining bytes [off, width) of the rows are staged in
+// shared memory as big-endian words (so an unsigned word compare is memcmp order), every lane ranks
+// its row against the others (ties keep the current = input order), and the permutation and the
+// group heads are rewritten in place.  Rows wider than SG_STAGE_BYTES are compared straight from
+// global memory instead.  Groups larger than 32 rows are left to the radix rounds; their total row
+// count is returned so that the host can stop as soon as there are none.
+#define SG_MAX 32
+#define SG_STAGE_BYTES 256
+
+template <bool STAGED>
+__global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
+                                                    uint32_t* __restrict__ perm, uint32_t* __restrict__ head, uint8_t* __restrict__ done,
+                                                    const uint32_t* __restrict__ headpos, const uint32_t* __restrict__ d_ngroups,
+                                                    uint32_t pitch, unsigned long long* __restrict__ large_rows) {
+    extern __shared__ uint32_t sg_smem[];
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    uint32_t* srows = sg_smem + (size_t)w * SG_MAX * pitch;
+    const uint32_t G = *d_ngroups;
+    const uint32_t rem = width - off;
+    const uint64_t warps_total = (uint64_t)gridDim.x * (ST / 32);
+    unsigned long long my_large = 0;
+    for (uint64_t g0 = ((uint64_t)blockIdx.x * (ST / 32) + w) * 32; g0 < G; g0 += warps_total * 32) {
+        const uint64_t g = g0 + lane;
+        uint32_t start = 0, size = 0;
+        if (g < G) { start = headpos[g]; size = headpos[g + 1] - start; }
+        const bool fin = size >= 2 && done[start];
+        if (size > SG_MAX && !fin) my_large += size;
+        unsigned need = __ballot_sync(0xffffffffu, size >= 2 && size <= SG_MAX && !fin);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const uint32_t s = __shfl_sync(0xffffffffu, start, src), sz = __shfl_sync(0xffffffffu, size, src);
+            const uint32_t r = lane < sz ? perm[s + lane] : 0u;
+            if (STAGED) {
+                for (uint32_t j = 0; j < sz; j++) {
+                    const uint32_t rj = __shfl_sync(0xffffffffu, r, j);
+                    const uint8_t* src_row = rows + (uint64_t)rj * width + off;
+                    for (uint32_t wd = lane; wd < pitch; wd += 32) {
+                        uint32_t v = 0;
+#pragma unroll
+                        for (uint32_t b = 0; b < 4; b++) {
+                            const uint32_t idx = wd * 4 + b;
+                            v = (v << 8) | (idx < rem ? (uint32_t)__ldg(src_row + idx) : 0u);
+                        }
+                        srows[j * pitch + wd] = v;
+                    }
+                }
+                __syncwarp();
+            }
+            uint32_t rank = 0;
+            bool eq_before = false;
+            for (uint32_t j = 0; j < sz; j++) {
+                const uint32_t rj = __shfl_sync(0xffffffffu, r, j);
+                if (lane < sz && j != lane) {
+                    int c = 0;       // memcmp(row_j, row_lane)
+                    if (STAGED) {
+                        for (uint32_t wd = 0; wd < pitch; wd++) {
+                            const uint32_t a = srows[j * pitch + wd], b = srows[lane * pitch + wd];
+                            if (a != b) { c = a < b ? -1 : 1; break; }
+                        }
+                    } else {
+                        const uint8_t* pa = rows + (uint64_t)rj * width + off;
+                        const uint8_t* pb = rows + (uint64_t)r * width + off;
+                        for (uint32_t i = 0; i < rem; i++) {
+                            const unsigned a = __ldg(pa + i), b = __ldg(pb + i);
+                            if (a != b) { c = a < b ? -1 : 1; break; }
+                        }
+                    }
+                    if (c < 0 || (c == 0 && j < lane)) rank++;
+                    if (c == 0 && j < lane) eq_before = true;
+                }
+            }
+            __syncwarp();
+            if (lane < sz) {
+                perm[s + rank] = r;
+                if (rank > 0) head[s + rank] = eq_before ? 0u : 1u;
+                done[s + lane] = 1;
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_large += __shfl_xor_sync(0xffffffffu, my_large, o);
+    if (lane == 0 && my_large) atomicAdd(large_rows, my_large);
 }
 
 __global__ void __launch_bounds__(ST) k_compact_active(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
@@ -133,22 +224,46 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
     const uint32_t nchunks = (width + 7) / 8;
     if (nchunks > 1) {
         uint32_t *headpos, *gdiff, *act, *apos;
-        UQB_TRY(uqb_dalloc_t(ctx, &headpos, n));
+        uint8_t* done;
+        unsigned long long* d_large;
+        UQB_TRY(uqb_dalloc_t(ctx, &headpos, n + 1));
         UQB_TRY(uqb_dalloc_t(ctx, &gdiff, n));
         UQB_TRY(uqb_dalloc_t(ctx, &act, n));
         UQB_TRY(uqb_dalloc_t(ctx, &apos, n));
+        UQB_TRY(uqb_dalloc_t(ctx, &done, n));
+        UQB_TRY(uqb_dalloc_t(ctx, &d_large, 1));
+        UQB_CUDA(cudaMemsetAsync(done, 0, n, ctx->stream));
+        auto k_small_groups_smem = k_small_groups<true>;
+        auto k_small_groups_gmem = k_small_groups<false>;
         for (uint32_t c = 1; c < nchunks; c++) {
             const uint32_t off = 8 * c;
             UQB_TRY(uqb_scan_u32(ctx, head, excl, n, d_tot));
             UQB_LAUNCH(k_headpos, nb, ST, 0, head, excl, n, headpos);
+            // small tie groups are finished right here
+            UQB_CUDA(cudaMemsetAsync(d_large, 0, 8, ctx->stream));
+            const uint32_t rem = width - off;
+            const unsigned sg_grid = uqb_grid(ctx, n, ST, 16);
+            if (rem <= SG_STAGE_BYTES) {
+                uint32_t pitch = (rem + 3) / 4;
+                if (!(pitch & 1u)) pitch++;                       // odd pitch: conflict-free row-strided reads
+                const size_t smem = (size_t)(ST / 32) * SG_MAX * pitch * 4;
+                UQB_CUDA(cudaFuncSetAttribute(k_small_groups_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                UQB_LAUNCH(k_small_groups_smem, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
+            } else {
+                UQB_LAUNCH(k_small_groups_gmem, sg_grid, ST, 0, rows, width, off, perm, head, done, headpos, d_tot, 1u, d_large);
+            }
+            unsigned long long large = 0;
+            UQB_TRY(uqb_readback(ctx, &large, d_large, 8));
+            if (large == 0) break;                                 // no tie group of more than 32 rows is left
+            // large tie groups: all-equal check, then one more 8-byte radix round over the still active rows
             UQB_CUDA(cudaMemsetAsync(gdiff, 0, n * 4, ctx->stream));
-            UQB_LAUNCH(k_group_diff, nb, ST, 0, rows, width, off, perm, head, excl, headpos, n, gdiff);
-            UQB_LAUNCH(k_active_flags, nb, ST, 0, head, excl, gdiff, n, act);
+            UQB_LAUNCH(k_group_diff, nb, ST, 0, rows, width, off, perm, head, excl, headpos, done, n, gdiff);
+            UQB_LAUNCH(k_active_flags, nb, ST, 0, head, excl, gdiff, done, n, act);
             UQB_TRY(uqb_scan_u32(ctx, act, apos, n, d_tot + 1));
             uint32_t tot[2];
             UQB_TRY(uqb_readback(ctx, tot, d_tot, 8));
             const uint64_t m = tot[1];
-            if (tot[0] == n || m == 0) break;      // every row is its own group, or only identical rows remain tied
+            if (m == 0) break;                                     // only identical rows remain tied
             uqb_sortbuf sb;
             uint32_t* pos_list;
             UQB_TRY(uqb_sortbuf_alloc(ctx, &sb, m, true));
@@ -159,10 +274,12 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
             UQB_TRY(uqb_dfree(ctx, pos_list, m * 4));
             UQB_TRY(uqb_sortbuf_free(ctx, &sb));
         }
-        UQB_TRY(uqb_dfree(ctx, headpos, n * 4));
+        UQB_TRY(uqb_dfree(ctx, headpos, (n + 1) * 4));
         UQB_TRY(uqb_dfree(ctx, gdiff, n * 4));
         UQB_TRY(uqb_dfree(ctx, act, n * 4));
         UQB_TRY(uqb_dfree(ctx, apos, n * 4));
+        UQB_TRY(uqb_dfree(ctx, done, n));
+        UQB_TRY(uqb_dfree(ctx, d_large, 8));
     }
     // ---- group ids in sorted order ----
     UQB_TRY(uqb_scan_u32(ctx, head, excl, n, d_tot));
@@ -205,6 +322,26 @@ __global__ void __launch_bounds__(ST) k_gather_rows(const uint8_t* __restrict__ 
     }
 }
 
+// narrow rows (1, 2, 4, 8 bytes): one thread per row, typed loads
+template <typename T>
+__global__ void __launch_bounds__(ST) k_gather_items(const T* __restrict__ table, const uint32_t* __restrict__ idx, uint64_t n, T* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * ST + threadIdx.x; i < n; i += (uint64_t)gridDim.x * ST) out[i] = table[idx[i]];
+}
+
+static int gather_rows_impl(uqb_ctx* ctx, const void* table, uint32_t width, const uint32_t* idx, uint64_t n, void* out) {
+    if (n == 0 || width == 0) return 0;
+    const uint64_t ab = n * (2 * (uint64_t)width + 4);
+    const unsigned g = uqb_grid(ctx, n, ST, 16);
+    switch (width) {
+        case 1: UQB_LAUNCH_B(ab, k_gather_items<uint8_t>, g, ST, 0, (const uint8_t*)table, idx, n, (uint8_t*)out); return 0;
+        case 2: UQB_LAUNCH_B(ab, k_gather_items<uint16_t>, g, ST, 0, (const uint16_t*)table, idx, n, (uint16_t*)out); return 0;
+        case 4: UQB_LAUNCH_B(ab, k_gather_items<uint32_t>, g, ST, 0, (const uint32_t*)table, idx, n, (uint32_t*)out); return 0;
+        case 8: UQB_LAUNCH_B(ab, k_gather_items<uint64_t>, g, ST, 0, (const uint64_t*)table, idx, n, (uint64_t*)out); return 0;
+    }
+    UQB_LAUNCH_B(ab, k_gather_rows, uqb_grid(ctx, n, ST / 32, 16), ST, 0, (const uint8_t*)table, width, idx, n, (uint8_t*)out);
+    return 0;
+}
+
 extern "C" int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** perm, uqb_array** key,
                              uqb_array** uniq, uint64_t* n_unique) {
     uint32_t *d_perm, *d_gid;
@@ -223,7 +360,7 @@ extern "C" int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** p
             uint32_t* first_row;
             UQB_TRY(uqb_dalloc_t(ctx, &first_row, u));
             UQB_LAUNCH(k_first_of_group, nb, ST, 0, d_perm, d_gid, n, first_row);
-            UQB_LAUNCH_B(u * (2 * (uint64_t)table->width + 4), k_gather_rows, uqb_grid(ctx, u, ST / 32, 16), ST, 0, (const uint8_t*)table->d, table->width, first_row, u, (uint8_t*)(*uniq)->d);
+            UQB_TRY(gather_rows_impl(ctx, table->d, table->width, first_row, u, (*uniq)->d));
             UQB_TRY(uqb_dfree(ctx, first_row, u * 4));
         }
     }
@@ -239,8 +376,7 @@ extern "C" int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** p
 extern "C" int uqb_gather_rows(uqb_ctx* ctx, const uqb_array* table, const uqb_array* perm, uqb_array** out) {
     if (perm->width != 4) return uqb_fail(ctx, "gather_rows: index array must be uint32");
     UQB_TRY(uqb_new_array(ctx, perm->n, table->width, out));
-    if (perm->n && table->width)
-        UQB_LAUNCH_B(perm->n * (2 * (uint64_t)table->width + 4), k_gather_rows, uqb_grid(ctx, perm->n, ST / 32, 16), ST, 0, (const uint8_t*)table->d, table->width, (const uint32_t*)perm->d, perm->n, (uint8_t*)(*out)->d);
+    UQB_TRY(gather_rows_impl(ctx, table->d, table->width, (const uint32_t*)perm->d, perm->n, (*out)->d));
     return 0;
 }
 
