@@ -162,11 +162,12 @@ int uqb_pack(uqb_ctx* ctx, uqb_fastq* fq, const uqb_pack_params* p, uqb_array** 
 /* ---- stage 3: sort / unique (replaces numpy.argsort / numpy.unique / fancy indexing in
  *      encode_dna_qual uq.py:765-805 and encode_qname uq.py:808-851) -------------------------- */
 /* Stable sort of the rows of `table` in memcmp order.  Any of the outputs may be NULL.
- *   perm  : uint32[n]  stable argsort                       (numpy.argsort(kind='stable'))
- *   key   : uint32[n]  index of each row in the unique table (numpy.unique return_inverse)
- *   uniq  : [n_unique][width] distinct rows ascending        (numpy.unique)               */
+ *   perm       : uint32[n]  stable argsort                        (numpy.argsort(kind='stable'))
+ *   key        : uint32[n]  index of each row in the unique table  (numpy.unique return_inverse)
+ *   key_sorted : uint32[n]  key[perm], i.e. the key in sorted order (key[argsort(key)], uq.py:796-798)
+ *   uniq       : [n_unique][width] distinct rows ascending         (numpy.unique)               */
 int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** perm, uqb_array** key,
-                  uqb_array** uniq, uint64_t* n_unique);
+                  uqb_array** key_sorted, uqb_array** uniq, uint64_t* n_unique);
 int uqb_gather_rows(uqb_ctx* ctx, const uqb_array* table, const uqb_array* perm, uqb_array** out); /* out[i] = table[perm[i]] */
 /* uint32 -> little-endian integer of itemsize bytes (key.astype(min_scalar_type(max)), uq.py:790) */
 int uqb_narrow_u32(uqb_ctx* ctx, const uqb_array* a, uint32_t itemsize, uqb_array** out);

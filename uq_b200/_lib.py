@@ -104,7 +104,7 @@ SIGNATURES = {
     "uqb_qname_dict": (C.c_int, [P, P, C.c_uint32, P, C.c_uint64]),
     "uqb_qname_encode": (C.c_int, [P, P, C.c_uint32, C.POINTER(ColSpec), PP]),
     "uqb_pack": (C.c_int, [P, P, C.POINTER(PackParams), PP, PP]),
-    "uqb_sort_rows": (C.c_int, [P, P, PP, PP, PP, C.POINTER(C.c_uint64)]),
+    "uqb_sort_rows": (C.c_int, [P, P, PP, PP, PP, PP, C.POINTER(C.c_uint64)]),
     "uqb_gather_rows": (C.c_int, [P, P, P, PP]),
     "uqb_narrow_u32": (C.c_int, [P, P, C.c_uint32, PP]),
     "uqb_columns_to_rows": (C.c_int, [P, C.c_uint32, PP, PP]),

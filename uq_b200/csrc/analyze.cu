@@ -357,30 +357,46 @@ __global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __re
     if (tid < (unsigned)nslots && S->last_mis[tid]) atomicMax(&s->last_count_mismatch[S->slot_char[tid]], (long long)S->last_mis[tid] - 1);
 }
 
-// base / quality histograms from record tiles.  Private packed 8-bit counters as in k_pair_hist, for
-// byte values 32..127 (24 words per thread and table); anything else takes the global-atomic path.
+// base / quality histograms from record tiles.  Private packed 8-bit counters per thread (word w of a
+// thread holds the counters of byte values 32+4w .. 32+4w+3; layout [word][thread] is bank-conflict
+// free), updated branch-free: values outside 32..127 are clamped to a dummy counter that the host
+// reads as "fall back to the generic kernels", inactive lanes to a second dummy.  The counters are
+// flushed every 254 warp iterations through a warp-shuffle reduction (pt_flush).
 #define PT_THREADS 256
-#define PT_WORDS 24
+#define PT_WORDS 25
 #define PT_LO 32u
+#define PT_OOR 96u           // clamped index of out-of-range bytes  -> histogram slot 128
+#define PT_IDLE 97u          // index used by inactive lanes          -> histogram slot 129
 
 struct pt_smem {
     tile_smem T;
     unsigned priv_b[PT_WORDS * PT_THREADS];
     unsigned priv_q[PT_WORDS * PT_THREADS];
-    unsigned hist_b[256], hist_q[256];
-    int first_q[256], multi[256];
+    unsigned hist_b[PT_LO + 4 * PT_WORDS], hist_q[PT_LO + 4 * PT_WORDS];
+    int state[256];                 // per base byte: -1 unseen, 0..255 its only quality so far, 256 = several
 };
 
+// Flush of the private counters of one warp: the four 8-bit fields of a word are widened to two words
+// of two 16-bit fields (32 lanes x 255 < 65536), summed across the warp with shuffles, and lane 0 adds
+// the four sums to the CTA histogram.  Must be called by all 32 lanes.
 __device__ __forceinline__ void pt_flush(unsigned* priv, unsigned* blk_hist, unsigned tid) {
-#pragma unroll 4
+    const unsigned lane = tid & 31u;
+#pragma unroll 5
     for (int w = 0; w < PT_WORDS; w++) {
         const unsigned x = priv[w * PT_THREADS + tid];
-        if (x) {
-            priv[w * PT_THREADS + tid] = 0;
+        priv[w * PT_THREADS + tid] = 0;
+        unsigned e = x & 0x00FF00FFu, o = (x >> 8) & 0x00FF00FFu;       // fields 0,2 and 1,3
+        if (__any_sync(0xffffffffu, x != 0u)) {
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const unsigned c = (x >> (8 * b)) & 255u;
-                if (c) atomicAdd(&blk_hist[PT_LO + 4 * w + b], c);
+            for (int sh = 16; sh > 0; sh >>= 1) {
+                e += __shfl_xor_sync(0xffffffffu, e, sh);
+                o += __shfl_xor_sync(0xffffffffu, o, sh);
+            }
+            if (lane == 0) {
+                if (e & 0xFFFFu) atomicAdd(&blk_hist[PT_LO + 4 * w + 0], e & 0xFFFFu);
+                if (o & 0xFFFFu) atomicAdd(&blk_hist[PT_LO + 4 * w + 1], o & 0xFFFFu);
+                if (e >> 16) atomicAdd(&blk_hist[PT_LO + 4 * w + 2], e >> 16);
+                if (o >> 16) atomicAdd(&blk_hist[PT_LO + 4 * w + 3], o >> 16);
             }
         }
     }
@@ -393,9 +409,12 @@ __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* _
     pt_smem* S = reinterpret_cast<pt_smem*>(pt_raw);
     const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     for (unsigned i = tid; i < PT_WORDS * PT_THREADS; i += PT_THREADS) { S->priv_b[i] = 0; S->priv_q[i] = 0; }
-    S->hist_b[tid] = 0; S->hist_q[tid] = 0; S->first_q[tid] = -1; S->multi[tid] = 0;
+    for (unsigned i = tid; i < PT_LO + 4 * PT_WORDS; i += PT_THREADS) { S->hist_b[i] = 0; S->hist_q[i] = 0; }
+    S->state[tid] = -1;
     tile_init(&S->T);
     __syncthreads();
+    unsigned* const pb = S->priv_b + tid;
+    unsigned* const pq = S->priv_q + tid;
     const uint64_t ntiles = (n_reads + TL_R - 1) / TL_R;
     unsigned phase = 0, since_flush = 0;
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -408,29 +427,50 @@ __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* _
             const uint32_t o1 = S->T.loff[4 * i + 1], o2 = S->T.loff[4 * i + 2], o3 = S->T.loff[4 * i + 3], o4 = S->T.loff[4 * i + 4];
             uint32_t len = o2 - o1 - 1;
             const uint32_t qlen = o4 - o3 - 1;
-            if (qlen < len) len = qlen;
-            const uint8_t* dna = S->T.bytes + o1;
-            const uint8_t* qual = S->T.bytes + o3;
-            for (uint32_t p = lane; p < len; p += 32) {
-                const unsigned b = dna[p], q = qual[p];
-                const unsigned bi = b - PT_LO, qi = q - PT_LO;
-                if (bi < 4u * PT_WORDS) S->priv_b[(bi >> 2) * PT_THREADS + tid] += 1u << (8 * (bi & 3u));
-                else atomicAdd(&s->base_count[b], 1ull);
-                if (qi < 4u * PT_WORDS) S->priv_q[(qi >> 2) * PT_THREADS + tid] += 1u << (8 * (qi & 3u));
-                else atomicAdd(&s->qual_count[q], 1ull);
-                const int f = S->first_q[b];
-                if (f != (int)q) {
-                    if (f < 0) {
-                        const int old = atomicCAS(&S->first_q[b], -1, (int)q);
-                        if (old >= 0 && old != (int)q) S->multi[b] = 1;
-                    } else {
-                        S->multi[b] = 1;
+            if (qlen < len) len = qlen;            // malformed records are reported by the record-stats kernel
+            const uint8_t* dna = S->T.bytes + o1 + lane;
+            const uint8_t* qual = S->T.bytes + o3 + lane;
+            const uint32_t iters = (len + 31) >> 5;
+            if (since_flush + iters > 254u) {      // warp-uniform; a counter is bumped at most once per iteration
+                pt_flush(S->priv_b, S->hist_b, tid);
+                pt_flush(S->priv_q, S->hist_q, tid);
+                since_flush = 0;
+            }
+            since_flush += iters;
+            if (iters > 254u) {                    // a single read longer than 254*32 bases: flush inside the loop
+                for (uint32_t it = 0; it < iters; it++) {
+                    const uint32_t p = it * 32 + lane;
+                    if ((it & 127u) == 127u) { pt_flush(S->priv_b, S->hist_b, tid); pt_flush(S->priv_q, S->hist_q, tid); }
+                    if (p < len) {
+                        const unsigned b = dna[it * 32], q = qual[it * 32];
+                        const unsigned bi = min(b - PT_LO, PT_OOR), qi = min(q - PT_LO, PT_OOR);
+                        pb[(bi >> 2) * PT_THREADS] += 1u << ((bi & 3u) * 8u);
+                        pq[(qi >> 2) * PT_THREADS] += 1u << ((qi & 3u) * 8u);
+                        const int f = S->state[b];
+                        if (f != 256 && f != (int)q) {
+                            if (f < 0) { const int old = atomicCAS(&S->state[b], -1, (int)q); if (old >= 0 && old != (int)q) S->state[b] = 256; }
+                            else S->state[b] = 256;
+                        }
                     }
                 }
-                if (++since_flush == 255u) {
-                    pt_flush(S->priv_b, S->hist_b, tid);
-                    pt_flush(S->priv_q, S->hist_q, tid);
-                    since_flush = 0;
+                since_flush = 255;
+                continue;
+            }
+            for (uint32_t it = 0; it < iters; it++) {
+                const bool act = it * 32 + lane < len;
+                const unsigned b = act ? (unsigned)dna[it * 32] : (PT_LO + PT_IDLE);
+                const unsigned q = act ? (unsigned)qual[it * 32] : (PT_LO + PT_IDLE);
+                const unsigned bi = act ? min(b - PT_LO, PT_OOR) : PT_IDLE, qi = act ? min(q - PT_LO, PT_OOR) : PT_IDLE;
+                pb[(bi >> 2) * PT_THREADS] += 1u << ((bi & 3u) * 8u);
+                pq[(qi >> 2) * PT_THREADS] += 1u << ((qi & 3u) * 8u);
+                const int f = S->state[b];
+                if (act && f != 256 && f != (int)q) {
+                    if (f < 0) {
+                        const int old = atomicCAS(&S->state[b], -1, (int)q);
+                        if (old >= 0 && old != (int)q) S->state[b] = 256;
+                    } else {
+                        S->state[b] = 256;
+                    }
                 }
             }
         }
@@ -438,14 +478,21 @@ __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* _
     pt_flush(S->priv_b, S->hist_b, tid);
     pt_flush(S->priv_q, S->hist_q, tid);
     __syncthreads();
-    if (S->hist_b[tid]) atomicAdd(&s->base_count[tid], (unsigned long long)S->hist_b[tid]);
-    if (S->hist_q[tid]) atomicAdd(&s->qual_count[tid], (unsigned long long)S->hist_q[tid]);
-    const int f = S->first_q[tid];
-    if (f >= 0) {
-        const int old = atomicCAS(&s->first_q[tid], -1, f);
-        if (old >= 0 && old != f) s->multi[tid] = 1;
+    if (tid < 128) {
+        if (S->hist_b[tid]) atomicAdd(&s->base_count[tid], (unsigned long long)S->hist_b[tid]);
+        if (S->hist_q[tid]) atomicAdd(&s->qual_count[tid], (unsigned long long)S->hist_q[tid]);
     }
-    if (S->multi[tid]) s->multi[tid] = 1;
+    if (tid == 0 && (S->hist_b[PT_LO + PT_OOR] | S->hist_q[PT_LO + PT_OOR])) atomicOr(fallback, 1u);
+    const int f = S->state[tid];
+    if (f >= 0) {
+        if (f == 256) {
+            s->multi[tid] = 1;
+            atomicCAS(&s->first_q[tid], -1, 0);                 // mark the base as present
+        } else {
+            const int old = atomicCAS(&s->first_q[tid], -1, f);
+            if (old >= 0 && old != f) s->multi[tid] = 1;
+        }
+    }
 }
 
 extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {

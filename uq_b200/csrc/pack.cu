@@ -110,6 +110,51 @@ __device__ __forceinline__ void or_bits(uint32_t* words, uint32_t gbit, uint32_t
     }
 }
 
+// 16 symbols of BITS bits -> a bit string (first symbol most significant) of NW words, ORed into the
+// staging words at bit position gbit.  Everything but the final placement is compile-time indexed.
+template <int BITS>
+__device__ __forceinline__ void place_chunk16(const uint32_t (&code)[16], uint32_t* stage, uint32_t gbit) {
+    constexpr int NW = (16 * BITS + 31) / 32;
+    uint32_t w[NW + 1];
+#pragma unroll
+    for (int k = 0; k <= NW; k++) w[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int off = k * BITS, wi = off >> 5, o = off & 31;
+        if (o + BITS <= 32) {
+            w[wi] |= code[k] << (32 - o - BITS);
+        } else {
+            w[wi] |= code[k] >> (o + BITS - 32);
+            w[wi + 1] |= code[k] << (64 - o - BITS);
+        }
+    }
+    const uint32_t sh = gbit & 31u, w0 = gbit >> 5;
+    uint32_t prev = 0;
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        const uint32_t out = __funnelshift_r(w[k], prev, sh);
+        if (out) atomicOr(&stage[w0 + k], out);
+        prev = w[k];
+    }
+    if (sh) {
+        const uint32_t out = prev << (32u - sh);
+        if (out) atomicOr(&stage[w0 + NW], out);
+    }
+}
+
+__device__ __forceinline__ void place_chunk16_any(uint32_t bits, const uint32_t (&code)[16], uint32_t* stage, uint32_t gbit) {
+    switch (bits) {          // warp-uniform
+        case 1: place_chunk16<1>(code, stage, gbit); break;
+        case 2: place_chunk16<2>(code, stage, gbit); break;
+        case 3: place_chunk16<3>(code, stage, gbit); break;
+        case 4: place_chunk16<4>(code, stage, gbit); break;
+        case 5: place_chunk16<5>(code, stage, gbit); break;
+        case 6: place_chunk16<6>(code, stage, gbit); break;
+        case 7: place_chunk16<7>(code, stage, gbit); break;
+        default: place_chunk16<8>(code, stage, gbit); break;
+    }
+}
+
 __global__ void __launch_bounds__(PKT_THREADS) k_pack_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
                                                            const uint64_t* __restrict__ line_off, uint64_t n_reads, pack_lut lut_in,
                                                            uint32_t bb, uint32_t bq, uint32_t wd, uint32_t wq, uint32_t L,
@@ -152,15 +197,44 @@ __global__ void __launch_bounds__(PKT_THREADS) k_pack_tiles(const uint8_t* __res
             uint32_t gd = (i * wd) * 8u + pad_d + p0 * bb;      // bit position in the tile's DNA staging area
             uint32_t gq = (i * wq) * 8u + pad_q + p0 * bq;
             uint32_t accd = 0, nd = 0, accq = 0, nq = 0;
-            for (uint32_t p = p0; p < p1; p++) {
-                const uint32_t be = lut->base[dna[p]];
-                const uint32_t cd = be & 0xFFu, tq = be >> 8;
-                const uint32_t cq = tq != 0xFFu ? tq : lut->qual[qual[p]];
-                if (nd + bb > 32u) { or_bits(stage_d, gd, accd, nd); gd += nd; accd = 0; nd = 0; }
-                accd = (accd << bb) | cd; nd += bb;
-                if (nq + bq > 32u) { or_bits(stage_q, gq, accq, nq); gq += nq; accq = 0; nq = 0; }
-                accq = (accq << bq) | cq; nq += bq;
+#define PKT_SYMBOL(BYTE_D, BYTE_Q)                                                              \
+            {                                                                                   \
+                const uint32_t be = lut->base[(BYTE_D)];                                        \
+                const uint32_t cd = be & 0xFFu, tq = be >> 8;                                   \
+                const uint32_t cq = tq != 0xFFu ? tq : lut->qual[(BYTE_Q)];                     \
+                if (nd + bb > 32u) { or_bits(stage_d, gd, accd, nd); gd += nd; accd = 0; nd = 0; } \
+                accd = (accd << bb) | cd; nd += bb;                                             \
+                if (nq + bq > 32u) { or_bits(stage_q, gq, accq, nq); gq += nq; accq = 0; nq = 0; } \
+                accq = (accq << bq) | cq; nq += bq;                                             \
             }
+            if (p1 - p0 == 16) {
+                // full chunk: 2 x 16 bytes through aligned 32-bit shared loads + funnel shifts, fully unrolled
+                uint32_t xd[5], xq[5];
+                const uint32_t ad = o1 + p0, aq = o3 + p0;
+                const uint32_t* wdp = reinterpret_cast<const uint32_t*>(T->bytes + (ad & ~3u));
+                const uint32_t* wqp = reinterpret_cast<const uint32_t*>(T->bytes + (aq & ~3u));
+#pragma unroll
+                for (int k = 0; k < 5; k++) { xd[k] = wdp[k]; xq[k] = wqp[k]; }
+                const uint32_t sd = (ad & 3u) * 8u, sq = (aq & 3u) * 8u;
+                uint32_t cdv[16], cqv[16];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t vd = __funnelshift_r(xd[k], xd[k + 1], sd), vq = __funnelshift_r(xq[k], xq[k + 1], sq);
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const uint32_t be = lut->base[(vd >> (8 * b)) & 0xFFu];
+                        const uint32_t tq = be >> 8;
+                        cdv[4 * k + b] = be & 0xFFu;
+                        cqv[4 * k + b] = tq != 0xFFu ? tq : lut->qual[(vq >> (8 * b)) & 0xFFu];
+                    }
+                }
+                place_chunk16_any(bb, cdv, stage_d, gd);
+                place_chunk16_any(bq, cqv, stage_q, gq);
+                continue;
+            } else {
+                for (uint32_t p = p0; p < p1; p++) PKT_SYMBOL(dna[p], qual[p])
+            }
+#undef PKT_SYMBOL
             if (nd) or_bits(stage_d, gd, accd, nd);
             if (nq) or_bits(stage_q, gq, accq, nq);
         }

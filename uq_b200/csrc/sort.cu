@@ -343,7 +343,7 @@ static int gather_rows_impl(uqb_ctx* ctx, const void* table, uint32_t width, con
 }
 
 extern "C" int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** perm, uqb_array** key,
-                             uqb_array** uniq, uint64_t* n_unique) {
+                             uqb_array** key_sorted, uqb_array** uniq, uint64_t* n_unique) {
     uint32_t *d_perm, *d_gid;
     uint64_t u = 0;
     const uint64_t n = table->n;
@@ -363,6 +363,10 @@ extern "C" int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** p
             UQB_TRY(gather_rows_impl(ctx, table->d, table->width, first_row, u, (*uniq)->d));
             UQB_TRY(uqb_dfree(ctx, first_row, u * 4));
         }
+    }
+    if (key_sorted) {
+        UQB_TRY(uqb_new_array(ctx, n, 4, key_sorted));
+        if (n) UQB_CUDA(cudaMemcpyAsync((*key_sorted)->d, d_gid, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     if (perm) {
         UQB_TRY(uqb_new_array(ctx, n, 4, perm));

@@ -143,13 +143,18 @@ class Context:
         return DeviceArray(self, h)
 
     # ---- stage 3 / 4 ----
-    def sort_rows(self, table, want_perm=False, want_key=False, want_uniq=False):
-        perm, key, uniq = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    def sort_rows(self, table, want_perm=False, want_key=False, want_uniq=False, want_key_sorted=False):
+        """-> (perm, key, uniq, n_unique[, key_sorted])"""
+        perm, key, uniq, ks = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         nu = C.c_uint64()
         self.check(self.lib.uqb_sort_rows(self.h, table.h, C.byref(perm) if want_perm else None,
-                                          C.byref(key) if want_key else None, C.byref(uniq) if want_uniq else None, C.byref(nu)))
-        return (DeviceArray(self, perm) if want_perm else None, DeviceArray(self, key) if want_key else None,
-                DeviceArray(self, uniq) if want_uniq else None, int(nu.value))
+                                          C.byref(key) if want_key else None, C.byref(ks) if want_key_sorted else None,
+                                          C.byref(uniq) if want_uniq else None, C.byref(nu)))
+        out = (DeviceArray(self, perm) if want_perm else None, DeviceArray(self, key) if want_key else None,
+               DeviceArray(self, uniq) if want_uniq else None, int(nu.value))
+        if want_key_sorted:
+            out = out + (DeviceArray(self, ks),)
+        return out
 
     def gather_rows(self, table, perm):
         h = C.c_void_p()

@@ -309,6 +309,28 @@ class DeviceMembers:
         self.items = {}
 
 
+def _layout(ctx, table, pattern):
+    """-> (stream DeviceArray, aliased).  Pattern 0.1 IS the table's own byte order: no kernel, no copy."""
+    if pattern == '0.1':
+        return table, True
+    return ctx.layout(table, pattern), False
+
+
+def _keyed(ctx, table, order):
+    """numpy.unique(return_inverse) + the ordering of the key (uq.py:786-798 / 830-836).
+    -> (key in output order as uint32 DeviceArray, uniq, n_unique, order)"""
+    if order is False:
+        # this table defines the order: key[argsort(key)] is the group id in sorted order
+        perm, _, uniq, nu, key = ctx.sort_rows(table, want_perm=True, want_uniq=True, want_key_sorted=True)
+        return key, uniq, nu, perm
+    _, key, uniq, nu = ctx.sort_rows(table, want_key=True, want_uniq=True)
+    if order is not None:
+        k2 = ctx.gather_rows(key, order)
+        key.free()
+        key = k2
+    return key, uniq, nu, order
+
+
 def _mix_dna_qual(ctx, out, table, name, order, raw, pattern):
     """encode_dna_qual (uq.py:765-805).  order: None / False / DeviceArray(uint32 perm)."""
     if raw:
@@ -317,23 +339,20 @@ def _mix_dna_qual(ctx, out, table, name, order, raw, pattern):
             if order is False:
                 order, _, _, _ = ctx.sort_rows(table, want_perm=True)              # uq.py:775
             src = ctx.gather_rows(table, order)                                    # uq.py:777
-        out.add_table(name + '.raw', ctx.layout(src, pattern), table.n, table.width, pattern)
-        if src is not table:
+        stream, aliased = _layout(ctx, src, pattern)
+        out.add_table(name + '.raw', stream, table.n, table.width, pattern)
+        if src is not table and not aliased:
             src.free()
     else:
-        perm, key, uniq, nu = ctx.sort_rows(table, want_perm=(order is False), want_key=True, want_uniq=True)   # uq.py:786
+        key, uniq, nu, order = _keyed(ctx, table, order)                           # uq.py:786, 796
         size = key_itemsize(nu)
-        if order is not None:
-            if order is False:
-                order = perm                                                       # argsort(key), uq.py:796
-            k2 = ctx.gather_rows(key, order)
-            key.free()
-            key = k2
         narrow = ctx.narrow_u32(key, size)                                         # uq.py:790
         key.free()
         out.add_vector(name + '.key', narrow, 'uint%d' % (8 * size))
-        out.add_table(name, ctx.layout(uniq, pattern), uniq.n, uniq.width, pattern)
-        uniq.free()
+        stream, aliased = _layout(ctx, uniq, pattern)
+        out.add_table(name, stream, uniq.n, uniq.width, pattern)
+        if not aliased:
+            uniq.free()
     return order
 
 
@@ -351,15 +370,9 @@ def _mix_qname(ctx, out, cols, columns, order, raw):
                 out.add_vector(meta['name'] + '.raw', c, meta['dtype'])
     else:
         rows = ctx.columns_to_rows(cols)
-        perm, key, uniq, nu = ctx.sort_rows(rows, want_perm=(order is False), want_key=True, want_uniq=True)    # uq.py:830
+        key, uniq, nu, order = _keyed(ctx, rows, order)                            # uq.py:830, 833
         rows.free()
         size = key_itemsize(nu)
-        if order is False:
-            order = perm                                                           # uq.py:833
-        if order is not None:
-            k2 = ctx.gather_rows(key, order)
-            key.free()
-            key = k2
         narrow = ctx.narrow_u32(key, size)
         key.free()
         out.add_vector('QNAME.key', narrow, 'uint%d' % (8 * size))
