@@ -92,9 +92,8 @@ class ClockSampler:
 
 
 def run_ours(args):
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from uq_b200 import shard
+    rank, local_rank, world = shard.world()
     dist = None
     if world > 1:
         import torch
@@ -103,31 +102,14 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from uq_b200 import host
     from uq_b200.device import Context
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    red = shard.Reducer(dist, "cuda")
+    barrier, max_over_ranks, sum_over_ranks = red.barrier, red.max, red.sum
 
     ctx = Context(local_rank)
     n = args.reads
     pool = max(1, n // 5)
-    dev = ctx.synth("genome", n, READ_LEN, SEED, first=rank * n, genome=GENOME, pool=pool)
+    first, n = shard.shard_range(rank, world, n)
+    dev = ctx.synth("genome", n, READ_LEN, SEED, first=first, genome=GENOME, pool=pool)
     fbytes = dev.nbytes
     opts = dict(sort=SORT, raw=RAW, pattern=PATTERN)
 
