@@ -180,65 +180,101 @@ __global__ void __launch_bounds__(PR_THREADS) k_radix_hist(const uint64_t* __res
     ghist[(uint64_t)threadIdx.x * nblk + blockIdx.x] = hist[threadIdx.x];
 }
 
-// Stable scatter: every warp owns 512 consecutive items of the tile and ranks them 32 at a time
-// with match_any, so the order inside a digit bucket is (CTA, warp, round, lane) = input order.
+// Stable scatter.  Every warp owns 512 consecutive items of the tile and ranks them 32 at a time with
+// match_any, so the order inside a digit bucket is (CTA, warp, round, lane) = input order.  The tile is
+// then re-ordered by digit in shared memory and written out as one contiguous run per digit, which
+// turns 4096 scattered 8/4-byte stores into ~256 coalesced runs (the random-digit passes went from
+// 0.74 TB/s to the speed of the already-clustered passes).
+struct rs_stage {
+    uint32_t whist[PR_THREADS / 32][256];     // per-warp digit counts, then per-warp exclusive prefix
+    uint32_t dstart[256];                     // first tile-local slot of every digit
+    uint32_t gbase[256];                      // first global slot of this CTA's run of every digit
+    uint32_t wtot[PR_THREADS / 32];
+    uint64_t key[PR_TILE];
+    uint32_t val[PR_TILE];
+    uint32_t aux[PR_TILE];
+};
+
 template <bool AUXDIGIT, bool HASAUX>
 __global__ void __launch_bounds__(PR_THREADS) k_radix_scatter(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ ain,
                                                              const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
                                                              uint32_t* __restrict__ aout, uint32_t* __restrict__ vout, uint64_t n,
                                                              int shift, const uint32_t* __restrict__ goff, uint32_t nblk) {
-    __shared__ uint32_t whist[PR_THREADS / 32][256];
-    __shared__ uint32_t wbase[PR_THREADS / 32][256];
+    extern __shared__ __align__(16) uint8_t rs_raw[];
+    rs_stage* S = reinterpret_cast<rs_stage*>(rs_raw);
     const unsigned tid = threadIdx.x, w = tid >> 5, lane = tid & 31u;
-    for (unsigned i = tid; i < (PR_THREADS / 32) * 256; i += PR_THREADS) (&whist[0][0])[i] = 0;
+    for (unsigned i = tid; i < (PR_THREADS / 32) * 256; i += PR_THREADS) (&S->whist[0][0])[i] = 0;
     __syncthreads();
-    const uint64_t warp0 = (uint64_t)blockIdx.x * PR_TILE + (uint64_t)w * (32 * PR_ITEMS);
-    uint64_t k[PR_ITEMS];
-    uint32_t a[PR_ITEMS], v[PR_ITEMS], rk[PR_ITEMS];
+    const uint64_t tile0 = (uint64_t)blockIdx.x * PR_TILE;
+    const uint64_t warp0 = tile0 + (uint64_t)w * (32 * PR_ITEMS);
+    const uint32_t ntile = (uint32_t)((n - tile0 < PR_TILE) ? (n - tile0) : PR_TILE);
+    uint32_t rk[PR_ITEMS];
 #pragma unroll
     for (int j = 0; j < PR_ITEMS; j++) {
-        uint64_t idx = warp0 + (uint64_t)j * 32 + lane;
-        bool valid = idx < n;
-        k[j] = 0; a[j] = 0; v[j] = 0;
-        if (valid) {
-            k[j] = kin[idx];
-            if (HASAUX) a[j] = ain[idx];
-            v[j] = vin[idx];
-        }
+        const uint64_t idx = warp0 + (uint64_t)j * 32 + lane;
+        const bool valid = idx < n;
         uint32_t d = 256u;    // sentinel digit for lanes beyond the end
-        if (valid) d = AUXDIGIT ? ((a[j] >> shift) & 255u) : (uint32_t)((k[j] >> shift) & 255ull);
-        unsigned m = __match_any_sync(0xffffffffu, d);
-        unsigned r = __popc(m & ((1u << lane) - 1u));
-        int leader = __ffs(m) - 1;
+        if (valid) d = AUXDIGIT ? ((ain[idx] >> shift) & 255u) : (uint32_t)((kin[idx] >> shift) & 255ull);
+        const unsigned m = __match_any_sync(0xffffffffu, d);
+        const unsigned r = __popc(m & ((1u << lane) - 1u));
+        const int leader = __ffs(m) - 1;
         uint32_t old = 0;
         if (valid && (int)lane == leader) {
-            old = whist[w][d];
-            whist[w][d] = old + __popc(m);
+            old = S->whist[w][d];
+            S->whist[w][d] = old + __popc(m);
         }
         old = __shfl_sync(0xffffffffu, old, leader);
         rk[j] = (d << 16) | (old + r);     // old + r < 512
         __syncwarp();
     }
     __syncthreads();
+    // digit totals -> per-warp exclusive prefixes, tile-local digit starts (256-wide scan), global bases
     {
-        uint32_t run = goff[(uint64_t)tid * nblk + blockIdx.x];
+        uint32_t tot = 0;
 #pragma unroll
         for (int w2 = 0; w2 < PR_THREADS / 32; w2++) {
-            wbase[w2][tid] = run;
-            run += whist[w2][tid];
+            const uint32_t c = S->whist[w2][tid];
+            S->whist[w2][tid] = tot;
+            tot += c;
+        }
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) S->wtot[w] = incl;
+        __syncthreads();
+        uint32_t wb = 0;
+#pragma unroll
+        for (int i = 0; i < PR_THREADS / 32; i++) if ((unsigned)i < w) wb += S->wtot[i];
+        const uint32_t start = wb + incl - tot;
+        S->dstart[tid] = start;
+        S->gbase[tid] = goff[(uint64_t)tid * nblk + blockIdx.x] - start;      // global slot = gbase[d] + tile-local slot
+    }
+    __syncthreads();
+    // stage the tile in digit order
+#pragma unroll
+    for (int j = 0; j < PR_ITEMS; j++) {
+        const uint64_t idx = warp0 + (uint64_t)j * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = rk[j] >> 16;
+            const uint32_t slot = S->dstart[d] + S->whist[w][d] + (rk[j] & 0xffffu);
+            S->key[slot] = kin[idx];
+            S->val[slot] = vin[idx];
+            if (HASAUX) S->aux[slot] = ain[idx];
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < PR_ITEMS; j++) {
-        uint64_t idx = warp0 + (uint64_t)j * 32 + lane;
-        if (idx < n) {
-            uint32_t d = rk[j] >> 16;
-            uint32_t pos = wbase[w][d] + (rk[j] & 0xffffu);
-            kout[pos] = k[j];
-            if (HASAUX) aout[pos] = a[j];
-            vout[pos] = v[j];
-        }
+    // contiguous runs out
+    for (uint32_t i = tid; i < ntile; i += PR_THREADS) {
+        const uint64_t key = S->key[i];
+        const uint32_t a = HASAUX ? S->aux[i] : 0u;
+        const uint32_t d = AUXDIGIT ? ((a >> shift) & 255u) : (uint32_t)((key >> shift) & 255ull);
+        const uint32_t pos = S->gbase[d] + i;
+        kout[pos] = key;
+        if (HASAUX) aout[pos] = a;
+        vout[pos] = S->val[i];
     }
 }
 
@@ -308,9 +344,13 @@ int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux) {
         auto k_radix_scatter_aux = k_radix_scatter<true, true>;
         auto k_radix_scatter_key_aux = k_radix_scatter<false, true>;
         auto k_radix_scatter_key = k_radix_scatter<false, false>;
-        if (auxd)         UQB_LAUNCH_B(n * 32, k_radix_scatter_aux, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
-        else if (has_aux) UQB_LAUNCH_B(n * 32, k_radix_scatter_key_aux, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
-        else              UQB_LAUNCH_B(n * 24, k_radix_scatter_key, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        const size_t rs_smem = sizeof(rs_stage);
+        UQB_CUDA(cudaFuncSetAttribute(k_radix_scatter_aux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+        UQB_CUDA(cudaFuncSetAttribute(k_radix_scatter_key_aux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+        UQB_CUDA(cudaFuncSetAttribute(k_radix_scatter_key, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+        if (auxd)         UQB_LAUNCH_B(n * 32, k_radix_scatter_aux, nblk, PR_THREADS, rs_smem, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        else if (has_aux) UQB_LAUNCH_B(n * 32, k_radix_scatter_key_aux, nblk, PR_THREADS, rs_smem, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        else              UQB_LAUNCH_B(n * 24, k_radix_scatter_key, nblk, PR_THREADS, rs_smem, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
         sb->cur = o;
     }
     UQB_TRY(uqb_dfree(ctx, ghist, hist_n * 4));

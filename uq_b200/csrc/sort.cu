@@ -75,6 +75,24 @@ __global__ void __launch_bounds__(ST) k_active_flags(const uint32_t* __restrict_
 // count is returned so that the host can stop as soon as there are none.
 #define SG_MAX 32
 #define SG_STAGE_BYTES 256
+#define SG_PAIRS (SG_MAX * (SG_MAX - 1) / 2)
+
+// pair q = b(b-1)/2 + a, a < b: all pairs of a group of sz rows are q < sz(sz-1)/2
+struct sg_pairs_t { uint8_t a[SG_PAIRS], b[SG_PAIRS]; };
+__constant__ sg_pairs_t c_sg_pairs;
+static bool g_sg_pairs_ready[64] = {false};
+
+static int sg_upload_pairs(uqb_ctx* ctx) {
+    if (ctx->device < 64 && g_sg_pairs_ready[ctx->device]) return 0;
+    sg_pairs_t h;
+    int q = 0;
+    for (int b = 1; b < SG_MAX; b++)
+        for (int a = 0; a < b; a++) { h.a[q] = (uint8_t)a; h.b[q] = (uint8_t)b; q++; }
+    UQB_CUDA(cudaMemcpyToSymbolAsync(c_sg_pairs, &h, sizeof(h), 0, cudaMemcpyHostToDevice, ctx->stream));
+    UQB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->device < 64) g_sg_pairs_ready[ctx->device] = true;
+    return 0;
+}
 
 template <bool STAGED>
 __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
@@ -83,7 +101,7 @@ __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__
                                                     uint32_t pitch, unsigned long long* __restrict__ large_rows) {
     extern __shared__ uint32_t sg_smem[];
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    uint32_t* srows = sg_smem + (size_t)w * SG_MAX * pitch;
+    uint32_t* srows = sg_smem + (size_t)w * (SG_MAX * pitch + 64);
     const uint32_t G = *d_ngroups;
     const uint32_t rem = width - off;
     const uint64_t warps_total = (uint64_t)gridDim.x * (ST / 32);
@@ -118,22 +136,49 @@ __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__
             }
             uint32_t rank = 0;
             bool eq_before = false;
+            if (STAGED) {
+                // all pairs (a < b) of the group, `np` pairs at a time: a sub-group of `sub` lanes compares
+                // the two rows word-parallel; ballots give the first differing word and its order
+                uint32_t* srank = srows + SG_MAX * pitch;          // [32] rank, [32] equal-to-an-earlier-row
+                srank[lane] = 0; srank[32 + lane] = 0;
+                __syncwarp();
+                const uint32_t sub = pitch <= 8 ? 8u : (pitch <= 16 ? 16u : 32u);
+                const uint32_t np = 32u / sub, sg = lane / sub, sl = lane % sub;
+                const uint32_t submask = sub == 32u ? 0xffffffffu : ((1u << sub) - 1u);
+                const uint32_t npairs = sz * (sz - 1) / 2;
+                for (uint32_t q0 = 0; q0 < npairs; q0 += np) {
+                    const uint32_t q = q0 + sg;
+                    const bool pv = q < npairs;
+                    const uint32_t a = pv ? c_sg_pairs.a[q] : 0u, b = pv ? c_sg_pairs.b[q] : 0u;
+                    int c = 0;            // memcmp(row_a, row_b), known to the whole sub-group
+                    for (uint32_t w0 = 0; w0 < pitch; w0 += sub) {          // warp-uniform trip count
+                        const uint32_t wd = w0 + sl;
+                        uint32_t x = 0, y = 0;
+                        if (pv && wd < pitch) { x = srows[a * pitch + wd]; y = srows[b * pitch + wd]; }
+                        const unsigned ne = (__ballot_sync(0xffffffffu, x != y) >> (sg * sub)) & submask;
+                        const unsigned lt = (__ballot_sync(0xffffffffu, x < y) >> (sg * sub)) & submask;
+                        if (c == 0 && ne) c = ((lt >> (__ffs(ne) - 1)) & 1u) ? -1 : 1;
+                    }
+                    if (pv && sl == 0) {
+                        if (c > 0) atomicAdd(&srank[a], 1u);                 // row_b < row_a
+                        else atomicAdd(&srank[b], 1u);                       // row_a <= row_b: a stays in front (stable)
+                        if (c == 0) srank[32 + b] = 1u;
+                    }
+                }
+                __syncwarp();
+                rank = srank[lane];
+                eq_before = srank[32 + lane] != 0u;
+                __syncwarp();
+            } else
             for (uint32_t j = 0; j < sz; j++) {
                 const uint32_t rj = __shfl_sync(0xffffffffu, r, j);
                 if (lane < sz && j != lane) {
                     int c = 0;       // memcmp(row_j, row_lane)
-                    if (STAGED) {
-                        for (uint32_t wd = 0; wd < pitch; wd++) {
-                            const uint32_t a = srows[j * pitch + wd], b = srows[lane * pitch + wd];
-                            if (a != b) { c = a < b ? -1 : 1; break; }
-                        }
-                    } else {
-                        const uint8_t* pa = rows + (uint64_t)rj * width + off;
-                        const uint8_t* pb = rows + (uint64_t)r * width + off;
-                        for (uint32_t i = 0; i < rem; i++) {
-                            const unsigned a = __ldg(pa + i), b = __ldg(pb + i);
-                            if (a != b) { c = a < b ? -1 : 1; break; }
-                        }
+                    const uint8_t* pa = rows + (uint64_t)rj * width + off;
+                    const uint8_t* pb = rows + (uint64_t)r * width + off;
+                    for (uint32_t i = 0; i < rem; i++) {
+                        const unsigned a = __ldg(pa + i), b = __ldg(pb + i);
+                        if (a != b) { c = a < b ? -1 : 1; break; }
                     }
                     if (c < 0 || (c == 0 && j < lane)) rank++;
                     if (c == 0 && j < lane) eq_before = true;
@@ -244,9 +289,9 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
             const uint32_t rem = width - off;
             const unsigned sg_grid = uqb_grid(ctx, n, ST, 16);
             if (rem <= SG_STAGE_BYTES) {
-                uint32_t pitch = (rem + 3) / 4;
-                if (!(pitch & 1u)) pitch++;                       // odd pitch: conflict-free row-strided reads
-                const size_t smem = (size_t)(ST / 32) * SG_MAX * pitch * 4;
+                UQB_TRY(sg_upload_pairs(ctx));
+                const uint32_t pitch = (rem + 3) / 4;
+                const size_t smem = (size_t)(ST / 32) * (SG_MAX * pitch + 64) * 4;
                 UQB_CUDA(cudaFuncSetAttribute(k_small_groups_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 UQB_LAUNCH(k_small_groups_smem, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
             } else {
