@@ -192,15 +192,21 @@ def run_ours(args):
         pin_out = ctx.pinned_empty(int(out_bytes * 1.05) + (1 << 20))
 
         def e2e_step():
-            fq = ctx.load_fastq(pin_in)
-            members, _ = host.encode_device(ctx, fq, **opts)
+            # H2D in chunks on the copy stream, overlapped with record splitting and the Pass-1 statistics;
+            # every output array starts its D2H copy as soon as it is final
+            fq = ctx.load_fastq_streamed(pin_in) if not args.e2e_serial else ctx.load_fastq(pin_in)
             cur = [0]
 
-            def into(name, nbytes):
+            def sink(name, nbytes):
                 a = pin_out.array[cur[0]:cur[0] + nbytes]
                 cur[0] += (nbytes + 63) & ~63
                 return a
-            members.download(into=into)
+            if args.e2e_serial:
+                members, _ = host.encode_device(ctx, fq, **opts)
+                members.download(into=sink)
+            else:
+                members, _ = host.encode_device(ctx, fq, sink=sink, **opts)
+                members.download()                      # waits for the copy stream
             nb = members.nbytes()
             members.free()
             fq.free()
@@ -315,6 +321,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=60000)
     ap.add_argument("--ref-sample", type=int, default=20000)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-serial", action="store_true", help="e2e without copy/compute overlap (diagnostics)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -63,6 +63,10 @@ int         uqb_mem_info(uqb_ctx* ctx, uint64_t* in_use, uint64_t* dev_free, uin
 int uqb_array_info(const uqb_array* a, uint64_t* n, uint32_t* width);
 int uqb_array_upload(uqb_ctx* ctx, const void* host, uint64_t n, uint32_t width, uqb_array** out);
 int uqb_array_download(uqb_ctx* ctx, const uqb_array* a, void* host, uint64_t nbytes);
+/* D2H on the copy stream, ordered after all work queued so far on the compute stream.  `host` should be
+ * pinned; the array must stay allocated until uqb_ctx_copy_sync returns. */
+int uqb_array_download_async(uqb_ctx* ctx, const uqb_array* a, void* host, uint64_t nbytes);
+int uqb_ctx_copy_sync(uqb_ctx* ctx);
 int uqb_array_free(uqb_ctx* ctx, uqb_array* a);
 void* uqb_array_device_ptr(const uqb_array* a);   /* for benches/tests that adopt device memory */
 
@@ -79,6 +83,10 @@ typedef struct {
 int uqb_fastq_load(uqb_ctx* ctx, const uint8_t* host, uint64_t nbytes, uqb_fastq** out);      /* H2D */
 /* adopt bytes already in HBM (not copied, not freed): used when inputs are device-resident */
 int uqb_fastq_adopt(uqb_ctx* ctx, const uint8_t* dev, uint64_t nbytes, uqb_fastq** out);
+/* H2D in chunks on a second stream while the compute stream splits and analyses every chunk that has
+ * landed: when the call returns, uqb_split / uqb_analyze on the handle only return the cached results.
+ * `host` should be pinned (uqb_host_alloc) for the copies to overlap; chunk_bytes 0 = 256 MiB. */
+int uqb_fastq_load_streamed(uqb_ctx* ctx, const uint8_t* host, uint64_t nbytes, uint64_t chunk_bytes, uqb_fastq** out);
 int uqb_fastq_free(uqb_ctx* ctx, uqb_fastq* fq);
 int uqb_fastq_download(uqb_ctx* ctx, const uqb_fastq* fq, uint64_t offset, uint8_t* host, uint64_t nbytes);
 int uqb_split(uqb_ctx* ctx, uqb_fastq* fq, uqb_split_info* info);

@@ -280,3 +280,45 @@ def test_roundtrip_variable_length_sort_qual(ctx):
     assert cfg["variable_read_lengths"] is True and cfg["bits_per_quality"] == 7
     assert records_multiset(out.tobytes()) == records_multiset(original)
     dev.free()
+
+
+def test_streamed_load_and_async_download_match_the_serial_path(ctx):
+    """uqb_fastq_load_streamed (chunked H2D overlapped with split + Pass-1 statistics) and the asynchronous
+    member downloads must give exactly the arrays of the serial path."""
+    from uq_b200 import host
+    from emu import emu_stats
+    dev = ctx.synth("genome", 300_000, 150, 77, genome=30_000, pool=50_000)
+    data = dev.download().copy()
+    dev.free()
+    want, want_cfg = host.encode(data, ctx=ctx, sort="DNA")
+    pin = ctx.pinned_empty(data.size)
+    pin.array[:] = data
+    for chunk in (1 << 20, 3 * 16384, 0):
+        fq = ctx.load_fastq_streamed(pin, chunk_bytes=chunk)
+        info = fq.split()
+        assert info.n_reads == 300_000 and info.status == 0
+        bufs = {}
+        def sink(name, nbytes):
+            bufs[name] = ctx.pinned_empty(nbytes)
+            return bufs[name].array
+        members, cfg = host.encode_device(ctx, fq, sort="DNA", sink=sink)
+        got = members.download()
+        assert_members_equal(got, want, "streamed chunk=%d" % chunk)
+        assert_config_equal(cfg, want_cfg)
+        members.free()
+        fq.free()
+        for b in bufs.values():
+            b.free()
+    # statistics of a streamed handle equal the contract emulation (small case, tiny chunks)
+    fq_small, _, _ = golden_case("c3_casava_raw")
+    pin2 = ctx.pinned_empty(len(fq_small))
+    pin2.array[:] = np.frombuffer(fq_small, dtype=np.uint8)
+    h = ctx.load_fastq_streamed(pin2, chunk_bytes=16384)
+    h.split()
+    st = h.analyze()
+    ref, _ = emu_stats(fq_small)
+    for f in STAT_SCALARS:
+        assert getattr(st, f) == getattr(ref, f), f
+    for f in STAT_FIELDS:
+        assert list(getattr(st, f)) == list(getattr(ref, f)), f
+    h.free(); pin2.free(); pin.free()

@@ -94,6 +94,9 @@ SIGNATURES = {
     "uqb_array_device_ptr": (C.c_void_p, [P]),
     "uqb_fastq_load": (C.c_int, [P, P, C.c_uint64, PP]),
     "uqb_fastq_adopt": (C.c_int, [P, P, C.c_uint64, PP]),
+    "uqb_fastq_load_streamed": (C.c_int, [P, P, C.c_uint64, C.c_uint64, PP]),
+    "uqb_array_download_async": (C.c_int, [P, P, P, C.c_uint64]),
+    "uqb_ctx_copy_sync": (C.c_int, [P]),
     "uqb_fastq_free": (C.c_int, [P, P]),
     "uqb_fastq_download": (C.c_int, [P, P, C.c_uint64, P, C.c_uint64]),
     "uqb_split": (C.c_int, [P, P, C.POINTER(SplitInfo)]),

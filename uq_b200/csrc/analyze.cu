@@ -230,7 +230,7 @@ struct rs_smem {
 };
 
 __global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
-                                                            const uint64_t* __restrict__ line_off, uint64_t n_reads,
+                                                            const uint64_t* __restrict__ line_off, uint64_t r_begin, uint64_t n_reads,
                                                             uint32_t first_len, an_dev* __restrict__ s, unsigned int* __restrict__ fallback) {
     extern __shared__ __align__(128) uint8_t rs_raw[];
     rs_smem* S = reinterpret_cast<rs_smem*>(rs_raw);
@@ -265,10 +265,10 @@ __global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __re
     unsigned long long mn = ~0ull, mx = 0ull;
     unsigned nm = 0;
     long long bad_plus = LLONG_MAX, bad_len = LLONG_MAX;
-    const uint64_t ntiles = (n_reads + TL_R - 1) / TL_R;
+    const uint64_t ntiles = (n_reads - r_begin + TL_R - 1) / TL_R;
     unsigned phase = 0;
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const uint64_t r0 = t * TL_R, r1 = (r0 + TL_R < n_reads) ? r0 + TL_R : n_reads;
+        const uint64_t r0 = r_begin + t * TL_R, r1 = (r0 + TL_R < n_reads) ? r0 + TL_R : n_reads;
         uint64_t a0;
         const uint32_t nrec = tile_load(&S->T, d, n_bytes, line_off, r0, r1, phase, &a0);
         if (!nrec) { if (tid == 0) atomicOr(fallback, 1u); continue; }
@@ -403,7 +403,7 @@ __device__ __forceinline__ void pt_flush(unsigned* priv, unsigned* blk_hist, uns
 }
 
 __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
-                                                               const uint64_t* __restrict__ line_off, uint64_t n_reads,
+                                                               const uint64_t* __restrict__ line_off, uint64_t r_begin, uint64_t n_reads,
                                                                an_dev* __restrict__ s, unsigned int* __restrict__ fallback) {
     extern __shared__ __align__(128) uint8_t pt_raw[];
     pt_smem* S = reinterpret_cast<pt_smem*>(pt_raw);
@@ -415,10 +415,10 @@ __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* _
     __syncthreads();
     unsigned* const pb = S->priv_b + tid;
     unsigned* const pq = S->priv_q + tid;
-    const uint64_t ntiles = (n_reads + TL_R - 1) / TL_R;
+    const uint64_t ntiles = (n_reads - r_begin + TL_R - 1) / TL_R;
     unsigned phase = 0, since_flush = 0;
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const uint64_t r0 = t * TL_R, r1 = (r0 + TL_R < n_reads) ? r0 + TL_R : n_reads;
+        const uint64_t r0 = r_begin + t * TL_R, r1 = (r0 + TL_R < n_reads) ? r0 + TL_R : n_reads;
         uint64_t a0;
         const uint32_t nrec = tile_load(&S->T, d, n_bytes, line_off, r0, r1, phase, &a0);
         if (!nrec) { if (tid == 0) atomicOr(fallback, 1u); continue; }
@@ -495,16 +495,37 @@ __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* _
     }
 }
 
-extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
-    if (!fq->line_off) return uqb_fail(ctx, "uqb_analyze: call uqb_split first");
-    if (fq->n_reads == 0) return uqb_fail(ctx, "uqb_analyze: no records");
-    memset(out, 0, sizeof(*out));
+// launches the two tile kernels over records [r0, r1)
+static int stats_tiles_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsigned int* d_fb, uint32_t flen, uint64_t r0, uint64_t r1) {
+    if (r1 <= r0) return 0;
+    const uint64_t ntiles = (r1 - r0 + TL_R - 1) / TL_R;
+    UQB_CUDA(cudaFuncSetAttribute(k_record_stats_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rs_smem)));
+    UQB_CUDA(cudaFuncSetAttribute(k_pair_hist_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pt_smem)));
+    const unsigned g1 = (unsigned)(ntiles < (uint64_t)ctx->sm_count * 3 ? ntiles : (uint64_t)ctx->sm_count * 3);
+    const unsigned g2 = (unsigned)(ntiles < (uint64_t)ctx->sm_count * 2 ? ntiles : (uint64_t)ctx->sm_count * 2);
+    const uint64_t ab = (uint64_t)((double)fq->n * (double)(r1 - r0) / (double)(fq->n_reads ? fq->n_reads : 1)) + 32 * (r1 - r0);
+    UQB_LAUNCH_B(ab, k_record_stats_tiles, g1, TL_R, sizeof(rs_smem), fq->d, fq->n, fq->line_off, r0, r1, flen, s, d_fb);
+    UQB_LAUNCH_B(ab, k_pair_hist_tiles, g2, PT_THREADS, sizeof(pt_smem), fq->d, fq->n, fq->line_off, r0, r1, s, d_fb);
+    return 0;
+}
+
+static int stats_generic(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, uint32_t flen) {
     const uint64_t N = fq->n_reads;
-    // line 1 and the last QNAME line
+    UQB_LAUNCH(k_an_init, 1, 256, 0, s);
+    UQB_LAUNCH(k_record_stats, uqb_blocks(N, AN_THREADS), AN_THREADS, 0, fq->d, fq->line_off, N, flen, s);
+    const size_t smem = (2 * PH_WORDS * PH_THREADS + 4 * 256) * sizeof(unsigned);
+    UQB_CUDA(cudaFuncSetAttribute(k_pair_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    UQB_LAUNCH(k_pair_hist, uqb_grid(ctx, N, PH_THREADS / 32, 3), PH_THREADS, smem, fq->d, fq->line_off, N, s);
+    return 0;
+}
+
+// first / last QNAME lines -> out; returns their lengths
+static int stats_names(uqb_ctx* ctx, const uqb_fastq* fq, uqb_stats* out, uint64_t* flen_out) {
+    const uint64_t N = fq->n_reads;
     uint64_t offs[2], offl[2];
     UQB_TRY(uqb_readback(ctx, offs, fq->line_off, 16));
     UQB_TRY(uqb_readback(ctx, offl, fq->line_off + 4 * (N - 1), 16));
-    uint64_t flen = offs[1] - offs[0] - 1, llen = offl[1] - offl[0] - 1;
+    const uint64_t flen = offs[1] - offs[0] - 1, llen = offl[1] - offl[0] - 1;
     if (flen > UQB_HDR_MAX || llen > UQB_HDR_MAX)
         return uqb_fail(ctx, "QNAME line longer than %d bytes is not supported by the device path", UQB_HDR_MAX);
     out->first_len = (uint32_t)flen;
@@ -512,43 +533,17 @@ extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
     if (flen) UQB_TRY(uqb_readback(ctx, out->first_name, fq->d + offs[0], flen));
     if (llen) UQB_TRY(uqb_readback(ctx, out->last_name, fq->d + offl[0], llen));
     out->bad_first_char = (flen >= 1 && out->first_name[0] == '@') ? -1 : 0;
+    *flen_out = flen;
+    return 0;
+}
 
-    an_dev* s;
-    UQB_TRY(uqb_dalloc_t(ctx, &s, 1));
-    bool done_fast = false;
-    if (fq->n / N <= (TL_CAP - 64) / TL_R) {
-        // v2: shared-memory record tiles
-        unsigned int* d_fb;
-        UQB_TRY(uqb_dalloc_t(ctx, &d_fb, 1));
-        UQB_CUDA(cudaMemsetAsync(d_fb, 0, 4, ctx->stream));
-        UQB_LAUNCH(k_an_init, 1, 256, 0, s);
-        const uint64_t ntiles = (N + TL_R - 1) / TL_R;
-        UQB_CUDA(cudaFuncSetAttribute(k_record_stats_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rs_smem)));
-        UQB_CUDA(cudaFuncSetAttribute(k_pair_hist_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pt_smem)));
-        unsigned g1 = (unsigned)(ntiles < (uint64_t)ctx->sm_count * 3 ? ntiles : (uint64_t)ctx->sm_count * 3);
-        unsigned g2 = (unsigned)(ntiles < (uint64_t)ctx->sm_count * 2 ? ntiles : (uint64_t)ctx->sm_count * 2);
-        UQB_LAUNCH_B(fq->n + 32 * N, k_record_stats_tiles, g1, TL_R, sizeof(rs_smem), fq->d, fq->n, fq->line_off, N, (uint32_t)flen, s, d_fb);
-        UQB_LAUNCH_B(fq->n + 32 * N, k_pair_hist_tiles, g2, PT_THREADS, sizeof(pt_smem), fq->d, fq->n, fq->line_off, N, s, d_fb);
-        unsigned int fb = 0;
-        UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
-        UQB_TRY(uqb_dfree(ctx, d_fb, 4));
-        done_fast = fb == 0;
-    }
-    if (!done_fast) {
-        UQB_LAUNCH(k_an_init, 1, 256, 0, s);
-        UQB_LAUNCH(k_record_stats, uqb_blocks(N, AN_THREADS), AN_THREADS, 0, fq->d, fq->line_off, N, (uint32_t)flen, s);
-        const size_t smem = (2 * PH_WORDS * PH_THREADS + 4 * 256) * sizeof(unsigned);
-        UQB_CUDA(cudaFuncSetAttribute(k_pair_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        unsigned grid = uqb_grid(ctx, N, PH_THREADS / 32, 3);
-        UQB_LAUNCH(k_pair_hist, grid, PH_THREADS, smem, fq->d, fq->line_off, N, s);
-    }
+// device accumulators -> uqb_stats
+static int stats_finish(uqb_ctx* ctx, uqb_fastq* fq, an_dev* s, uqb_stats* out, uint64_t flen) {
     an_dev* h = new an_dev();
     int rc = uqb_readback(ctx, h, s, sizeof(an_dev));
-    if (rc == 0) rc = uqb_dfree(ctx, s, sizeof(an_dev));
     if (rc) { delete h; return rc; }
     fq->total_bases = 0;
     for (int i = 0; i < 256; i++) fq->total_bases += h->base_count[i];
-    if (!done_fast) uqb_timer_add_bytes(ctx, 2 * fq->total_bases + 32 * N);   // k_pair_hist: every base + quality byte, 4 offsets per record
     for (int i = 0; i < 256; i++) {
         out->base_count[i] = h->base_count[i];
         out->qual_count[i] = h->qual_count[i];
@@ -573,4 +568,144 @@ extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
     out->suffix_len = sl;
     delete h;
     return 0;
+}
+
+extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
+    if (!fq->line_off) return uqb_fail(ctx, "uqb_analyze: call uqb_split first");
+    if (fq->n_reads == 0) return uqb_fail(ctx, "uqb_analyze: no records");
+    if (fq->cached_stats) { memcpy(out, fq->cached_stats, sizeof(*out)); return 0; }     // produced by the streamed load
+    memset(out, 0, sizeof(*out));
+    const uint64_t N = fq->n_reads;
+    uint64_t flen = 0;
+    UQB_TRY(stats_names(ctx, fq, out, &flen));
+    an_dev* s;
+    UQB_TRY(uqb_dalloc_t(ctx, &s, 1));
+    bool done_fast = false;
+    if (fq->n / N <= (TL_CAP - 64) / TL_R) {
+        // v2: shared-memory record tiles
+        unsigned int* d_fb;
+        UQB_TRY(uqb_dalloc_t(ctx, &d_fb, 1));
+        UQB_CUDA(cudaMemsetAsync(d_fb, 0, 4, ctx->stream));
+        UQB_LAUNCH(k_an_init, 1, 256, 0, s);
+        UQB_TRY(stats_tiles_range(ctx, fq, s, d_fb, (uint32_t)flen, 0, N));
+        unsigned int fb = 0;
+        UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
+        UQB_TRY(uqb_dfree(ctx, d_fb, 4));
+        done_fast = fb == 0;
+    }
+    if (!done_fast) UQB_TRY(stats_generic(ctx, fq, s, (uint32_t)flen));
+    UQB_TRY(stats_finish(ctx, fq, s, out, flen));
+    UQB_TRY(uqb_dfree(ctx, s, sizeof(an_dev)));
+    return 0;
+}
+
+// ================================================================================================
+// Streamed load: H2D copy of the FASTQ in chunks on the copy stream while the compute stream splits and
+// analyses every chunk as soon as it has landed (newline count -> line offsets -> record tiles of the
+// records completed so far).  When the last chunk arrives the split and the Pass-1 statistics are
+// done; uqb_split / uqb_analyze on the returned handle return them without touching the data again.
+// ================================================================================================
+extern "C" int uqb_fastq_load_streamed(uqb_ctx* ctx, const uint8_t* host, uint64_t nbytes, uint64_t chunk_bytes, uqb_fastq** out_fq) {
+    if (chunk_bytes == 0) chunk_bytes = 256ull << 20;
+    chunk_bytes = (chunk_bytes + UQB_SPLIT_TILE - 1) / UQB_SPLIT_TILE * UQB_SPLIT_TILE;
+    cudaStream_t cs;
+    UQB_TRY(uqb_copy_stream(ctx, &cs));
+    uqb_fastq* fq = new uqb_fastq();
+    *out_fq = fq;
+    uint8_t* d;
+    UQB_TRY(uqb_dalloc(ctx, (void**)&d, nbytes + 64));
+    fq->d = d; fq->n = nbytes; fq->owned = true; fq->streamed = true;
+    UQB_CUDA(cudaMemsetAsync(d + nbytes, 0, 64, ctx->stream));
+    const uint64_t nchunks = (nbytes + chunk_bytes - 1) / chunk_bytes;
+    // all copies are queued up front; one event per chunk gates the compute stream
+    std::vector<cudaEvent_t> ev(nchunks);
+    UQB_CUDA(cudaStreamSynchronize(ctx->stream));        // the destination buffer may be recycled arena memory still in use
+    for (uint64_t c = 0; c < nchunks; c++) {
+        const uint64_t off = c * chunk_bytes, len = (off + chunk_bytes <= nbytes) ? chunk_bytes : nbytes - off;
+        UQB_CUDA(cudaMemcpyAsync(d + off, host + off, len, cudaMemcpyHostToDevice, cs));
+        UQB_CUDA(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
+        UQB_CUDA(cudaEventRecord(ev[c], cs));
+    }
+    const uint64_t ntiles = (nbytes + UQB_SPLIT_TILE - 1) / UQB_SPLIT_TILE;
+    uint32_t* counts = nullptr;
+    uint64_t *bases = nullptr, *d_total = nullptr;
+    an_dev* s = nullptr;
+    unsigned int* d_fb = nullptr;
+    if (ntiles) {
+        UQB_TRY(uqb_dalloc_t(ctx, &counts, ntiles));
+        UQB_TRY(uqb_dalloc_t(ctx, &bases, ntiles));
+    }
+    UQB_TRY(uqb_dalloc_t(ctx, &d_total, 1));
+    UQB_TRY(uqb_dalloc_t(ctx, &s, 1));
+    UQB_TRY(uqb_dalloc_t(ctx, &d_fb, 1));
+    UQB_CUDA(cudaMemsetAsync(d_fb, 0, 4, ctx->stream));
+    UQB_LAUNCH(k_an_init, 1, 256, 0, s);
+    uint64_t lines_done = 0, cap = 0, recs_done = 0, flen = 0;
+    bool tiles_ok = true, have_first = false;
+    uqb_stats* st = new uqb_stats();
+    memset(st, 0, sizeof(*st));
+    fq->cached_stats = st;
+    for (uint64_t c = 0; c < nchunks; c++) {
+        const uint64_t off = c * chunk_bytes, end = (off + chunk_bytes <= nbytes) ? off + chunk_bytes : nbytes;
+        const uint64_t t0 = off / UQB_SPLIT_TILE, t1 = (end + UQB_SPLIT_TILE - 1) / UQB_SPLIT_TILE;
+        UQB_CUDA(cudaStreamWaitEvent(ctx->stream, ev[c], 0));
+        UQB_TRY(uqb_split_count_tiles(ctx, d, end, t0, t1 - t0, counts));
+        UQB_TRY(uqb_scan_u32_to_u64(ctx, counts + t0, bases + t0, t1 - t0, d_total));
+        uint64_t chunk_lines = 0;
+        UQB_TRY(uqb_readback(ctx, &chunk_lines, d_total, 8));
+        if (lines_done + chunk_lines + 1 > cap) {        // (re)size the line-offset array from the density seen so far
+            const double density = (double)(lines_done + chunk_lines + 1) / (double)end;
+            uint64_t want = (uint64_t)(density * (double)nbytes * 1.05) + 4096;
+            if (want < lines_done + chunk_lines + 1) want = lines_done + chunk_lines + 1;
+            uint64_t* nl;
+            UQB_TRY(uqb_dalloc_t(ctx, &nl, want));
+            if (fq->line_off) {
+                UQB_CUDA(cudaMemcpyAsync(nl, fq->line_off, (lines_done + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+                UQB_TRY(uqb_dfree(ctx, fq->line_off, 0));
+            } else {
+                UQB_TRY(uqb_split_set_first(ctx, nl));
+            }
+            fq->line_off = nl;
+            cap = want;
+        }
+        UQB_TRY(uqb_split_write_tiles(ctx, d, end, t0, t1 - t0, lines_done, bases, fq->line_off));
+        lines_done += chunk_lines;
+        fq->n_lines = lines_done;
+        fq->n_reads = lines_done / 4;
+        // Pass-1 statistics of the records that are complete now
+        const uint64_t recs_now = lines_done / 4;
+        if (recs_now > 0 && !have_first) {
+            uint64_t offs[2];
+            UQB_TRY(uqb_readback(ctx, offs, fq->line_off, 16));
+            flen = offs[1] - offs[0] - 1;
+            if (flen > UQB_HDR_MAX) return uqb_fail(ctx, "QNAME line longer than %d bytes is not supported by the device path", UQB_HDR_MAX);
+            have_first = true;
+            // records of typical short-read files fit the tiles; otherwise the generic kernels run at the end
+            tiles_ok = true;
+        }
+        if (have_first && tiles_ok && recs_now > recs_done) {
+            if ((double)end / (double)recs_now > (double)((TL_CAP - 64) / TL_R)) tiles_ok = false;
+            else UQB_TRY(stats_tiles_range(ctx, fq, s, d_fb, (uint32_t)flen, recs_done, recs_now));
+            recs_done = recs_now;
+        }
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    if (counts) { UQB_TRY(uqb_dfree(ctx, counts, 0)); UQB_TRY(uqb_dfree(ctx, bases, 0)); }
+    UQB_TRY(uqb_dfree(ctx, d_total, 0));
+    if (!fq->line_off) { UQB_TRY(uqb_dalloc_t(ctx, &fq->line_off, 1)); UQB_TRY(uqb_split_set_first(ctx, fq->line_off)); }
+    int rc = 0;
+    if (fq->n_reads > 0) {
+        unsigned int fb = 0;
+        UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
+        uint64_t fl2 = 0;
+        UQB_TRY(stats_names(ctx, fq, st, &fl2));
+        if (!tiles_ok || fb != 0) UQB_TRY(stats_generic(ctx, fq, s, (uint32_t)fl2));
+        rc = stats_finish(ctx, fq, s, st, fl2);
+    } else {
+        delete st;
+        fq->cached_stats = nullptr;
+    }
+    UQB_TRY(uqb_dfree(ctx, s, 0));
+    UQB_TRY(uqb_dfree(ctx, d_fb, 0));
+    return rc;
 }

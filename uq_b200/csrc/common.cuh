@@ -35,6 +35,7 @@ struct uqb_ctx {
     uqb_arena arena;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;      // H2D / D2H copies that overlap the compute stream
     char err[512] = {0};
     uint64_t launches = 0;
     uint64_t bytes_in_use = 0;
@@ -74,6 +75,8 @@ struct uqb_fastq {
     uint64_t* line_off = nullptr; // uint64[n_lines + 1]
     uint64_t n_lines = 0, n_reads = 0;
     uint64_t total_bases = 0;     // sum of read lengths (set by uqb_analyze; bookkeeping for byte counts)
+    bool streamed = false;        // split + Pass-1 statistics were produced while the bytes streamed in
+    uqb_stats* cached_stats = nullptr;
     uint32_t prefix_len = 0, suffix_len = 0, ncols = 0;
     std::vector<uqb_qcol> qcols;
 };
@@ -160,6 +163,14 @@ __device__ __forceinline__ void atomic_max_i64(int64_t* addr, int64_t v) {
     atomicMax((long long*)addr, (long long)v);
 }
 #endif
+
+// ---- split building blocks (split.cu) ------------------------------------------------------------
+#define UQB_SPLIT_TILE (256 * 64)
+int uqb_split_count_tiles(uqb_ctx* ctx, const uint8_t* d, uint64_t n_end, uint64_t tile0, uint64_t ntiles, uint32_t* counts);
+int uqb_split_write_tiles(uqb_ctx* ctx, const uint8_t* d, uint64_t n_end, uint64_t tile0, uint64_t ntiles, uint64_t line_base,
+                          const uint64_t* bases, uint64_t* line_off);
+int uqb_split_set_first(uqb_ctx* ctx, uint64_t* line_off);
+int uqb_copy_stream(uqb_ctx* ctx, cudaStream_t* out);
 
 // ---- primitives (prims.cu) ---------------------------------------------------------------------
 // exclusive prefix sum of n uint32 values into uint32 / uint64; total written to *d_total (device)

@@ -154,6 +154,7 @@ extern "C" void uqb_ctx_destroy(uqb_ctx* ctx) {
     for (auto e : ctx->free_events) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->span_a) { cudaEventDestroy(ctx->span_a); cudaEventDestroy(ctx->span_b); }
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     arena_destroy(ctx);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -385,6 +386,32 @@ extern "C" int uqb_array_download(uqb_ctx* ctx, const uqb_array* a, void* host, 
     if (nbytes > a->nbytes()) return uqb_fail(ctx, "download of %llu bytes from an array of %llu", (unsigned long long)nbytes, (unsigned long long)a->nbytes());
     if (nbytes) UQB_CUDA(cudaMemcpyAsync(host, a->d, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
     UQB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int uqb_copy_stream(uqb_ctx* ctx, cudaStream_t* out) {
+    if (!ctx->copy_stream) UQB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    *out = ctx->copy_stream;
+    return 0;
+}
+
+// D2H on the copy stream, ordered after everything enqueued so far on the compute stream; the array must
+// stay allocated until uqb_ctx_copy_sync() returns.
+extern "C" int uqb_array_download_async(uqb_ctx* ctx, const uqb_array* a, void* host, uint64_t nbytes) {
+    if (nbytes > a->nbytes()) return uqb_fail(ctx, "async download of %llu bytes from an array of %llu", (unsigned long long)nbytes, (unsigned long long)a->nbytes());
+    cudaStream_t cs;
+    UQB_TRY(uqb_copy_stream(ctx, &cs));
+    cudaEvent_t ev;
+    UQB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    UQB_CUDA(cudaEventRecord(ev, ctx->stream));
+    UQB_CUDA(cudaStreamWaitEvent(cs, ev, 0));
+    UQB_CUDA(cudaEventDestroy(ev));                      // released once the wait has consumed it
+    if (nbytes) UQB_CUDA(cudaMemcpyAsync(host, a->d, nbytes, cudaMemcpyDeviceToHost, cs));
+    return 0;
+}
+
+extern "C" int uqb_ctx_copy_sync(uqb_ctx* ctx) {
+    if (ctx->copy_stream) UQB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     return 0;
 }
 

@@ -36,8 +36,8 @@ __device__ __forceinline__ void load_chunk(const uint8_t* __restrict__ d, uint64
     }
 }
 
-__global__ void __launch_bounds__(SP_THREADS) k_newline_count(const uint8_t* __restrict__ d, uint64_t n, uint32_t* __restrict__ tile_counts) {
-    uint64_t pos = (uint64_t)blockIdx.x * SP_TILE + (uint64_t)threadIdx.x * SP_BYTES_PER_THREAD;
+__global__ void __launch_bounds__(SP_THREADS) k_newline_count(const uint8_t* __restrict__ d, uint64_t n, uint64_t tile0, uint32_t* __restrict__ tile_counts) {
+    uint64_t pos = (tile0 + blockIdx.x) * SP_TILE + (uint64_t)threadIdx.x * SP_BYTES_PER_THREAD;
     unsigned c = 0;
     if (pos < n) {
         unsigned w[16];
@@ -56,13 +56,13 @@ __global__ void __launch_bounds__(SP_THREADS) k_newline_count(const uint8_t* __r
         unsigned t = 0;
 #pragma unroll
         for (int i = 0; i < SP_THREADS / 32; i++) t += ws[i];
-        tile_counts[blockIdx.x] = t;
+        tile_counts[tile0 + blockIdx.x] = t;
     }
 }
 
-__global__ void __launch_bounds__(SP_THREADS) k_newline_write(const uint8_t* __restrict__ d, uint64_t n, const uint64_t* __restrict__ tile_base,
-                                                            uint64_t* __restrict__ line_off) {
-    uint64_t pos = (uint64_t)blockIdx.x * SP_TILE + (uint64_t)threadIdx.x * SP_BYTES_PER_THREAD;
+__global__ void __launch_bounds__(SP_THREADS) k_newline_write(const uint8_t* __restrict__ d, uint64_t n, uint64_t tile0, uint64_t line_base,
+                                                            const uint64_t* __restrict__ tile_base, uint64_t* __restrict__ line_off) {
+    uint64_t pos = (tile0 + blockIdx.x) * SP_TILE + (uint64_t)threadIdx.x * SP_BYTES_PER_THREAD;
     unsigned w[16];
     unsigned c = 0;
     if (pos < n) {
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_newline_write(const uint8_t* __r
     for (int i = 0; i < SP_THREADS / 32; i++)
         if ((unsigned)i < wid) wbase += ws[i];
     if (c == 0) return;
-    uint64_t out = tile_base[blockIdx.x] + wbase + incl - c + 1;   // +1: line_off[0] = 0 is the first line
+    uint64_t out = line_base + tile_base[tile0 + blockIdx.x] + wbase + incl - c + 1;   // +1: line_off[0] = 0 is the first line
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         unsigned m = nl_mask(w[i]);
@@ -143,6 +143,7 @@ extern "C" int uqb_fastq_free(uqb_ctx* ctx, uqb_fastq* fq) {
     if (!fq) return 0;
     UQB_TRY(free_qcols(ctx, fq));
     if (fq->line_off) UQB_TRY(uqb_dfree(ctx, fq->line_off, (fq->n_lines + 1) * 8));
+    delete fq->cached_stats;
     if (fq->owned) UQB_TRY(uqb_dfree(ctx, (void*)fq->d, fq->n + 64));
     delete fq;
     return 0;
@@ -155,8 +156,28 @@ extern "C" int uqb_fastq_download(uqb_ctx* ctx, const uqb_fastq* fq, uint64_t of
     return 0;
 }
 
+// chunk-wise building blocks for the streamed load (analyze.cu)
+int uqb_split_count_tiles(uqb_ctx* ctx, const uint8_t* d, uint64_t n_end, uint64_t tile0, uint64_t ntiles, uint32_t* counts) {
+    UQB_LAUNCH_B(ntiles * SP_TILE, k_newline_count, (unsigned)ntiles, SP_THREADS, 0, d, n_end, tile0, counts);
+    return 0;
+}
+int uqb_split_write_tiles(uqb_ctx* ctx, const uint8_t* d, uint64_t n_end, uint64_t tile0, uint64_t ntiles, uint64_t line_base,
+                          const uint64_t* bases, uint64_t* line_off) {
+    UQB_LAUNCH_B(ntiles * SP_TILE, k_newline_write, (unsigned)ntiles, SP_THREADS, 0, d, n_end, tile0, line_base, bases, line_off);
+    return 0;
+}
+int uqb_split_set_first(uqb_ctx* ctx, uint64_t* line_off) {
+    UQB_LAUNCH(k_set_u64, 1, 1, 0, line_off, 0ull);
+    return 0;
+}
+
 extern "C" int uqb_split(uqb_ctx* ctx, uqb_fastq* fq, uqb_split_info* info) {
     memset(info, 0, sizeof(*info));
+    if (fq->streamed && fq->line_off) {          // already split while the bytes were streaming in
+        info->n_bytes = fq->n; info->n_lines = fq->n_lines; info->n_reads = fq->n_reads;
+        info->status = (fq->n_lines % 4 == 0) ? 0 : 1;
+        return 0;
+    }
     info->n_bytes = fq->n;
     if (fq->line_off) { UQB_TRY(uqb_dfree(ctx, fq->line_off, (fq->n_lines + 1) * 8)); fq->line_off = nullptr; }
     uint64_t ntiles = (fq->n + SP_TILE - 1) / SP_TILE;
@@ -168,7 +189,7 @@ extern "C" int uqb_split(uqb_ctx* ctx, uqb_fastq* fq, uqb_split_info* info) {
         UQB_TRY(uqb_dalloc_t(ctx, &counts, ntiles));
         UQB_TRY(uqb_dalloc_t(ctx, &bases, ntiles));
         UQB_TRY(uqb_dalloc_t(ctx, &d_total, 1));
-        UQB_LAUNCH_B(fq->n, k_newline_count, (unsigned)ntiles, SP_THREADS, 0, fq->d, fq->n, counts);
+        UQB_LAUNCH_B(fq->n, k_newline_count, (unsigned)ntiles, SP_THREADS, 0, fq->d, fq->n, 0ull, counts);
         UQB_TRY(uqb_scan_u32_to_u64(ctx, counts, bases, ntiles, d_total));
         UQB_TRY(uqb_readback(ctx, &total, d_total, 8));
     }
@@ -177,7 +198,7 @@ extern "C" int uqb_split(uqb_ctx* ctx, uqb_fastq* fq, uqb_split_info* info) {
     UQB_TRY(uqb_dalloc_t(ctx, &fq->line_off, total + 1));
     UQB_LAUNCH(k_set_u64, 1, 1, 0, fq->line_off, 0ull);
     if (ntiles) {
-        UQB_LAUNCH_B(fq->n + 8 * total, k_newline_write, (unsigned)ntiles, SP_THREADS, 0, fq->d, fq->n, bases, fq->line_off);
+        UQB_LAUNCH_B(fq->n + 8 * total, k_newline_write, (unsigned)ntiles, SP_THREADS, 0, fq->d, fq->n, 0ull, 0ull, bases, fq->line_off);
         UQB_TRY(uqb_dfree(ctx, counts, ntiles * 4));
         UQB_TRY(uqb_dfree(ctx, bases, ntiles * 8));
         UQB_TRY(uqb_dfree(ctx, d_total, 8));

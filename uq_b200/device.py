@@ -117,6 +117,21 @@ class Context:
         self.check(self.lib.uqb_fastq_load(self.h, _ptr(arr) if arr.size else None, int(arr.size), C.byref(h)))
         return Fastq(self, h, int(arr.size))
 
+    def load_fastq_streamed(self, data, chunk_bytes=0):
+        """H2D in chunks overlapped with record splitting and the Pass-1 statistics (data: PinnedBuffer or ndarray)."""
+        arr = data.array if isinstance(data, PinnedBuffer) else np.ascontiguousarray(data, dtype=np.uint8)
+        h = C.c_void_p()
+        rc = self.lib.uqb_fastq_load_streamed(self.h, _ptr(arr) if arr.size else None, int(arr.size), int(chunk_bytes), C.byref(h))
+        if rc:
+            msg = self.lib.uqb_last_error(self.h).decode()
+            if h:
+                self.lib.uqb_fastq_free(self.h, h)
+            raise DeviceError(msg)
+        return Fastq(self, h, int(arr.size))
+
+    def copy_sync(self):
+        self.check(self.lib.uqb_ctx_copy_sync(self.h))
+
     def adopt_fastq(self, device_array):
         """Wrap FASTQ bytes that already live in HBM (no copy); the array must outlive the Fastq."""
         h = C.c_void_p()
@@ -229,6 +244,10 @@ class DeviceArray:
         if dtype == np.uint8 and self.width == 1:
             return out[:self.nbytes]
         return out[:self.nbytes].reshape(self.n, self.width)
+
+    def download_async(self, out):
+        """Queue the D2H copy into `out` (uint8 ndarray over pinned memory) on the copy stream; call ctx.copy_sync()."""
+        self.ctx.check(self.ctx.lib.uqb_array_download_async(self.ctx.h, self.h, _ptr(out), self.nbytes))
 
     def free(self):
         if self.h:

@@ -274,36 +274,54 @@ def key_itemsize(n_unique):
 
 class DeviceMembers:
     """Output members kept in HBM: name -> (DeviceArray, kind, meta).  download() turns them into the
-    exact ndarray objects the reference hands to numpy.save."""
+    exact ndarray objects the reference hands to numpy.save.
 
-    def __init__(self):
+    With a `sink` (callable (name, nbytes) -> uint8 ndarray over pinned host memory) every member starts
+    its device->host copy on the copy stream the moment it is final, so the copies overlap the rest of
+    the encode; download() then only waits for the copy stream."""
+
+    def __init__(self, ctx=None, sink=None):
         self.items = {}
+        self.ctx, self.sink, self.host = ctx, sink, {}
+
+    def _queue(self, name, arr):
+        if self.sink is not None:
+            buf = self.sink(name, arr.nbytes)
+            arr.download_async(buf)
+            self.host[name] = buf
 
     def add_table(self, name, stream, n, width, pattern):
         self.items[name] = (stream, 'table', (n, width, pattern))
+        self._queue(name, stream)
 
     def add_vector(self, name, arr, dtype):
         self.items[name] = (arr, 'vector', np.dtype(dtype))
+        self._queue(name, arr)
 
     def nbytes(self):
         return sum(a.nbytes for a, _, _ in self.items.values())
 
     def download(self, into=None):
         out = {}
+        if self.sink is not None:
+            self.ctx.copy_sync()
         for name, (arr, kind, meta) in self.items.items():
-            buf = None if into is None else into(name, arr.nbytes)
+            if self.sink is not None:
+                flat = self.host[name][:arr.nbytes]
+            else:
+                buf = None if into is None else into(name, arr.nbytes)
+                flat = arr.download(dtype=np.uint8, out=buf).reshape(-1)
             if kind == 'vector':
-                out[name] = arr.download(dtype=meta, out=buf).reshape(-1)
-                if meta == np.uint8:
-                    out[name] = out[name].reshape(-1)
+                out[name] = flat.view(meta).reshape(-1)
             else:
                 n, width, pattern = meta
-                flat = arr.download(dtype=np.uint8, out=buf).reshape(-1)
                 shape = (n, width) if pattern[0] in '02' else (width, n)
                 out[name] = np.ndarray(shape, dtype=np.uint8, buffer=flat, order='C' if pattern[2] == '1' else 'F')
         return out
 
     def free(self):
+        if self.sink is not None and self.ctx is not None:
+            self.ctx.copy_sync()
         for a, _, _ in self.items.values():
             a.free()
         self.items = {}
@@ -331,7 +349,18 @@ def _keyed(ctx, table, order):
     return key, uniq, nu, order
 
 
-def _mix_dna_qual(ctx, out, table, name, order, raw, pattern):
+def _prepare_keyed(ctx, out, table, name, pattern):
+    """Order-independent half of a keyed DNA/QUAL table that does not define the sort order: unique table
+    (emitted at once, so that its device->host copy can start) and the row -> unique-index key."""
+    _, key, uniq, nu = ctx.sort_rows(table, want_key=True, want_uniq=True)         # uq.py:786
+    stream, aliased = _layout(ctx, uniq, pattern)
+    out.add_table(name, stream, uniq.n, uniq.width, pattern)
+    if not aliased:
+        uniq.free()
+    return key, nu
+
+
+def _mix_dna_qual(ctx, out, table, name, order, raw, pattern, prepared=None):
     """encode_dna_qual (uq.py:765-805).  order: None / False / DeviceArray(uint32 perm)."""
     if raw:
         src = table
@@ -343,6 +372,16 @@ def _mix_dna_qual(ctx, out, table, name, order, raw, pattern):
         out.add_table(name + '.raw', stream, table.n, table.width, pattern)
         if src is not table and not aliased:
             src.free()
+    elif prepared is not None:
+        key, nu = prepared
+        if order is not None:
+            k2 = ctx.gather_rows(key, order)                                       # key[sort_order], uq.py:798
+            key.free()
+            key = k2
+        size = key_itemsize(nu)
+        narrow = ctx.narrow_u32(key, size)                                         # uq.py:790
+        key.free()
+        out.add_vector(name + '.key', narrow, 'uint%d' % (8 * size))
     else:
         key, uniq, nu, order = _keyed(ctx, table, order)                           # uq.py:786, 796
         size = key_itemsize(nu)
@@ -383,30 +422,36 @@ def _mix_qname(ctx, out, cols, columns, order, raw):
     return order
 
 
-def run_mix(ctx, dna, qual, cols, columns, sorted_on, raw_tables, pattern):
-    out = DeviceMembers()
+def run_mix(ctx, dna, qual, cols, columns, sorted_on, raw_tables, pattern, sink=None):
+    """uq.py:739-753.  The reference runs the sorted-on table first; here the order-independent half of the
+    other keyed table (its unique table - the largest output) is produced before that, so that its
+    device->host copy overlaps the remaining sorts.  The results are identical."""
+    out = DeviceMembers(ctx, sink)
     pd, pq = pattern
     if sorted_on in ('DNA', 'QUAL'):
         first = (dna, 'DNA', pd) if sorted_on == 'DNA' else (qual, 'QUAL', pq)
         second = (qual, 'QUAL', pq) if sorted_on == 'DNA' else (dna, 'DNA', pd)
+        prepared = None
+        if second[1] not in raw_tables:
+            prepared = _timed(ctx, 'mix_' + second[1], _prepare_keyed, ctx, out, second[0], second[1], second[2])
         order = _timed(ctx, 'mix_' + first[1], _mix_dna_qual, ctx, out, first[0], first[1], False, first[1] in raw_tables, first[2])
-        _timed(ctx, 'mix_' + second[1], _mix_dna_qual, ctx, out, second[0], second[1], order, second[1] in raw_tables, second[2])
+        _timed(ctx, 'mix_' + second[1], _mix_dna_qual, ctx, out, second[0], second[1], order, second[1] in raw_tables, second[2], prepared)
         _timed(ctx, 'mix_QNAME', _mix_qname, ctx, out, cols, columns, order, 'QNAME' in raw_tables)
     elif sorted_on == 'QNAME':
         order = _timed(ctx, 'mix_QNAME', _mix_qname, ctx, out, cols, columns, False, 'QNAME' in raw_tables)
-        _timed(ctx, 'mix_DNA', _mix_dna_qual, ctx, out, dna, 'DNA', order, 'DNA' in raw_tables, pd)
         _timed(ctx, 'mix_QUAL', _mix_dna_qual, ctx, out, qual, 'QUAL', order, 'QUAL' in raw_tables, pq)
+        _timed(ctx, 'mix_DNA', _mix_dna_qual, ctx, out, dna, 'DNA', order, 'DNA' in raw_tables, pd)
     else:
-        _timed(ctx, 'mix_QNAME', _mix_qname, ctx, out, cols, columns, None, 'QNAME' in raw_tables)
-        _timed(ctx, 'mix_DNA', _mix_dna_qual, ctx, out, dna, 'DNA', None, 'DNA' in raw_tables, pd)
         _timed(ctx, 'mix_QUAL', _mix_dna_qual, ctx, out, qual, 'QUAL', None, 'QUAL' in raw_tables, pq)
+        _timed(ctx, 'mix_DNA', _mix_dna_qual, ctx, out, dna, 'DNA', None, 'DNA' in raw_tables, pd)
+        _timed(ctx, 'mix_QNAME', _mix_qname, ctx, out, cols, columns, None, 'QNAME' in raw_tables)
     return out
 
 
 # ------------------------------------------------------------------------------------------------
 # encode
 # ------------------------------------------------------------------------------------------------
-def encode_device(ctx, fq, sort=None, raw=None, pattern=None, pad=False, notricks=False, stages=None):
+def encode_device(ctx, fq, sort=None, raw=None, pattern=None, pad=False, notricks=False, stages=None, sink=None):
     """FASTQ already in HBM (device.Fastq) -> (DeviceMembers, config).  All O(N) work is on the GPU."""
     sort, raw, pattern = normalise_options(sort, raw, pattern)
     info = _timed(ctx, 'split', fq.split)
@@ -436,7 +481,7 @@ def encode_device(ctx, fq, sort=None, raw=None, pattern=None, pad=False, notrick
     if stages is not None:
         stages.update(stats=st, dec=dec, columns=columns, dna=dna, qual=qual, cols=cols, prefix=prefix, suffix=suffix,
                       separators=separators, total=n)
-    members = run_mix(ctx, dna, qual, cols, columns, sort, raw, pattern)
+    members = run_mix(ctx, dna, qual, cols, columns, sort, raw, pattern, sink=sink)
     if stages is None:
         keep = {id(a) for a, _, _ in members.items.values()}
         for a in [dna, qual] + cols:
