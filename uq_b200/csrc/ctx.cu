@@ -326,17 +326,33 @@ int uqb_pinned(uqb_ctx* ctx, size_t nbytes, void** out) {
     if (ctx->pinned_bytes < nbytes) {
         if (ctx->pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
         size_t want = nbytes < (1u << 20) ? (1u << 20) : nbytes;
-        UQB_CUDA(cudaHostAlloc(&ctx->pinned, want, cudaHostAllocDefault));
+        UQB_CUDA(cudaHostAlloc(&ctx->pinned, want, cudaHostAllocMapped));
         ctx->pinned_bytes = want;
     }
     *out = ctx->pinned;
     return 0;
 }
 
+// Small device->host read-backs go through a copy KERNEL into mapped pinned memory, not through the
+// DMA engine: a bulk D2H of finished output arrays may be in flight on the copy stream, and a tiny
+// cudaMemcpy queued behind it would stall the control flow of the sort for the whole transfer.
+__global__ void k_readback(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 int uqb_readback(uqb_ctx* ctx, void* host, const void* dev, size_t nbytes) {
+    if (nbytes == 0) return 0;
     void* stage;
     UQB_TRY(uqb_pinned(ctx, nbytes, &stage));
-    UQB_CUDA(cudaMemcpyAsync(stage, dev, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nbytes <= (1u << 20)) {
+        void* dstage = nullptr;
+        UQB_CUDA(cudaHostGetDevicePointer(&dstage, stage, 0));
+        const unsigned blocks = (unsigned)((nbytes + 255) / 256 < 64 ? (nbytes + 255) / 256 : 64);
+        k_readback<<<blocks, 256, 0, ctx->stream>>>((uint8_t*)dstage, (const uint8_t*)dev, nbytes);
+        UQB_CUDA(cudaGetLastError());
+    } else {
+        UQB_CUDA(cudaMemcpyAsync(stage, dev, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     UQB_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(host, stage, nbytes);
     return 0;
