@@ -10,6 +10,7 @@
 #define SP_THREADS 256
 #define SP_BYTES_PER_THREAD 64
 #define SP_TILE (SP_THREADS * SP_BYTES_PER_THREAD)
+#define SP_STAGE 1024          // line offsets staged per tile (a 16 KB tile of FASTQ holds ~200)
 
 __device__ __forceinline__ unsigned nl_mask(unsigned w) { return __vcmpeq4(w, 0x0A0A0A0Au); }   // 0xFF per '\n' byte
 
@@ -86,16 +87,31 @@ __global__ void __launch_bounds__(SP_THREADS) k_newline_write(const uint8_t* __r
 #pragma unroll
     for (int i = 0; i < SP_THREADS / 32; i++)
         if ((unsigned)i < wid) wbase += ws[i];
-    if (c == 0) return;
-    uint64_t out = line_base + tile_base[tile0 + blockIdx.x] + wbase + incl - c + 1;   // +1: line_off[0] = 0 is the first line
+    // the tile's offsets are staged in shared memory in order and stored as one contiguous run
+    __shared__ uint64_t stage[SP_STAGE];
+    __shared__ unsigned tile_total;
+    if (threadIdx.x == SP_THREADS - 1) tile_total = wbase + incl;
+    __syncthreads();
+    const unsigned total = tile_total;
+    const uint64_t out0 = line_base + tile_base[tile0 + blockIdx.x] + 1;      // +1: line_off[0] = 0 is the first line
+    unsigned k = wbase + incl - c;
+    const bool staged = total <= SP_STAGE;
+    if (c) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        unsigned m = nl_mask(w[i]);
-        while (m) {
-            int b = (__ffs(m) - 1) >> 3;
-            line_off[out++] = pos + 4 * i + b + 1;    // the next line starts after the newline
-            m &= ~(0xFFu << (8 * b));
+        for (int i = 0; i < 16; i++) {
+            unsigned m = nl_mask(w[i]);
+            while (m) {
+                int b = (__ffs(m) - 1) >> 3;
+                const uint64_t v = pos + 4 * i + b + 1;                      // the next line starts after the newline
+                if (staged) stage[k] = v; else line_off[out0 + k] = v;
+                k++;
+                m &= ~(0xFFu << (8 * b));
+            }
         }
+    }
+    if (staged) {
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < total; i += SP_THREADS) line_off[out0 + i] = stage[i];
     }
 }
 
