@@ -215,13 +215,17 @@ def run_ours(args):
         ctx.sync()
         barrier()
         t0 = time.perf_counter()
+        step_ms = []
         for _ in range(args.steps):
+            ts = time.perf_counter()
             d2h = e2e_step()
+            step_ms.append(round((time.perf_counter() - ts) * 1e3, 1))
         ctx.sync()
         barrier()
         te = max_over_ranks(time.perf_counter() - t0) / args.steps
         e2e = {"value": total_reads / te, "unit": "reads/s", "h2d_bytes_per_step": int(fbytes) * world,
-               "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": round(te * 1e3, 2)}
+               "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": round(te * 1e3, 2), "ms_steps_rank0": step_ms,
+               "overlap": "serial" if args.e2e_serial else "H2D chunks overlapped with split+Pass-1, D2H per output array as soon as final"}
         sample_src = pin_in
     else:
         sample_src = None
