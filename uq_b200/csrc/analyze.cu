@@ -415,6 +415,8 @@ __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* _
     __syncthreads();
     unsigned* const pb = S->priv_b + tid;
     unsigned* const pq = S->priv_q + tid;
+    const uint32_t bytes_a = smem_u32(S->T.bytes), pb_a = smem_u32(pb), pq_a = smem_u32(pq), state_a = smem_u32(S->state);
+    static_assert(PT_THREADS == 256, "private counter rows are 1024 bytes apart");
     const uint64_t ntiles = (n_reads - r_begin + TL_R - 1) / TL_R;
     unsigned phase = 0, since_flush = 0;
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -456,14 +458,16 @@ __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* _
                 since_flush = 255;
                 continue;
             }
+            const uint32_t dna_a = bytes_a + o1 + lane, qual_a = bytes_a + o3 + lane;
             for (uint32_t it = 0; it < iters; it++) {
                 const bool act = it * 32 + lane < len;
-                const unsigned b = act ? (unsigned)dna[it * 32] : (PT_LO + PT_IDLE);
-                const unsigned q = act ? (unsigned)qual[it * 32] : (PT_LO + PT_IDLE);
-                const unsigned bi = act ? min(b - PT_LO, PT_OOR) : PT_IDLE, qi = act ? min(q - PT_LO, PT_OOR) : PT_IDLE;
-                pb[(bi >> 2) * PT_THREADS] += 1u << ((bi & 3u) * 8u);
-                pq[(qi >> 2) * PT_THREADS] += 1u << ((qi & 3u) * 8u);
-                const int f = S->state[b];
+                const unsigned b = act ? lds_u8(dna_a + it * 32) : (PT_LO + PT_IDLE);
+                const unsigned q = act ? lds_u8(qual_a + it * 32) : (PT_LO + PT_IDLE);
+                const unsigned bi = min(b - PT_LO, act ? PT_OOR : PT_IDLE), qi = min(q - PT_LO, act ? PT_OOR : PT_IDLE);
+                const uint32_t wb = pb_a + ((bi >> 2) << 10), wq = pq_a + ((qi >> 2) << 10);     // [word][thread], 256 threads * 4 B
+                sts_u32(wb, lds_u32(wb) + (1u << ((bi & 3u) << 3)));
+                sts_u32(wq, lds_u32(wq) + (1u << ((qi & 3u) << 3)));
+                const int f = (int)lds_u32(state_a + (b << 2));
                 if (act && f != 256 && f != (int)q) {
                     if (f < 0) {
                         const int old = atomicCAS(&S->state[b], -1, (int)q);

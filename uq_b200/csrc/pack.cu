@@ -132,8 +132,7 @@ __device__ __forceinline__ void place_chunk16(const uint32_t (&code)[16], uint32
     uint32_t prev = 0;
 #pragma unroll
     for (int k = 0; k < NW; k++) {
-        const uint32_t out = __funnelshift_r(w[k], prev, sh);
-        if (out) atomicOr(&stage[w0 + k], out);
+        atomicOr(&stage[w0 + k], __funnelshift_r(w[k], prev, sh));
         prev = w[k];
     }
     if (sh) {
@@ -222,10 +221,12 @@ __global__ void __launch_bounds__(PKT_THREADS) k_pack_tiles(const uint8_t* __res
                     const uint32_t vd = __funnelshift_r(xd[k], xd[k + 1], sd), vq = __funnelshift_r(xq[k], xq[k + 1], sq);
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
-                        const uint32_t be = lut->base[(vd >> (8 * b)) & 0xFFu];
+                        // branch-free: both LUTs are always read, the N-trick code is a select
+                        const uint32_t be = lut->base[__byte_perm(vd, 0, 0x4440 + b)];
+                        const uint32_t ql = lut->qual[__byte_perm(vq, 0, 0x4440 + b)];
                         const uint32_t tq = be >> 8;
                         cdv[4 * k + b] = be & 0xFFu;
-                        cqv[4 * k + b] = tq != 0xFFu ? tq : lut->qual[(vq >> (8 * b)) & 0xFFu];
+                        cqv[4 * k + b] = (tq != 0xFFu) ? tq : ql;
                     }
                 }
                 place_chunk16_any(bb, cdv, stage_d, gd);
