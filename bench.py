@@ -160,6 +160,17 @@ def run_ours(args):
                 "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                 "launches_per_step": top_cnt / args.steps, "avg_launch_ms": round(top_ms / max(top_cnt, 1), 4),
                 "share_of_step": round(top_ms / (ms * 1.0), 4), "algorithmic_bytes_per_launch": top_bytes / max(top_cnt, 1)}
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (same workload, per launch)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_full_100m_summary.json")) as f:
+            for rec in json.load(f):
+                if rec["kernel"].replace("void ", "").split("<")[0] == top_name.split("<")[0] and n == 100_000_000:
+                    gb = float(rec["dram__bytes_read.sum"].split()[0]) + float(rec["dram__bytes_write.sum"].split()[0])
+                    roofline["traffic"] = gb * 1e9
+                    roofline["traffic_source"] = "profiles/r01_ncu_full_100m_summary.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+                    break
+    except Exception:
+        pass
     a_enc = total_fbytes + total_out
     pipeline = {"algorithmic_bytes_per_step": a_enc, "achieved_GBps": round(a_enc / 1e9 / t, 1),
                 "frac_of_peak": round(a_enc / 1e9 / t / (peak * world), 4),
