@@ -102,36 +102,56 @@ __global__ void __launch_bounds__(DC) k_decode_write(const dec_params* __restric
         const uint8_t* drow = dna + r * P.wd;
         const uint8_t* qrow = qual + r * P.wq;
         uint8_t* o = out + rec_off[r];
-        uint32_t hl = 0, len = 0;
-        if (lane == 0) {
-            // ---- QNAME: prefix + sum(column text + separator) + suffix (uq.py:1010-1024) ----
-            uint8_t* w = o;
-            for (uint32_t i = 0; i < P.prefix_len; i++) *w++ = P.prefix[i];
-            for (uint32_t c = 0; c < P.ncols; c++) {
+        // ---- QNAME: prefix + sum(column text + separator) + suffix (uq.py:1010-1024) ----
+        // lane c formats column c: text length -> warp prefix sum over the columns -> every lane writes
+        // its own column text (and the separator behind it) straight to its place in the output line
+        uint32_t run = P.prefix_len;                // offset of the next column's text within the line
+        for (uint32_t c0 = 0; c0 < P.ncols; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            uint32_t tl = 0;
+            unsigned long long raw = 0;
+            long long v = 0;
+            if (c < P.ncols) {
                 const dec_col& dc = P.cols[c];
-                unsigned long long raw = load_le(dc.data + r * dc.itemsize, dc.itemsize);
+                raw = load_le(dc.data + r * dc.itemsize, dc.itemsize);
+                if (dc.format == 0) {
+                    tl = raw < dc.dict_count ? dc.dict_len[raw] : 0u;
+                } else {
+                    v = (long long)raw + (dc.offset ? dc.min_val : 0ll);
+                    tl = dec_digits(v);
+                }
+                if (c < P.nseps) tl += 1;           // the separator that follows this column
+            }
+            uint32_t incl = tl;
+#pragma unroll
+            for (int sh = 1; sh < 32; sh <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, sh);
+                if (lane >= (unsigned)sh) incl += t;
+            }
+            if (c < P.ncols) {
+                const dec_col& dc = P.cols[c];
+                uint8_t* w = o + run + incl - tl;
+                uint32_t body = tl - (c < P.nseps ? 1u : 0u);
                 if (dc.format == 0) {
                     if (raw < dc.dict_count) {
-                        const uint8_t* s = dc.dict + raw * dc.dict_width;
-                        const uint32_t l = dc.dict_len[raw];
-                        for (uint32_t i = 0; i < l; i++) *w++ = s[i];
+                        const uint8_t* sp = dc.dict + raw * dc.dict_width;
+                        for (uint32_t i = 0; i < body; i++) w[i] = sp[i];
                     }
                 } else {
-                    long long v = (long long)raw + (dc.offset ? dc.min_val : 0ll);
-                    const uint32_t nd = dec_digits(v);
                     unsigned long long a = v < 0 ? (unsigned long long)(-(v + 1)) + 1ull : (unsigned long long)v;
                     if (v < 0) w[0] = '-';
-                    for (uint32_t i = 0; i < nd - (v < 0 ? 1u : 0u); i++) { w[nd - 1 - i] = (uint8_t)('0' + a % 10ull); a /= 10ull; }
-                    w += nd;
+                    for (uint32_t i = 0; i < body - (v < 0 ? 1u : 0u); i++) { w[body - 1 - i] = (uint8_t)('0' + a % 10ull); a /= 10ull; }
                 }
-                if (c < P.nseps) *w++ = P.seps[c];
+                if (c < P.nseps) w[body] = P.seps[c];
             }
-            for (uint32_t i = 0; i < P.suffix_len; i++) *w++ = P.suffix[i];
-            *w = '\n';
-            hl = (uint32_t)(w - o) + 1;
-            len = row_read_len(drow, P.wd, P.bb, P.dna_max, P.variable);
+            run += __shfl_sync(0xffffffffu, incl, 31);
         }
-        hl = __shfl_sync(0xffffffffu, hl, 0);
+        for (uint32_t i = lane; i < P.prefix_len; i += 32) o[i] = P.prefix[i];
+        for (uint32_t i = lane; i < P.suffix_len; i += 32) o[run + i] = P.suffix[i];
+        if (lane == 0) o[run + P.suffix_len] = '\n';
+        const uint32_t hl = run + P.suffix_len + 1;
+        uint32_t len = 0;
+        if (lane == 0) len = row_read_len(drow, P.wd, P.bb, P.dna_max, P.variable);
         len = __shfl_sync(0xffffffffu, len, 0);
         uint8_t* od = o + hl;                  // DNA line
         uint8_t* oq = od + len + 3;            // after "\n+\n"

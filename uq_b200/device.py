@@ -205,9 +205,27 @@ class Context:
         return DeviceArray(self, h)
 
 
+class _PinnedArray(np.ndarray):
+    """ndarray over pinned host memory that keeps its PinnedBuffer (and so the allocation) alive."""
+    _pin = None
+
+
 class PinnedBuffer:
     def __init__(self, ctx, ptr, array):
         self.ctx, self.ptr, self.array = ctx, ptr, array
+
+    def owned_view(self, nbytes=None):
+        """uint8 ndarray over the buffer; the pinned allocation is released when the last view dies."""
+        a = (self.array if nbytes is None else self.array[:nbytes]).view(_PinnedArray)
+        a._pin = self
+        return a
+
+    def __del__(self):
+        try:
+            if self.ptr and self.ctx.h:
+                self.free()
+        except Exception:
+            pass
 
     def free(self):
         if self.ptr:

@@ -613,7 +613,9 @@ def decode(members, config, ctx=None):
     handles = (C.c_void_p * max(ncol, 1))(*[c.h for c in dcols])
     ctx.check(ctx.lib.uqb_decode(ctx.h, dna.h, qual.h, handles, C.byref(p), C.byref(h)))
     out = DeviceArray(ctx, h)
-    data = out.download()
+    pin = ctx.pinned_empty(out.nbytes)                  # pinned: the D2H copy runs at PCIe speed
+    out.download(out=pin.array)
+    data = pin.owned_view(out.nbytes)
     for a in [dna, qual, out] + dcols:
         a.free()
     if own:
