@@ -67,6 +67,8 @@ int uqb_array_download(uqb_ctx* ctx, const uqb_array* a, void* host, uint64_t nb
  * pinned; the array must stay allocated until uqb_ctx_copy_sync returns. */
 int uqb_array_download_async(uqb_ctx* ctx, const uqb_array* a, void* host, uint64_t nbytes);
 int uqb_ctx_copy_sync(uqb_ctx* ctx);
+/* index of the first differing byte of two device arrays, -1 if identical (round-trip checks at full size) */
+int uqb_array_first_difference(uqb_ctx* ctx, const uqb_array* a, const uqb_array* b, int64_t* first);
 int uqb_array_free(uqb_ctx* ctx, uqb_array* a);
 void* uqb_array_device_ptr(const uqb_array* a);   /* for benches/tests that adopt device memory */
 

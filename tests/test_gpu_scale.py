@@ -137,3 +137,29 @@ def test_config5_shape_variable_length_roundtrip_20k(ctx):
     decoded = host.decode(out, cfg, ctx=ctx).tobytes()
     assert records_multiset(decoded) == records_multiset(fastq)
     dev.free()
+
+
+def test_full_size_roundtrip_on_device(ctx):
+    """BASELINE full size (100 M reads x 150 bp = 34 GB, offsets beyond 4 GiB): encode -> decode entirely in HBM,
+    the decoded text must equal the input byte for byte (compared on the device)."""
+    from uq_b200 import host
+    n = 100_000_000
+    used, free, total = ctx.mem_info()
+    if free < 120 << 30:
+        pytest.skip("needs ~100 GB of free HBM")
+    dev = ctx.synth("genome", n, 150, 1002, genome=10_000_000, pool=n // 5)
+    assert dev.nbytes > 8 << 30          # far beyond 32-bit offsets
+    fq = ctx.adopt_fastq(dev)
+    st = {}
+    members, cfg = host.encode_device(ctx, fq, sort="None", raw=["DNA", "QUAL", "QNAME"], stages=st)
+    assert cfg["reads"] == n and cfg["dna_max"] == 150 and cfg["N_qual"] == {"N": 0}
+    text = host.decode_device(ctx, st["dna"], st["qual"], st["cols"], cfg)
+    assert text.nbytes == dev.nbytes
+    assert text.first_difference(dev) == -1
+    # and the comparison itself detects a difference
+    other = ctx.synth("genome", 1000, 150, 1003, genome=10_000_000, pool=200)
+    ref = ctx.synth("genome", 1000, 150, 1002, genome=10_000_000, pool=200)
+    assert other.first_difference(ref) >= 0
+    for a in (text, other, ref):
+        a.free()
+    members.free(); fq.free(); dev.free()

@@ -90,6 +90,7 @@ SIGNATURES = {
     "uqb_array_info": (C.c_int, [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "uqb_array_upload": (C.c_int, [P, P, C.c_uint64, C.c_uint32, PP]),
     "uqb_array_download": (C.c_int, [P, P, P, C.c_uint64]),
+    "uqb_array_first_difference": (C.c_int, [P, P, P, C.POINTER(C.c_int64)]),
     "uqb_array_free": (C.c_int, [P, P]),
     "uqb_array_device_ptr": (C.c_void_p, [P]),
     "uqb_fastq_load": (C.c_int, [P, P, C.c_uint64, PP]),

@@ -431,6 +431,36 @@ extern "C" int uqb_ctx_copy_sync(uqb_ctx* ctx) {
     return 0;
 }
 
+// byte-wise comparison of two device arrays (full-size round-trip checks without a 34 GB host copy)
+__global__ void k_first_diff(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint64_t n, unsigned long long* __restrict__ first) {
+    unsigned long long best = ~0ull;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i < n; i += (uint64_t)gridDim.x * blockDim.x * 16) {
+        if (i + 16 <= n) {
+            const uint4 x = *reinterpret_cast<const uint4*>(a + i), y = *reinterpret_cast<const uint4*>(b + i);
+            if (x.x != y.x || x.y != y.y || x.z != y.z || x.w != y.w) {
+                for (int k = 0; k < 16; k++) if (a[i + k] != b[i + k]) { if (i + k < best) best = i + k; break; }
+            }
+        } else {
+            for (uint64_t k = i; k < n; k++) if (a[k] != b[k]) { if (k < best) best = k; break; }
+        }
+    }
+    if (best != ~0ull) atomicMin(first, best);
+}
+
+extern "C" int uqb_array_first_difference(uqb_ctx* ctx, const uqb_array* a, const uqb_array* b, int64_t* first) {
+    if (a->nbytes() != b->nbytes()) { *first = (int64_t)(a->nbytes() < b->nbytes() ? a->nbytes() : b->nbytes()); return 0; }
+    unsigned long long* d;
+    UQB_TRY(uqb_dalloc_t(ctx, &d, 1));
+    UQB_CUDA(cudaMemsetAsync(d, 0xFF, 8, ctx->stream));
+    const uint64_t n = a->nbytes();
+    if (n) UQB_LAUNCH_B(2 * n, k_first_diff, uqb_grid(ctx, n, 256 * 16, 16), 256, 0, (const uint8_t*)a->d, (const uint8_t*)b->d, n, d);
+    unsigned long long h = 0;
+    UQB_TRY(uqb_readback(ctx, &h, d, 8));
+    UQB_TRY(uqb_dfree(ctx, d, 8));
+    *first = h == ~0ull ? -1 : (int64_t)h;
+    return 0;
+}
+
 extern "C" int uqb_array_free(uqb_ctx* ctx, uqb_array* a) {
     if (!a) return 0;
     int r = 0;

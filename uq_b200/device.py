@@ -263,6 +263,12 @@ class DeviceArray:
             return out[:self.nbytes]
         return out[:self.nbytes].reshape(self.n, self.width)
 
+    def first_difference(self, other):
+        """index of the first differing byte, -1 if the two device arrays are identical"""
+        r = C.c_int64()
+        self.ctx.check(self.ctx.lib.uqb_array_first_difference(self.ctx.h, self.h, other.h, C.byref(r)))
+        return int(r.value)
+
     def download_async(self, out):
         """Queue the D2H copy into `out` (uint8 ndarray over pinned memory) on the copy stream; call ctx.copy_sync()."""
         self.ctx.check(self.ctx.lib.uqb_array_download_async(self.ctx.h, self.h, _ptr(out), self.nbytes))

@@ -541,32 +541,12 @@ def _upload_table(ctx, members, name, pattern):
     raise UQError('ERROR: No %s data was found in this uQ file?!' % name)
 
 
-def decode(members, config, ctx=None):
-    """members/config as container.read_container returns them -> FASTQ bytes (ndarray uint8)."""
+def decode_device(ctx, dna, qual, dcols, config):
+    """Logical tables already in HBM (dna / qual: [n][bytes]; dcols: one DeviceArray per QNAME column,
+    already expanded through QNAME.key) -> DeviceArray holding the FASTQ text (uq.py:1002-1058)."""
     import ctypes as C
-    own = ctx is None
-    ctx = ctx or Context()
-    pat = config['pattern']
-    dna = _upload_table(ctx, members, 'DNA', pat[0])
-    qual = _upload_table(ctx, members, 'QUAL', pat[1])
     cols_meta = config['QNAME_columns']
     ncol = len(cols_meta)
-    keyed = 'QNAME.key' in members
-    dcols = []
-    key = ctx.upload(np.ascontiguousarray(members['QNAME.key'], dtype=np.uint32)) if keyed else None
-    for i, meta in enumerate(cols_meta):
-        nm = 'QNAME_%d' % (i + 1) + ('' if keyed else '.raw')
-        if nm not in members:
-            raise UQError('ERROR: No QNAME data exists in this uQ file?')
-        c = ctx.upload(np.ascontiguousarray(members[nm], dtype=meta['dtype']))
-        if keyed:
-            c2 = ctx.gather_rows(c, key)                                           # uq.py:973
-            c.free()
-            c = c2
-        dcols.append(c)
-    if key is not None:
-        key.free()
-
     p = L.DecodeParams()
     for i, ch in enumerate(config['bases']):
         p.base_char[i] = ord(ch)
@@ -612,11 +592,38 @@ def decode(members, config, ctx=None):
     h = C.c_void_p()
     handles = (C.c_void_p * max(ncol, 1))(*[c.h for c in dcols])
     ctx.check(ctx.lib.uqb_decode(ctx.h, dna.h, qual.h, handles, C.byref(p), C.byref(h)))
-    out = DeviceArray(ctx, h)
-    pin = ctx.pinned_empty(out.nbytes)                  # pinned: the D2H copy runs at PCIe speed
-    out.download(out=pin.array)
-    data = pin.owned_view(out.nbytes)
-    for a in [dna, qual, out] + dcols:
+    return DeviceArray(ctx, h)
+
+
+def decode(members, config, ctx=None, out=None):
+    """members/config as container.read_container returns them -> FASTQ bytes (uint8 ndarray).  `out`: optional
+    uint8 ndarray to receive the text (e.g. over pinned memory, which makes the D2H copy run at PCIe speed)."""
+    own = ctx is None
+    ctx = ctx or Context()
+    pat = config['pattern']
+    dna = _upload_table(ctx, members, 'DNA', pat[0])
+    qual = _upload_table(ctx, members, 'QUAL', pat[1])
+    cols_meta = config['QNAME_columns']
+    keyed = 'QNAME.key' in members
+    dcols = []
+    key = ctx.upload(np.ascontiguousarray(members['QNAME.key'], dtype=np.uint32)) if keyed else None
+    for i, meta in enumerate(cols_meta):
+        nm = 'QNAME_%d' % (i + 1) + ('' if keyed else '.raw')
+        if nm not in members:
+            raise UQError('ERROR: No QNAME data exists in this uQ file?')
+        c = ctx.upload(np.ascontiguousarray(members[nm], dtype=meta['dtype']))
+        if keyed:
+            c2 = ctx.gather_rows(c, key)                                           # uq.py:973
+            c.free()
+            c = c2
+        dcols.append(c)
+    if key is not None:
+        key.free()
+    text = decode_device(ctx, dna, qual, dcols, config)
+    if out is not None and out.size < text.nbytes:
+        raise UQError('ERROR: output buffer too small (%d < %d bytes)' % (out.size, text.nbytes))
+    data = text.download(out=out).reshape(-1)
+    for a in [dna, qual, text] + dcols:
         a.free()
     if own:
         ctx.close()
