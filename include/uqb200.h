@@ -61,6 +61,7 @@ int         uqb_mem_info(uqb_ctx* ctx, uint64_t* in_use, uint64_t* dev_free, uin
 
 /* ---- arrays -------------------------------------------------------------------------------- */
 int uqb_array_info(const uqb_array* a, uint64_t* n, uint32_t* width);
+int uqb_array_alloc(uqb_ctx* ctx, uint64_t n, uint32_t width, uqb_array** out);      /* uninitialised */
 int uqb_array_upload(uqb_ctx* ctx, const void* host, uint64_t n, uint32_t width, uqb_array** out);
 int uqb_array_download(uqb_ctx* ctx, const uqb_array* a, void* host, uint64_t nbytes);
 /* D2H on the copy stream, ordered after all work queued so far on the compute stream.  `host` should be
@@ -122,6 +123,9 @@ typedef struct {
 } uqb_stats;
 
 int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out);
+/* multi-GPU shards: the handle holds records [rbase, rbase+n) of a larger file whose first QNAME line is
+ * `name`; uqb_analyze then measures prefixes / suffixes / byte counts against that line (indices stay local) */
+int uqb_fastq_set_reference(uqb_ctx* ctx, uqb_fastq* fq, const uint8_t* name, uint32_t len, uint64_t rbase);
 
 /* ---- stage 1b: QNAME tokenisation + Pass-2 column statistics (replaces qname_reader and the
  *      Pass-2 loop uq.py:557-638; the typing decisions uq.py:586-602, 641-676 stay in Python) -- */
@@ -142,6 +146,12 @@ typedef struct {
  * sequence differs (the reference falls back / exits at uq.py:609-613, 637), -1 if none. */
 int uqb_qname_scan(uqb_ctx* ctx, uqb_fastq* fq, uint32_t prefix_len, uint32_t suffix_len,
                    const uint8_t* seps, uint32_t nseps, uqb_colstats* cols, int64_t* bad_record);
+/* as uqb_qname_scan with a per-column mode (NULL = all 0): 0 automatic, 1 no dictionary wanted (the column
+ * is known to leave 'mapping'), 2 dictionary forced (skip the checkpoint-0 shortcut) - used by multi-GPU merges */
+int uqb_qname_scan_ex(uqb_ctx* ctx, uqb_fastq* fq, uint32_t prefix_len, uint32_t suffix_len,
+                      const uint8_t* seps, uint32_t nseps, const uint8_t* col_mode, uqb_colstats* cols, int64_t* bad_record);
+/* first record (local index) holding each dictionary entry, uint32[count] */
+int uqb_qname_dict_first(uqb_ctx* ctx, uqb_fastq* fq, uint32_t col, uint32_t* host, uint64_t count);
 /* sorted dictionary of a column (uq.py:659-661): count rows x width bytes, zero padded */
 int uqb_qname_dict_info(uqb_ctx* ctx, uqb_fastq* fq, uint32_t col, uint64_t* count, uint32_t* width);
 int uqb_qname_dict(uqb_ctx* ctx, uqb_fastq* fq, uint32_t col, uint8_t* host, uint64_t nbytes);
@@ -179,6 +189,9 @@ int uqb_pack(uqb_ctx* ctx, uqb_fastq* fq, const uqb_pack_params* p, uqb_array** 
 int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** perm, uqb_array** key,
                   uqb_array** key_sorted, uqb_array** uniq, uint64_t* n_unique);
 int uqb_gather_rows(uqb_ctx* ctx, const uqb_array* table, const uqb_array* perm, uqb_array** out); /* out[i] = table[perm[i]] */
+int uqb_add_scalar_u32(uqb_ctx* ctx, uqb_array* a, uint32_t value);   /* a[i] += value, uint32 array */
+/* lower_bound of k host rows in a table sorted in memcmp order (splitter search of the multi-GPU sample sort) */
+int uqb_rows_lower_bound(uqb_ctx* ctx, const uqb_array* sorted_table, const uint8_t* probes_host, uint32_t k, uint64_t* out_host);
 /* uint32 -> little-endian integer of itemsize bytes (key.astype(min_scalar_type(max)), uq.py:790) */
 int uqb_narrow_u32(uqb_ctx* ctx, const uqb_array* a, uint32_t itemsize, uqb_array** out);
 /* QNAME columns <-> rows in sort-key form: columns concatenated big-endian at their own widths,

@@ -18,7 +18,8 @@ def records(fastq):
     return [lines[i:i + 4] for i in range(0, nl - nl % 4, 4)], nl
 
 
-def emu_stats(fastq):
+def emu_stats(fastq, ref=None, base=0):
+    """ref / base: a multi-GPU shard measured against the global first QNAME line, holding records base.."""
     recs, nl = records(fastq)
     st = L.Stats()
     for i in range(256):
@@ -26,12 +27,13 @@ def emu_stats(fastq):
         st.last_count_mismatch[i] = -1
     for j in range(L.HDR_MAX + 1):
         st.first_lcp_eq[j] = st.first_lcs_eq[j] = st.first_short_prefix[j] = st.first_short_suffix[j] = NONE
-    first = recs[0][0]
+    own_first = recs[0][0]
+    first = own_first if ref is None else ref
     last = recs[-1][0]
-    st.first_len, st.last_len = len(first), len(last)
-    for i, b in enumerate(first): st.first_name[i] = b
+    st.first_len, st.last_len = len(own_first), len(last)
+    for i, b in enumerate(own_first): st.first_name[i] = b
     for i, b in enumerate(last): st.last_name[i] = b
-    st.bad_first_char = -1 if first[:1] == b"@" else 0
+    st.bad_first_char = -1 if own_first[:1] == b"@" else 0
     st.bad_plus_record = st.bad_len_record = -1
     dmin, dmax, maxname = None, 0, 0
     seen = {}
@@ -52,7 +54,7 @@ def emu_stats(fastq):
         while lcp < lim and name[lcp] == first[lcp]: lcp += 1
         lcs = 0
         while lcs < lim and name[len(name) - 1 - lcs] == first[len(first) - 1 - lcs]: lcs += 1
-        if r >= 1:
+        if r + base >= 1:
             st.first_lcp_eq[lcp] = min(st.first_lcp_eq[lcp], r)
             st.first_lcs_eq[lcs] = min(st.first_lcs_eq[lcs], r)
             if lcp == len(name) and len(name) < len(first):

@@ -1,0 +1,82 @@
+"""Global (one container) encode over 2 GPUs against the single-GPU encode of the same file - needs 2 GPUs
+(`gpurun --gpus 2 -- python -m pytest tests/test_multigpu_gpu.py -m gpu`); skipped on a single-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("genome", 24000, 60, dict(sort="DNA")),
+    ("genome", 24000, 60, dict(sort="None", raw=["DNA", "QUAL", "QNAME"])),
+    ("genome", 9000, 40, dict(sort="QUAL", raw=["DNA"])),
+    ("casava", 26000, 50, dict(sort="QNAME")),
+    ("casava", 8000, 50, dict(sort="DNA", raw=["QNAME", "QUAL"])),
+    ("illumina", 7000, 30, dict()),
+]
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle import synth
+    from uq_b200 import host, multigpu as mg
+    from uq_b200.device import Context
+    ctx = Context(rank)
+    comm = mg.Comm(dist, "cuda:%d" % rank)
+    results = []
+    for kind, n, length, kw in CASES:
+        kwg = dict(genome=max(4 * length, n // 6), pool=max(1, n // 7)) if kind == "genome" else {}
+        n0 = int(n * 0.55)
+        first, cnt = (0, n0) if rank == 0 else (n0, n - n0)
+        shard = synth.make_fastq(kind=kind, n=cnt, length=length, seed=21, first=first, **kwg)
+        fq = ctx.load_fastq(shard)
+        res, cfg = mg.encode_sharded(ctx, comm, fq, **kw)
+        members = mg.assemble(comm, res.download())
+        res.free(); fq.free()
+        if rank == 0:
+            whole = synth.make_fastq(kind=kind, n=n, length=length, seed=21, first=0, **kwg)
+            want, want_cfg = host.encode(whole, ctx=ctx, **kw)
+            bad = []
+            if sorted(members) != sorted(want):
+                bad.append("names %s vs %s" % (sorted(members), sorted(want)))
+            else:
+                for k in want:
+                    a, b = members[k], np.asarray(want[k])
+                    if a.dtype != b.dtype or a.shape != b.shape or not np.array_equal(a, b):
+                        bad.append("%s dtype %s/%s shape %s/%s equal %s" % (k, a.dtype, b.dtype, a.shape, b.shape,
+                                                                           a.shape == b.shape and bool(np.array_equal(a, b))))
+            import json
+            if json.loads(json.dumps(cfg, default=str)) != json.loads(json.dumps(want_cfg, default=str)):
+                bad.append("config differs")
+            results.append((kind, kw, bad))
+    if rank == 0:
+        q.put(results)
+    dist.destroy_process_group()
+
+
+def test_two_gpu_global_encode_equals_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    results = q.get(timeout=600)
+    for p in procs: p.join(timeout=120)
+    assert all(p.exitcode == 0 for p in procs)
+    for kind, kw, bad in results:
+        assert not bad, (kind, kw, bad)

@@ -1,0 +1,130 @@
+"""Host-side merges of the multi-GPU global encode (uq_b200/multigpu.py) on CPU: per-shard statistics produced
+by the contract emulation must merge into exactly the statistics of the whole file; the object collectives run
+over 2 gloo ranks."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import golden_case, load_manifest
+from emu import emu_colstats, emu_stats
+from uq_b200 import _lib as L, host, multigpu as mg
+from test_gpu_parity import STAT_FIELDS, STAT_SCALARS
+
+CASES = ["c2_keyed_sortDNA", "c3_casava_sortQNAME", "c7_offset_suffix_keyed", "c6_checkpoints", "c5_variable_raw"]
+
+
+def shards_of(fq, cuts):
+    lines = fq.split(b"\n")[:-1]
+    recs = [b"\n".join(lines[i:i + 4]) + b"\n" for i in range(0, len(lines), 4)]
+    bounds = [0] + [int(len(recs) * c) for c in cuts] + [len(recs)]
+    return [(b"".join(recs[a:b]), a, b - a) for a, b in zip(bounds[:-1], bounds[1:])]
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("cuts", [(0.5,), (0.6, 0.61, 0.9)])
+def test_merged_statistics_equal_whole_file_statistics(name, cuts):
+    fq, _, kw = golden_case(name)
+    shards = shards_of(fq, cuts)
+    ref = fq.split(b"\n")[0]
+    parts = []
+    for data, base, n in shards:
+        st, _ = emu_stats(data, ref=ref, base=base)
+        parts.append((mg.stats_to_plain(st), base, n))
+    parts[0][0]["first_name"] = ref
+    got = mg.merge_stats(parts)
+    want, n_total = emu_stats(fq)
+    for f in STAT_SCALARS:
+        assert getattr(got, f) == getattr(want, f), f
+    for f in STAT_FIELDS:
+        assert list(getattr(got, f)) == list(getattr(want, f)), f
+    prefix, suffix, seps = host.derive_qname_layout(got, n_total)
+    # column statistics and dictionaries
+    whole_cols, bad, whole_dicts = emu_colstats(fq, len(prefix), len(suffix), seps)
+    ncols = len(seps) + 1
+    early = [whole_cols[c].n_distinct == L.U64_MAX for c in range(ncols)]
+    plains, dicts = [], []
+    for data, base, n in shards:
+        cols, bad, _ = emu_colstats(data, len(prefix), len(suffix), seps)
+        plains.append(mg.colstats_to_plain(cols, ncols))
+        # local dictionaries with global first occurrences, computed directly
+        toks = [l.split(b"\n")[0] for l in data.split(b"\n")[0::4][:-1]]
+        d = {}
+        for c in range(ncols):
+            if early[c]:
+                continue
+            first = {}
+            for r, name_line in enumerate(data.split(b"\n")[0::4][:n]):
+                mid = name_line[len(prefix):len(name_line) - len(suffix)].decode("latin-1")
+                import re
+                tok = re.split("(.*)".join(seps), mid)[c]
+                first.setdefault(tok, base + r)
+            ks = sorted(first)
+            d[c] = (ks, [first[k] for k in ks])
+        dicts.append(d)
+    if n_total > 10000 and shards[0][2] < 10001:
+        pytest.skip("rank 0 would not hold checkpoint 0")
+    # rank 0's checkpoint-0 value is the global one for early-demoted columns
+    for c in range(ncols):
+        if early[c]:
+            plains[0][c]["distinct_at"][0] = int(whole_cols[c].distinct_at[0])
+    merged, gd = mg.merge_colstats(plains, n_total, early, dicts)
+    for c in range(ncols):
+        for f in ("all_int", "all_canonical", "overflow", "min_len", "max_len", "n_distinct", "n_checkpoints"):
+            assert getattr(merged[c], f) == getattr(whole_cols[c], f), (c, f)
+        if whole_cols[c].all_int:
+            assert (merged[c].min_val, merged[c].max_val) == (whole_cols[c].min_val, whole_cols[c].max_val)
+        assert list(merged[c].distinct_at) == list(whole_cols[c].distinct_at), c
+        if c in whole_dicts:
+            assert gd[c] == whole_dicts[c]
+    assert host.decide_columns(merged, n_total, lambda i: gd[i]) == host.decide_columns(whole_cols, n_total, lambda i: whole_dicts[i])
+
+
+def test_pick_splitters_is_deterministic_and_sorted():
+    rng = np.random.default_rng(3)
+    s = rng.integers(0, 4, size=(500, 5), dtype=np.uint8)
+    a = mg.pick_splitters(s, 4)
+    b = mg.pick_splitters(s[rng.permutation(500)], 4)
+    assert a.shape == (3, 5) and np.array_equal(a, b)
+    v = a.view("V5").reshape(-1)
+    assert np.array_equal(np.sort(v), v)
+    assert mg.pick_splitters(np.zeros((0, 5), np.uint8), 4).shape == (0, 5)
+    assert mg.n_checkpoints(10000) == 0 and mg.n_checkpoints(10001) == 1 and mg.n_checkpoints(20001) == 2
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = mg.Comm(dist, "cpu")
+    fq, _, _ = golden_case("c3_casava_sortQNAME")
+    data, base, n = shards_of(fq, (0.4,))[rank]
+    ref = comm.all_gather_object(data.split(b"\n")[0])[0]
+    st, _ = emu_stats(data, ref=ref, base=base)
+    parts = comm.all_gather_object((mg.stats_to_plain(st), base, n))
+    parts[0][0]["first_name"] = ref
+    merged = mg.merge_stats(parts)
+    recv = comm.exchange_counts([10 * rank + k for k in range(world)])
+    if rank == 0:
+        q.put((host.derive_qname_layout(merged, 700), recv))
+    dist.destroy_process_group()
+
+
+def test_object_collectives_over_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    layout, recv = q.get(timeout=120)
+    for p in procs: p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    assert layout == ("@EAS139:136:FC706VJ:", "", "::: :::")
+    assert recv == [0, 10]          # rank 0 receives send_counts[0] of rank 0 (=0) and of rank 1 (=10)

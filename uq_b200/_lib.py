@@ -88,6 +88,7 @@ SIGNATURES = {
     "uqb_host_free": (C.c_int, [P, P]),
     "uqb_mem_info": (C.c_int, [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "uqb_array_info": (C.c_int, [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "uqb_array_alloc": (C.c_int, [P, C.c_uint64, C.c_uint32, PP]),
     "uqb_array_upload": (C.c_int, [P, P, C.c_uint64, C.c_uint32, PP]),
     "uqb_array_download": (C.c_int, [P, P, P, C.c_uint64]),
     "uqb_array_first_difference": (C.c_int, [P, P, P, C.POINTER(C.c_int64)]),
@@ -103,6 +104,11 @@ SIGNATURES = {
     "uqb_split": (C.c_int, [P, P, C.POINTER(SplitInfo)]),
     "uqb_fastq_line_offsets": (C.c_int, [P, P, C.c_uint64, C.c_uint64, P]),
     "uqb_analyze": (C.c_int, [P, P, C.POINTER(Stats)]),
+    "uqb_fastq_set_reference": (C.c_int, [P, P, P, C.c_uint32, C.c_uint64]),
+    "uqb_qname_scan_ex": (C.c_int, [P, P, C.c_uint32, C.c_uint32, P, C.c_uint32, P, C.POINTER(ColStats), C.POINTER(C.c_int64)]),
+    "uqb_qname_dict_first": (C.c_int, [P, P, C.c_uint32, P, C.c_uint64]),
+    "uqb_rows_lower_bound": (C.c_int, [P, P, P, C.c_uint32, P]),
+    "uqb_add_scalar_u32": (C.c_int, [P, P, C.c_uint32]),
     "uqb_qname_scan": (C.c_int, [P, P, C.c_uint32, C.c_uint32, P, C.c_uint32, C.POINTER(ColStats), C.POINTER(C.c_int64)]),
     "uqb_qname_dict_info": (C.c_int, [P, P, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "uqb_qname_dict": (C.c_int, [P, P, C.c_uint32, P, C.c_uint64]),

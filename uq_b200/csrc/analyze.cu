@@ -43,7 +43,8 @@ __global__ void k_an_init(an_dev* s) {
 }
 
 __global__ void __launch_bounds__(AN_THREADS) k_record_stats(const uint8_t* __restrict__ d, const uint64_t* __restrict__ line_off,
-                                                           uint64_t n_reads, uint32_t first_len, an_dev* __restrict__ s) {
+                                                           uint64_t n_reads, const uint8_t* __restrict__ ref, uint64_t rbase,
+                                                           uint32_t first_len, an_dev* __restrict__ s) {
     __shared__ uint8_t first[UQB_HDR_MAX];
     __shared__ uint8_t slot_of[256];          // byte value -> slot in the distinct-char list of line 1
     __shared__ uint8_t slot_char[MAXCH];
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(AN_THREADS) k_record_stats(const uint8_t* __re
     __shared__ int nslots_s;
     __shared__ long long blk_last[MAXCH];
     const unsigned tid = threadIdx.x;
-    for (unsigned i = tid; i < first_len; i += AN_THREADS) first[i] = d[i];
+    for (unsigned i = tid; i < first_len; i += AN_THREADS) first[i] = ref[i];
     slot_of[tid] = 255;
     if (tid < MAXCH) { first_cnt[tid] = 0; blk_last[tid] = -1; }
     __syncthreads();
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(AN_THREADS) k_record_stats(const uint8_t* __re
         }
         unsigned lcs = 0;
         while (lcs < lim && __ldg(name + name_len - 1 - lcs) == first[first_len - 1 - lcs]) lcs++;
-        if (r >= 1) {
+        if (r + rbase >= 1) {
             atomicMin(&s->first_lcp_eq[lcp], (long long)r);
             atomicMin(&s->first_lcs_eq[lcs], (long long)r);
             if (lcp == name_len && name_len < first_len) atomicMin(&s->first_short_prefix[name_len], (long long)r);
@@ -231,11 +232,12 @@ struct rs_smem {
 
 __global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
                                                             const uint64_t* __restrict__ line_off, uint64_t r_begin, uint64_t n_reads,
+                                                            const uint8_t* __restrict__ ref, uint64_t rbase,
                                                             uint32_t first_len, an_dev* __restrict__ s, unsigned int* __restrict__ fallback) {
     extern __shared__ __align__(128) uint8_t rs_raw[];
     rs_smem* S = reinterpret_cast<rs_smem*>(rs_raw);
     const unsigned tid = threadIdx.x, lane = tid & 31u;
-    for (unsigned i = tid; i < first_len; i += TL_R) S->first[i] = d[i];
+    for (unsigned i = tid; i < first_len; i += TL_R) S->first[i] = ref[i];
     for (unsigned i = tid; i < 256; i += TL_R) S->slot_of[i] = 255;
     for (unsigned i = tid; i <= UQB_HDR_MAX; i += TL_R) { S->lcp_first[i] = S->lcs_first[i] = S->sp_first[i] = S->ss_first[i] = 0xFFFFFFFFu; }
     if (tid < RS_SLOTS) S->last_mis[tid] = 0;
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __re
         }
         // first record per lcp / lcs value: the lowest lane of each match group is the lowest record
         {
-            const bool part = active && r >= 1;
+            const bool part = active && r + rbase >= 1;
             const unsigned key1 = part ? lcp : 0xFFFFu, key2 = part ? lcs : 0xFFFFu;
             const unsigned m1 = __match_any_sync(0xffffffffu, key1), m2 = __match_any_sync(0xffffffffu, key2);
             if (part && (int)lane == __ffs(m1) - 1) atomicMin(&S->lcp_first[lcp], (uint32_t)r);
@@ -508,7 +510,8 @@ static int stats_tiles_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsig
     const unsigned g1 = (unsigned)(ntiles < (uint64_t)ctx->sm_count * 3 ? ntiles : (uint64_t)ctx->sm_count * 3);
     const unsigned g2 = (unsigned)(ntiles < (uint64_t)ctx->sm_count * 2 ? ntiles : (uint64_t)ctx->sm_count * 2);
     const uint64_t ab = (uint64_t)((double)fq->n * (double)(r1 - r0) / (double)(fq->n_reads ? fq->n_reads : 1)) + 32 * (r1 - r0);
-    UQB_LAUNCH_B(ab, k_record_stats_tiles, g1, TL_R, sizeof(rs_smem), fq->d, fq->n, fq->line_off, r0, r1, flen, s, d_fb);
+    UQB_LAUNCH_B(ab, k_record_stats_tiles, g1, TL_R, sizeof(rs_smem), fq->d, fq->n, fq->line_off, r0, r1,
+                 fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb);
     UQB_LAUNCH_B(ab, k_pair_hist_tiles, g2, PT_THREADS, sizeof(pt_smem), fq->d, fq->n, fq->line_off, r0, r1, s, d_fb);
     return 0;
 }
@@ -516,7 +519,8 @@ static int stats_tiles_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsig
 static int stats_generic(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, uint32_t flen) {
     const uint64_t N = fq->n_reads;
     UQB_LAUNCH(k_an_init, 1, 256, 0, s);
-    UQB_LAUNCH(k_record_stats, uqb_blocks(N, AN_THREADS), AN_THREADS, 0, fq->d, fq->line_off, N, flen, s);
+    UQB_LAUNCH(k_record_stats, uqb_blocks(N, AN_THREADS), AN_THREADS, 0, fq->d, fq->line_off, N,
+               fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s);
     const size_t smem = (2 * PH_WORDS * PH_THREADS + 4 * 256) * sizeof(unsigned);
     UQB_CUDA(cudaFuncSetAttribute(k_pair_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     UQB_LAUNCH(k_pair_hist, uqb_grid(ctx, N, PH_THREADS / 32, 3), PH_THREADS, smem, fq->d, fq->line_off, N, s);
@@ -574,6 +578,21 @@ static int stats_finish(uqb_ctx* ctx, uqb_fastq* fq, an_dev* s, uqb_stats* out, 
     return 0;
 }
 
+// Multi-GPU: this handle holds records [rbase, rbase + n) of a larger file whose first QNAME line is `name`.
+// uqb_analyze then reports prefix/suffix/separator statistics against that line (record indices stay local).
+extern "C" int uqb_fastq_set_reference(uqb_ctx* ctx, uqb_fastq* fq, const uint8_t* name, uint32_t len, uint64_t rbase) {
+    if (len > UQB_HDR_MAX) return uqb_fail(ctx, "reference QNAME longer than %d bytes", UQB_HDR_MAX);
+    if (fq->ref_name) { UQB_TRY(uqb_dfree(ctx, fq->ref_name, 0)); fq->ref_name = nullptr; }
+    UQB_TRY(uqb_dalloc(ctx, (void**)&fq->ref_name, len + 16));
+    if (len) UQB_CUDA(cudaMemcpyAsync(fq->ref_name, name, len, cudaMemcpyHostToDevice, ctx->stream));
+    UQB_CUDA(cudaStreamSynchronize(ctx->stream));
+    fq->ref_len = len;
+    fq->rbase = rbase;
+    delete fq->cached_stats;
+    fq->cached_stats = nullptr;
+    return 0;
+}
+
 extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
     if (!fq->line_off) return uqb_fail(ctx, "uqb_analyze: call uqb_split first");
     if (fq->n_reads == 0) return uqb_fail(ctx, "uqb_analyze: no records");
@@ -582,6 +601,7 @@ extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
     const uint64_t N = fq->n_reads;
     uint64_t flen = 0;
     UQB_TRY(stats_names(ctx, fq, out, &flen));
+    if (fq->ref_name) flen = fq->ref_len;        // multi-GPU shard: everything is measured against the global line 1
     an_dev* s;
     UQB_TRY(uqb_dalloc_t(ctx, &s, 1));
     bool done_fast = false;

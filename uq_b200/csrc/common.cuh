@@ -63,6 +63,7 @@ struct uqb_qcol {                 // per QNAME column device state produced by u
     int64_t* val = nullptr;       // parsed integer value per record (valid where the token is an integer)
     uint32_t* span = nullptr;     // (start<<16 | len) of the token inside the QNAME middle part
     uint32_t* rank = nullptr;     // rank of the token in the sorted dictionary (filled lazily)
+    uint32_t* first_occ = nullptr;// first record holding each dictionary entry
     uint8_t* dict = nullptr;      // sorted distinct tokens, zero padded rows
     uint64_t dict_count = 0;
     uint32_t dict_width = 0;
@@ -75,6 +76,10 @@ struct uqb_fastq {
     uint64_t* line_off = nullptr; // uint64[n_lines + 1]
     uint64_t n_lines = 0, n_reads = 0;
     uint64_t total_bases = 0;     // sum of read lengths (set by uqb_analyze; bookkeeping for byte counts)
+    // multi-GPU: a shard compares its QNAME lines with the GLOBAL first line and knows its first global record
+    uint8_t* ref_name = nullptr;
+    uint32_t ref_len = 0;
+    uint64_t rbase = 0;
     bool streamed = false;        // split + Pass-1 statistics were produced while the bytes streamed in
     uqb_stats* cached_stats = nullptr;
     uint32_t prefix_len = 0, suffix_len = 0, ncols = 0;

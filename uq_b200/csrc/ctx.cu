@@ -387,6 +387,10 @@ extern "C" int uqb_array_info(const uqb_array* a, uint64_t* n, uint32_t* width) 
 
 extern "C" void* uqb_array_device_ptr(const uqb_array* a) { return a ? a->d : nullptr; }
 
+extern "C" int uqb_array_alloc(uqb_ctx* ctx, uint64_t n, uint32_t width, uqb_array** out) {
+    return uqb_new_array(ctx, n, width, out);
+}
+
 extern "C" int uqb_array_upload(uqb_ctx* ctx, const void* host, uint64_t n, uint32_t width, uqb_array** out) {
     uqb_array* a;
     UQB_TRY(uqb_new_array(ctx, n, width, &a));

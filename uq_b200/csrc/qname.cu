@@ -201,6 +201,12 @@ static int distinct_of_prefix(uqb_ctx* ctx, uqb_fastq* fq, const uqb_qcol& qc, u
 
 extern "C" int uqb_qname_scan(uqb_ctx* ctx, uqb_fastq* fq, uint32_t prefix_len, uint32_t suffix_len,
                               const uint8_t* seps, uint32_t nseps, uqb_colstats* cols, int64_t* bad_record) {
+    return uqb_qname_scan_ex(ctx, fq, prefix_len, suffix_len, seps, nseps, nullptr, cols, bad_record);
+}
+
+extern "C" int uqb_qname_scan_ex(uqb_ctx* ctx, uqb_fastq* fq, uint32_t prefix_len, uint32_t suffix_len,
+                                 const uint8_t* seps, uint32_t nseps, const uint8_t* col_mode,
+                                 uqb_colstats* cols, int64_t* bad_record) {
     if (!fq->line_off) return uqb_fail(ctx, "uqb_qname_scan: call uqb_split first");
     if (nseps + 1 > UQB_MAX_COLS) return uqb_fail(ctx, "uqb_qname_scan: more than %d QNAME columns", UQB_MAX_COLS);
     const uint64_t N = fq->n_reads;
@@ -252,7 +258,13 @@ extern "C" int uqb_qname_scan(uqb_ctx* ctx, uqb_fastq* fq, uint32_t prefix_len, 
         cs.n_checkpoints = ncheck;
         const uint32_t w = red[c].max_len;
         bool demoted_early = false;
-        if (ncheck >= 1) {
+        const uint8_t mode = col_mode ? col_mode[c] : 0;      // 0 auto, 1 no dictionary wanted, 2 dictionary forced
+        if (mode == 1) {
+            for (uint32_t k = 0; k < UQB_MAX_CHECKPOINTS; k++) cs.distinct_at[k] = UINT64_MAX;
+            cs.n_distinct = UINT64_MAX;
+            continue;
+        }
+        if (ncheck >= 1 && mode == 0) {
             // checkpoint 0 on its own: high-cardinality columns leave 'mapping' here (uq.py:634-636)
             uint64_t d0 = 0;
             UQB_TRY(distinct_of_prefix(ctx, fq, qc, w, 10001, &d0));
@@ -288,7 +300,7 @@ extern "C" int uqb_qname_scan(uqb_ctx* ctx, uqb_fastq* fq, uint32_t prefix_len, 
         for (uint32_t k = 0; k < ncheck; k++) { run += hist[k]; cs.distinct_at[k] = run; }
         cs.n_distinct = u;
         UQB_TRY(uqb_dfree(ctx, dhist, 8 * (UQB_MAX_CHECKPOINTS + 1)));
-        UQB_TRY(uqb_dfree(ctx, first_row, u * 4));
+        qc.first_occ = first_row;                 // first record of every dictionary entry (multi-GPU merges need it)
         UQB_TRY(uqb_dfree(ctx, perm, N * 4));
         UQB_TRY(uqb_dfree(ctx, gid, N * 4));
         UQB_TRY(uqb_dfree(ctx, rows, N * w + 64));
@@ -301,6 +313,15 @@ extern "C" int uqb_qname_dict_info(uqb_ctx* ctx, uqb_fastq* fq, uint32_t col, ui
     if (!fq->qcols[col].rank) return uqb_fail(ctx, "qname_dict: column %u has no dictionary (it left 'mapping' at the first checkpoint)", col);
     *count = fq->qcols[col].dict_count;
     *width = fq->qcols[col].dict_width;
+    return 0;
+}
+
+extern "C" int uqb_qname_dict_first(uqb_ctx* ctx, uqb_fastq* fq, uint32_t col, uint32_t* host, uint64_t count) {
+    if (col >= fq->qcols.size() || !fq->qcols[col].rank) return uqb_fail(ctx, "qname_dict_first: column %u has no dictionary", col);
+    const uqb_qcol& qc = fq->qcols[col];
+    if (count != qc.dict_count) return uqb_fail(ctx, "qname_dict_first: buffer size mismatch");
+    if (count) UQB_CUDA(cudaMemcpyAsync(host, qc.first_occ, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    UQB_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

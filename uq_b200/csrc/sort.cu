@@ -506,3 +506,50 @@ extern "C" int uqb_rows_to_columns(uqb_ctx* ctx, const uqb_array* rows, uint32_t
     if (rows->n) UQB_LAUNCH(k_rows_to_cols, uqb_grid(ctx, rows->n * ncols, ST, 16), ST, 0, cd, rows->n, (const uint8_t*)rows->d);
     return 0;
 }
+
+// ---- multi-GPU sample sort support ---------------------------------------------------------------
+// lower_bound of k probe rows in a table sorted in memcmp order: out[j] = first i with table[i] >= probe[j]
+__global__ void k_rows_lower_bound(const uint8_t* __restrict__ table, uint64_t n, uint32_t width, const uint8_t* __restrict__ probes,
+                                   uint32_t k, uint64_t* __restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    const uint8_t* p = probes + (uint64_t)j * width;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        const uint8_t* row = table + mid * width;
+        int c = 0;
+        for (uint32_t b = 0; b < width; b++) {
+            const unsigned x = row[b], y = p[b];
+            if (x != y) { c = x < y ? -1 : 1; break; }
+        }
+        if (c < 0) lo = mid + 1; else hi = mid;
+    }
+    out[j] = lo;
+}
+
+extern "C" int uqb_rows_lower_bound(uqb_ctx* ctx, const uqb_array* sorted_table, const uint8_t* probes_host, uint32_t k, uint64_t* out_host) {
+    if (k == 0) return 0;
+    const uint32_t w = sorted_table->width;
+    uint8_t* dp;
+    uint64_t* dout;
+    UQB_TRY(uqb_dalloc(ctx, (void**)&dp, (size_t)k * w + 16));
+    UQB_TRY(uqb_dalloc_t(ctx, &dout, k));
+    UQB_CUDA(cudaMemcpyAsync(dp, probes_host, (size_t)k * w, cudaMemcpyHostToDevice, ctx->stream));
+    UQB_LAUNCH(k_rows_lower_bound, (k + 63) / 64, 64, 0, (const uint8_t*)sorted_table->d, sorted_table->n, w, dp, k, dout);
+    UQB_TRY(uqb_readback(ctx, out_host, dout, (size_t)k * 8));
+    UQB_TRY(uqb_dfree(ctx, dp, 0));
+    UQB_TRY(uqb_dfree(ctx, dout, 0));
+    return 0;
+}
+
+__global__ void __launch_bounds__(ST) k_add_u32(uint32_t* __restrict__ a, uint64_t n, uint32_t v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * ST + threadIdx.x; i < n; i += (uint64_t)gridDim.x * ST) a[i] += v;
+}
+
+// a[i] += value for a uint32 array (global unique ids = range offset + local id)
+extern "C" int uqb_add_scalar_u32(uqb_ctx* ctx, uqb_array* a, uint32_t value) {
+    if (a->width != 4) return uqb_fail(ctx, "add_scalar_u32: array must be uint32");
+    if (a->n && value) UQB_LAUNCH_B(a->n * 8, k_add_u32, uqb_grid(ctx, a->n, ST, 16), ST, 0, (uint32_t*)a->d, a->n, value);
+    return 0;
+}

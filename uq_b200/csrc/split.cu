@@ -147,6 +147,7 @@ static int free_qcols(uqb_ctx* ctx, uqb_fastq* fq) {
         UQB_TRY(uqb_dfree(ctx, c.val, fq->n_reads * 8));
         UQB_TRY(uqb_dfree(ctx, c.span, fq->n_reads * 4));
         UQB_TRY(uqb_dfree(ctx, c.rank, fq->n_reads * 4));
+        UQB_TRY(uqb_dfree(ctx, c.first_occ, 0));
         UQB_TRY(uqb_dfree(ctx, c.dict, c.dict_count * c.dict_width + 64));
     }
     fq->qcols.clear();
@@ -160,6 +161,7 @@ extern "C" int uqb_fastq_free(uqb_ctx* ctx, uqb_fastq* fq) {
     UQB_TRY(free_qcols(ctx, fq));
     if (fq->line_off) UQB_TRY(uqb_dfree(ctx, fq->line_off, (fq->n_lines + 1) * 8));
     delete fq->cached_stats;
+    if (fq->ref_name) UQB_TRY(uqb_dfree(ctx, fq->ref_name, 0));
     if (fq->owned) UQB_TRY(uqb_dfree(ctx, (void*)fq->d, fq->n + 64));
     delete fq;
     return 0;

@@ -105,6 +105,24 @@ class Context:
         self.check(self.lib.uqb_array_upload(self.h, _ptr(arr), int(n), int(width), C.byref(h)))
         return DeviceArray(self, h)
 
+    def alloc(self, n, width):
+        """uninitialised device array of n rows x width bytes"""
+        h = C.c_void_p()
+        self.check(self.lib.uqb_array_alloc(self.h, int(n), int(width), C.byref(h)))
+        return DeviceArray(self, h)
+
+    def add_scalar_u32(self, arr, value):
+        self.check(self.lib.uqb_add_scalar_u32(self.h, arr.h, int(value)))
+
+    def rows_lower_bound(self, sorted_table, probes):
+        """lower_bound of every row of `probes` (uint8 [k][width], host) in a device table sorted in memcmp order"""
+        probes = np.ascontiguousarray(probes, dtype=np.uint8)
+        k = probes.shape[0]
+        out = np.zeros(k, dtype=np.uint64)
+        if k:
+            self.check(self.lib.uqb_rows_lower_bound(self.h, sorted_table.h, _ptr(probes), int(k), _ptr(out)))
+        return out
+
     def load_fastq(self, data):
         """H2D copy of FASTQ bytes (bytes / bytearray / uint8 ndarray / PinnedBuffer)."""
         if isinstance(data, PinnedBuffer):
@@ -263,6 +281,11 @@ class DeviceArray:
             return out[:self.nbytes]
         return out[:self.nbytes].reshape(self.n, self.width)
 
+    @property
+    def __cuda_array_interface__(self):
+        """zero-copy view for torch.as_tensor(...) (NCCL collectives of the multi-GPU path): flat uint8"""
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.device_ptr.value or 0, False), "version": 3, "strides": None}
+
     def first_difference(self, other):
         """index of the first differing byte, -1 if the two device arrays are identical"""
         r = C.c_int64()
@@ -331,14 +354,28 @@ class Fastq:
         self.ctx.check(self.ctx.lib.uqb_analyze(self.ctx.h, self.h, C.byref(st)))
         return st
 
-    def qname_scan(self, prefix_len, suffix_len, separators):
+    def set_reference(self, name, rbase):
+        """multi-GPU shard: measure QNAME statistics against the global first line; rbase = first global record"""
+        b = np.frombuffer(name, dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.uqb_fastq_set_reference(self.ctx.h, self.h, _ptr(b) if b.size else None, int(b.size), int(rbase)))
+
+    def qname_scan(self, prefix_len, suffix_len, separators, col_mode=None):
         seps = np.frombuffer(separators.encode('latin-1'), dtype=np.uint8)
         ncols = len(seps) + 1
         cols = (L.ColStats * ncols)()
         bad = C.c_int64()
-        self.ctx.check(self.ctx.lib.uqb_qname_scan(self.ctx.h, self.h, int(prefix_len), int(suffix_len),
-                                                   _ptr(seps) if len(seps) else None, len(seps), cols, C.byref(bad)))
+        mode = None if col_mode is None else np.ascontiguousarray(col_mode, dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.uqb_qname_scan_ex(self.ctx.h, self.h, int(prefix_len), int(suffix_len),
+                                                      _ptr(seps) if len(seps) else None, len(seps),
+                                                      _ptr(mode) if mode is not None else None, cols, C.byref(bad)))
         return cols, int(bad.value)
+
+    def qname_dict_first(self, col):
+        cnt, w = C.c_uint64(), C.c_uint32()
+        self.ctx.check(self.ctx.lib.uqb_qname_dict_info(self.ctx.h, self.h, int(col), C.byref(cnt), C.byref(w)))
+        out = np.zeros(max(cnt.value, 1), dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.uqb_qname_dict_first(self.ctx.h, self.h, int(col), _ptr(out), cnt.value))
+        return out[:cnt.value]
 
     def qname_dict(self, col):
         cnt, w = C.c_uint64(), C.c_uint32()

@@ -1,0 +1,450 @@
+"""One uQ container from N GPUs: every rank holds a contiguous range of the reads of ONE
+FASTQ file and the result is bit-identical to the single-GPU encode of the whole file.
+
+  phase                      what crosses ranks
+  -------------------------  --------------------------------------------------------------------------
+  split                      all-gather of the per-rank read counts (object collective)
+  Pass-1 statistics          every rank measures against the GLOBAL first QNAME line (uqb_fastq_set_reference);
+                             the O(alphabet) structs are all-gathered and merged on the host (merge_stats)
+  QNAME column typing        all-gather + merge of the per-column statistics and of the dictionaries of the
+                             columns that stay 'mapping' (merge_colstats)
+  pack / column encode       nothing (per read)
+  sort / unique              sample sort: splitters from gathered samples, ONE all-to-all of each rank's *unique*
+                             rows (NCCL over NVLink), local sort/unique of the received key range, all-to-all of
+                             the global ids back (global_unique)
+  --sort order               all-to-all of the per-record payload (keys / raw rows) to the rank that owns the
+                             record's key range; a stable local sort by key finishes it (global_order)
+
+The device collectives go through torch.distributed (NCCL) on zero-copy tensor views of the arena memory
+(`__cuda_array_interface__`); the host-side merges are plain Python over tiny structs and are covered by
+2-rank gloo tests on CPU.
+"""
+import numpy as np
+
+from . import _lib as L
+from . import host
+
+_ARRAY_FIELDS = ("base_count", "qual_count", "base_single_qual", "last_count_mismatch", "first_lcp_eq", "first_lcs_eq",
+                 "first_short_prefix", "first_short_suffix")
+_SCALAR_FIELDS = ("dna_min", "dna_max", "bad_first_char", "bad_plus_record", "bad_len_record", "first_len", "last_len",
+                  "max_name_len", "prefix_len", "suffix_len")
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side merges (no device, no torch)
+# ------------------------------------------------------------------------------------------------
+def stats_to_plain(st):
+    d = {f: list(getattr(st, f)) for f in _ARRAY_FIELDS}
+    d.update({f: int(getattr(st, f)) for f in _SCALAR_FIELDS})
+    d["first_name"] = bytes(st.first_name[:st.first_len])
+    d["last_name"] = bytes(st.last_name[:st.last_len])
+    return d
+
+
+def merge_stats(parts):
+    """parts: [(plain stats measured against the global line 1, first global record, number of records)] in rank
+    order, empty shards skipped by the caller -> uqb_stats of the whole file."""
+    st = L.Stats()
+    ref_len = len(parts[0][0]["first_name"])
+    for i in range(256):
+        st.base_single_qual[i] = -1
+        st.last_count_mismatch[i] = -1
+    for j in range(L.HDR_MAX + 1):
+        st.first_lcp_eq[j] = st.first_lcs_eq[j] = st.first_short_prefix[j] = st.first_short_suffix[j] = L.NONE_I64
+    st.bad_plus_record = st.bad_len_record = -1
+    dmin, dmax, mname = None, 0, 0
+    for p, base, n in parts:
+        for i in range(256):
+            st.base_count[i] += p["base_count"][i]
+            st.qual_count[i] += p["qual_count"][i]
+            a, b = st.base_single_qual[i], p["base_single_qual"][i]
+            st.base_single_qual[i] = b if a == -1 else (a if b == -1 or b == a else 256)
+            if p["last_count_mismatch"][i] >= 0:
+                st.last_count_mismatch[i] = max(st.last_count_mismatch[i], base + p["last_count_mismatch"][i])
+        for f in ("first_lcp_eq", "first_lcs_eq", "first_short_prefix", "first_short_suffix"):
+            dst = getattr(st, f)
+            for j in range(ref_len + 1):
+                v = p[f][j]
+                if v != L.NONE_I64:
+                    dst[j] = min(dst[j], base + v)
+        for f in ("bad_plus_record", "bad_len_record"):
+            v = p[f]
+            if v >= 0:
+                cur = getattr(st, f)
+                setattr(st, f, base + v if cur < 0 else min(cur, base + v))
+        dmin = p["dna_min"] if dmin is None else min(dmin, p["dna_min"])
+        dmax = max(dmax, p["dna_max"])
+        mname = max(mname, p["max_name_len"])
+    first, last = parts[0][0]["first_name"], parts[-1][0]["last_name"]
+    st.first_len, st.last_len = len(first), len(last)
+    for i, b in enumerate(first): st.first_name[i] = b
+    for i, b in enumerate(last): st.last_name[i] = b
+    st.bad_first_char = parts[0][0]["bad_first_char"]
+    st.dna_min, st.dna_max, st.max_name_len = dmin, dmax, mname
+    pl = sl = ref_len
+    for j in range(ref_len + 1):
+        if st.first_lcp_eq[j] != L.NONE_I64: pl = min(pl, j)
+        if st.first_lcs_eq[j] != L.NONE_I64: sl = min(sl, j)
+    st.prefix_len, st.suffix_len = pl, sl
+    return st
+
+
+def colstats_to_plain(cols, ncols):
+    out = []
+    for c in range(ncols):
+        cs = cols[c]
+        out.append(dict(all_int=int(cs.all_int), all_canonical=int(cs.all_canonical), overflow=int(cs.overflow),
+                        min_val=int(cs.min_val), max_val=int(cs.max_val), min_len=int(cs.min_len), max_len=int(cs.max_len),
+                        n_distinct=int(cs.n_distinct), distinct_at=list(cs.distinct_at)))
+    return out
+
+
+def n_checkpoints(n_total):
+    k, t = 0, 10000
+    while t <= n_total - 1 and k < L.MAX_CHECKPOINTS:
+        k += 1
+        t *= 2
+    return k
+
+
+def merge_colstats(parts, n_total, early_demoted, dictionaries):
+    """parts: per rank [plain colstats per column]; early_demoted[c]: the column left 'mapping' at checkpoint 0
+    (decided on the rank that holds records 0..10000); dictionaries: per rank {column: (tokens, first global
+    record of each token)} for the other columns -> (uqb_colstats array of the whole file, {column: sorted
+    global dictionary})."""
+    ncols = len(parts[0])
+    cols = (L.ColStats * ncols)()
+    ncheck = n_checkpoints(n_total)
+    merged_dicts = {}
+    for c in range(ncols):
+        cs = cols[c]
+        ps = [p[c] for p in parts]
+        cs.all_int = int(all(p["all_int"] for p in ps))
+        cs.all_canonical = int(all(p["all_canonical"] for p in ps))
+        cs.overflow = int(any(p["overflow"] for p in ps))
+        cs.min_val = min(p["min_val"] for p in ps)
+        cs.max_val = max(p["max_val"] for p in ps)
+        cs.min_len = min(p["min_len"] for p in ps)
+        cs.max_len = max(p["max_len"] for p in ps)
+        cs.n_checkpoints = ncheck
+        if early_demoted[c]:
+            cs.distinct_at[0] = parts[0][c]["distinct_at"][0]
+            for k in range(1, L.MAX_CHECKPOINTS): cs.distinct_at[k] = L.U64_MAX
+            cs.n_distinct = L.U64_MAX
+            continue
+        first = {}
+        for d in dictionaries:
+            toks, occ = d[c]
+            for t, o in zip(toks, occ):
+                o = int(o)
+                if t not in first or o < first[t]:
+                    first[t] = o
+        t = 10000
+        for k in range(ncheck):
+            cs.distinct_at[k] = sum(1 for o in first.values() if o <= t)
+            t *= 2
+        cs.n_distinct = len(first)
+        merged_dicts[c] = sorted(first)
+    return cols, merged_dicts
+
+
+def pick_splitters(all_samples, world):
+    """all_samples: uint8 [m][w] (gathered, any order) -> the world-1 splitter rows (identical on every rank)."""
+    m, w = all_samples.shape
+    if m == 0 or world == 1:
+        return np.zeros((0, w), dtype=np.uint8)
+    v = np.ascontiguousarray(all_samples).view("V%d" % w).reshape(-1) if w else np.zeros(m, dtype="V1")
+    order = np.argsort(v, kind="stable")
+    pos = [min(m - 1, (k * m) // world) for k in range(1, world)]
+    return np.ascontiguousarray(all_samples[order[pos]])
+
+
+# ------------------------------------------------------------------------------------------------
+# communication
+# ------------------------------------------------------------------------------------------------
+class Comm:
+    """torch.distributed behind four calls; `dist=None` is the single-rank case."""
+
+    def __init__(self, dist=None, device=None):
+        self.dist, self.device = dist, device
+        self.rank = dist.get_rank() if dist else 0
+        self.world = dist.get_world_size() if dist else 1
+
+    def all_gather_object(self, obj):
+        if not self.dist:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def exchange_counts(self, send_counts):
+        """send_counts[k] = rows this rank sends to rank k -> rows it receives from every rank"""
+        table = self.all_gather_object(list(map(int, send_counts)))
+        return [table[src][self.rank] for src in range(self.world)]
+
+    def _tensor(self, arr):
+        import torch
+        if arr.nbytes == 0:
+            return torch.empty(0, dtype=torch.uint8, device=self.device)
+        return torch.as_tensor(arr, device=self.device)
+
+    def all_to_all_rows(self, ctx, send, send_counts, recv_counts):
+        """send: DeviceArray whose rows are grouped by destination rank in rank order -> DeviceArray holding
+        the rows received from rank 0, 1, ... in that order (NCCL all-to-all over NVLink)."""
+        w = send.width
+        recv = ctx.alloc(sum(recv_counts), w)
+        if not self.dist:
+            raise RuntimeError("all_to_all on a single rank")
+        ctx.sync()
+        self.dist.all_to_all_single(self._tensor(recv), self._tensor(send), [c * w for c in recv_counts], [c * w for c in send_counts])
+        import torch
+        torch.cuda.current_stream().synchronize()
+        return recv
+
+
+# ------------------------------------------------------------------------------------------------
+# distributed sort / unique
+# ------------------------------------------------------------------------------------------------
+SAMPLES_PER_RANK = 256
+
+
+def global_unique(ctx, comm, table, want_perm=False):
+    """-> dict(key: uint32[n] global unique-row index of every local row, uniq: this rank's key range of the
+    global unique table (rows ascending; the ranges concatenate in rank order), n_unique, offset, counts (unique
+    rows per rank), perm: local stable argsort if wanted)."""
+    perm, key_local, uniq_local, nu = ctx.sort_rows(table, want_perm=want_perm, want_key=True, want_uniq=True)
+    if comm.world == 1:
+        return dict(key=key_local, uniq=uniq_local, n_unique=nu, offset=0, counts=[nu], perm=perm)
+    w = table.width
+    # splitters from evenly spaced samples of every rank's sorted unique rows
+    if nu:
+        idx = np.unique(np.linspace(0, nu - 1, num=min(nu, SAMPLES_PER_RANK)).astype(np.uint32))
+        d_idx = ctx.upload(idx)
+        d_s = ctx.gather_rows(uniq_local, d_idx)
+        samples = d_s.download().reshape(len(idx), w) if w else np.zeros((len(idx), 0), np.uint8)
+        d_idx.free(); d_s.free()
+    else:
+        samples = np.zeros((0, w), dtype=np.uint8)
+    splitters = pick_splitters(np.concatenate(comm.all_gather_object(samples)), comm.world)
+    if len(splitters) == comm.world - 1:
+        b = [0] + [int(x) for x in ctx.rows_lower_bound(uniq_local, splitters)] + [nu]
+        for i in range(1, len(b)):                      # equal splitters give equal bounds; keep them monotone
+            b[i] = max(b[i], b[i - 1])
+    else:                                               # nothing anywhere
+        b = [0] * comm.world + [nu]
+    send_counts = [b[k + 1] - b[k] for k in range(comm.world)]
+    recv_counts = comm.exchange_counts(send_counts)
+    recv = comm.all_to_all_rows(ctx, uniq_local, send_counts, recv_counts)
+    uniq_local.free()
+    _, key_recv, uniq_range, nr = ctx.sort_rows(recv, want_key=True, want_uniq=True)
+    recv.free()
+    counts = comm.all_gather_object(nr)
+    offset = sum(counts[:comm.rank])
+    ctx.add_scalar_u32(key_recv, offset)                # global id of every received unique row
+    ids_back = comm.all_to_all_rows(ctx, key_recv, recv_counts, send_counts)     # in the order the rows were sent = sorted
+    key_recv.free()
+    key_global = ctx.gather_rows(ids_back, key_local)   # ids_back[local unique index]
+    ids_back.free(); key_local.free()
+    return dict(key=key_global, uniq=uniq_range, n_unique=sum(counts), offset=offset, counts=counts, perm=perm)
+
+
+def global_order(ctx, comm, key_global, perm, counts, payloads):
+    """Stable global sort of the records by `key_global` (a global unique-row index).  `perm` is the local stable
+    argsort of the same table, `counts` the unique rows owned by every rank.  payloads: {name: DeviceArray [n][w]}.
+    Every record goes to the rank that owns its key range; there a stable sort by key finishes the job (the
+    all-to-all delivers source ranks in order, and source rank order is global record order).
+    -> {name: DeviceArray} holding this rank's slice of the globally sorted arrays."""
+    if comm.world == 1:
+        return {k: ctx.gather_rows(v, perm) for k, v in payloads.items()}
+    key_sorted = ctx.gather_rows(key_global, perm)                      # non-decreasing
+    key_be = ctx.columns_to_rows([key_sorted])                          # big-endian rows: memcmp order = numeric order
+    bounds = np.cumsum(counts)[:-1].astype(">u4").view(np.uint8).reshape(-1, 4)
+    b = [0] + [int(x) for x in ctx.rows_lower_bound(key_be, bounds)] + [key_sorted.n]
+    key_be.free()
+    send_counts = [b[k + 1] - b[k] for k in range(comm.world)]
+    recv_counts = comm.exchange_counts(send_counts)
+    key_recv = comm.all_to_all_rows(ctx, key_sorted, send_counts, recv_counts)
+    key_sorted.free()
+    kb = ctx.columns_to_rows([key_recv])
+    perm2, _, _, _ = ctx.sort_rows(kb, want_perm=True)                  # stable
+    kb.free(); key_recv.free()
+    out = {}
+    for name, arr in payloads.items():
+        s = ctx.gather_rows(arr, perm)
+        r = comm.all_to_all_rows(ctx, s, send_counts, recv_counts)
+        s.free()
+        out[name] = ctx.gather_rows(r, perm2)
+        r.free()
+    perm2.free()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the encode
+# ------------------------------------------------------------------------------------------------
+class ShardResult:
+    """This rank's part of every member.  `slices[name]` = (DeviceArray, kind, dtype or width); members
+    concatenate over the ranks in rank order (axis 0)."""
+
+    def __init__(self):
+        self.slices = {}
+
+    def download(self):
+        out = {}
+        for name, (arr, kind, meta) in self.slices.items():
+            if kind == "vector":
+                out[name] = arr.download(dtype=np.uint8).reshape(-1).view(np.dtype(meta)).reshape(-1)
+            else:
+                out[name] = arr.download(dtype=np.uint8).reshape(arr.n, arr.width)
+        return out
+
+    def free(self):
+        for arr, _, _ in self.slices.values():
+            arr.free()
+        self.slices = {}
+
+
+def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, notricks=False):
+    """fq: this rank's contiguous range of the reads (device.Fastq).  -> (ShardResult, config); config is identical on
+    every rank and equal to the single-GPU config of the whole file."""
+    sort, raw, pattern = host.normalise_options(sort, raw, pattern)
+    if pattern != ['0.1', '0.1']:
+        raise host.UQError('ERROR: the multi-GPU path writes pattern 0.1 only (other layouts interleave the ranks\' rows)')
+    info = fq.split()
+    n_local = int(info.n_reads)
+    lines_bad = info.status == 1
+    counts = comm.all_gather_object((n_local, lines_bad))
+    if any(b for _, b in counts):
+        raise host.UQError('ERROR: The FASTQ file provided contains a number of rows which is not divisible by 4!')
+    ns = [c for c, _ in counts]
+    n_total = sum(ns)
+    base = sum(ns[:comm.rank])
+    if n_total == 0:
+        raise host.UQError('ERROR: the FASTQ file holds no records')
+    if any(c == 0 for c in ns):
+        raise host.UQError('ERROR: every rank needs at least one read')
+    if n_total > 10000 and ns[0] < 10001:
+        raise host.UQError('ERROR: rank 0 must hold the first 10001 reads (Pass-2 checkpoint 0)')
+    # ---- Pass 1 against the global first QNAME line ----
+    first_off = fq.line_offsets(0, 2)
+    my_first = fq.download(0, int(first_off[1]) - 1).tobytes()
+    ref = comm.all_gather_object(my_first)[0]
+    fq.set_reference(ref, base)
+    plain = stats_to_plain(fq.analyze())
+    parts = comm.all_gather_object((plain, base, n_local))
+    parts[0][0]["first_name"] = ref
+    st = merge_stats(parts)
+    if st.bad_first_char != -1:
+        raise host.UQError('ERROR: This does not look like a FASTA/FASTQ file! (first line does not start with @)')
+    bad = [(r, w) for r, w in ((st.bad_plus_record, 'plus'), (st.bad_len_record, 'len')) if r >= 0]
+    if bad:
+        r, w = min(bad, key=lambda t: (t[0], t[1] != 'plus'))
+        raise host.UQError('ERROR: malformed FASTQ record %d (%s)' % (r, w))
+    prefix, suffix, separators = host.derive_qname_layout(st, n_total)
+    dec = host.decide_alphabets(st, notricks=notricks, pad=pad)
+    # ---- Pass 2: rank 0 decides which columns leave 'mapping' at checkpoint 0, the others skip those dictionaries ----
+    ncols = len(separators) + 1
+    if comm.rank == 0:
+        cols0, bad0 = fq.qname_scan(len(prefix), len(suffix), separators)
+        early = [bool(cols0[c].n_distinct == L.U64_MAX) for c in range(ncols)] if bad0 < 0 else [False] * ncols
+    else:
+        cols0, bad0, early = None, -1, None
+    early = comm.all_gather_object(early)[0]
+    if comm.rank != 0:
+        cols0, bad0 = fq.qname_scan(len(prefix), len(suffix), separators, col_mode=[1 if e else 2 for e in early])
+    bads = comm.all_gather_object(bad0)
+    if any(b >= 0 for b in bads):
+        raise host.UQError('Encoding QNAMEs as strings has not been implimented yet.')
+    my_dicts = {}
+    for c in range(ncols):
+        if not early[c]:
+            toks = fq.qname_dict(c)
+            my_dicts[c] = (toks, (fq.qname_dict_first(c).astype(np.int64) + base).tolist())
+    all_plain = comm.all_gather_object(colstats_to_plain(cols0, ncols))
+    all_dicts = comm.all_gather_object(my_dicts)
+    colstats, gdicts = merge_colstats(all_plain, n_total, early, all_dicts)
+    columns = host.decide_columns(colstats, n_total, lambda i: gdicts[i])
+    # ---- pack + column encode (per read) ----
+    dna, qual = fq.pack(host.pack_params(dec))
+    specs = host.column_specs(columns)
+    cols = fq.qname_encode([(f, 4 if f == 0 else size, off, mn) for f, size, off, mn in specs])
+    for c, meta in enumerate(columns):
+        if meta['format'] == 'mapping':                 # local dictionary rank -> global dictionary rank
+            local = my_dicts[c][0]
+            remap = np.searchsorted(np.array(gdicts[c], dtype=object), np.array(local, dtype=object)).astype(np.uint32) if local else np.zeros(0, np.uint32)
+            d_remap = ctx.upload(remap)
+            g = ctx.gather_rows(d_remap, cols[c])
+            d_remap.free(); cols[c].free()
+            cols[c] = ctx.narrow_u32(g, specs[c][1])
+            g.free()
+    # ---- run_mix over the ranks ----
+    res = ShardResult()
+    sorted_on = sort if sort in ('DNA', 'QUAL', 'QNAME') else None
+    tables = {'DNA': dna, 'QUAL': qual, 'QNAME': ctx.columns_to_rows(cols)}
+    keyed = {t: (t not in raw) for t in tables}
+    uniq = {}
+    payload = {}
+    order_info = None
+    for t in ('QUAL', 'DNA', 'QNAME'):
+        if keyed[t] or t == sorted_on:
+            g = global_unique(ctx, comm, tables[t], want_perm=(t == sorted_on))
+            if t == sorted_on:
+                order_info = (g['key'], g['perm'], g['counts'])
+            if keyed[t]:
+                uniq[t] = (g['uniq'], g['n_unique'])
+                payload[t + '.key'] = g['key']
+            else:
+                g['uniq'].free()
+                if t != sorted_on:
+                    g['key'].free()
+        if not keyed[t]:
+            if t == 'QNAME':
+                for c, meta in zip(cols, columns):
+                    payload[meta['name'] + '.raw'] = c
+            else:
+                payload[t + '.raw'] = tables[t]
+    if order_info is not None:
+        key_x, perm_x, counts_x = order_info
+        moved = global_order(ctx, comm, key_x, perm_x, counts_x, payload)
+        old = {id(v): v for v in payload.values()}
+        old[id(key_x)] = key_x
+        old[id(perm_x)] = perm_x
+        for v in old.values():
+            v.free()
+        payload = moved
+    # keys are narrowed to min_scalar_type(max(key)) of the WHOLE file (uq.py:790, 832)
+    for t in ('DNA', 'QUAL', 'QNAME'):
+        if keyed[t]:
+            u, nu = uniq[t]
+            size = host.key_itemsize(nu)
+            k32 = payload[t + '.key']
+            res.slices[t + '.key'] = (ctx.narrow_u32(k32, size), 'vector', 'uint%d' % (8 * size))
+            if t == 'QNAME':
+                ucols = ctx.rows_to_columns(u, [np.dtype(m['dtype']).itemsize for m in columns])
+                for c, meta in zip(ucols, columns):
+                    res.slices[meta['name']] = (c, 'vector', meta['dtype'])
+            else:
+                res.slices[t] = (u, 'table', u.width)
+        elif t == 'QNAME':
+            for meta in columns:
+                res.slices[meta['name'] + '.raw'] = (payload[meta['name'] + '.raw'], 'vector', meta['dtype'])
+        else:
+            res.slices[t + '.raw'] = (payload[t + '.raw'], 'table', tables[t].width)
+    config = {
+        'base_distribution': dec['base_distribution'], 'qual_distribution': dec['qual_distribution'],
+        'reads': n_total, 'bases': dec['bases'], 'qualities': dec['qualities'],
+        'variable_read_lengths': dec['variable_read_lengths'], 'bits_per_base': dec['bits_per_base'],
+        'bits_per_quality': dec['bits_per_quality'], 'N_qual': dec['N_qual'], 'dna_max': dec['dna_max'],
+        'QNAME_prefix': prefix, 'QNAME_suffix': suffix, 'QNAME_separators': separators,
+        'QNAME_columns': columns, 'sort': sort, 'raw': list(raw), 'pattern': pattern,
+    }
+    return res, config
+
+
+def assemble(comm, shard_members):
+    """Gather every rank's host slices on rank 0 and concatenate them (axis 0) -> members dict on rank 0, None
+    elsewhere.  (A production writer would let every rank write its slice at its byte offset of the tar.)"""
+    parts = comm.all_gather_object(shard_members)
+    if comm.rank != 0:
+        return None
+    return {name: np.concatenate([p[name] for p in parts], axis=0) for name in parts[0]}
