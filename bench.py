@@ -113,11 +113,22 @@ def run_ours(args):
     fbytes = dev.nbytes
     opts = dict(sort=SORT, raw=RAW, pattern=PATTERN)
 
+    global_mode = world > 1 and args.multi == "global"
+    if global_mode:
+        from uq_b200 import multigpu
+        comm = multigpu.Comm(dist, "cuda:%d" % local_rank)
+
     def one_step():
         fq = ctx.adopt_fastq(dev)
-        members, cfg = host.encode_device(ctx, fq, **opts)
-        out_bytes = members.nbytes()
-        members.free()
+        if global_mode:
+            # ONE container from all ranks: global statistics, sample-sort unique (NCCL all-to-all), global order
+            res, cfg = multigpu.encode_sharded(ctx, comm, fq, **opts)
+            out_bytes = sum(a.nbytes for a, _, _ in res.slices.values())
+            res.free()
+        else:
+            members, cfg = host.encode_device(ctx, fq, **opts)
+            out_bytes = members.nbytes()
+            members.free()
         fq.free()
         return out_bytes, cfg
 
@@ -205,13 +216,25 @@ def run_ours(args):
         def e2e_step():
             # H2D in chunks on the copy stream, overlapped with record splitting and the Pass-1 statistics;
             # every output array starts its D2H copy as soon as it is final
-            fq = ctx.load_fastq_streamed(pin_in) if not args.e2e_serial else ctx.load_fastq(pin_in)
             cur = [0]
 
             def sink(name, nbytes):
                 a = pin_out.array[cur[0]:cur[0] + nbytes]
                 cur[0] += (nbytes + 63) & ~63
                 return a
+            if global_mode:
+                # the global first QNAME line is read from rank 0's host buffer, so every rank can measure its
+                # Pass-1 statistics against it while its own chunks are still streaming in
+                line1 = bytes(pin_in.array[:min(int(fbytes), 4096)]).split(b"\n")[0]
+                ref = comm.all_gather_object(line1)[0]
+                fq = ctx.load_fastq_streamed(pin_in, ref=ref, rbase=0 if rank == 0 else 1)
+                members, _ = multigpu.encode_sharded(ctx, comm, fq, sink=sink, **opts)
+                members.download()
+                nb = members.nbytes()
+                members.free()
+                fq.free()
+                return nb
+            fq = ctx.load_fastq_streamed(pin_in) if not args.e2e_serial else ctx.load_fastq(pin_in)
             if args.e2e_serial:
                 members, _ = host.encode_device(ctx, fq, **opts)
                 members.download(into=sink)
@@ -272,7 +295,9 @@ def run_ours(args):
                        "output_bytes_per_gpu": int(out_bytes), "genome": GENOME, "qual_pool": pool,
                        "l2": "inputs (%.1f GB) far larger than the 126 MB L2; no flush needed" % (fbytes / 1e9),
                        "bits": [cfg["bits_per_base"], cfg["bits_per_quality"]],
-                       "sharding": "independent read ranges per rank, one container shard per rank"},
+                       "sharding": ("contiguous read ranges per rank, ONE global container: merged statistics, sample-sort unique with "
+                                    "NCCL all-to-all, global --sort order" if global_mode else
+                                    "independent read ranges per rank, one container shard per rank (no data-path collective)")},
             "gb_per_s": round(total_fbytes / 1e9 / t, 2),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "pipeline_roofline": pipeline, "kernels": top5, "cpu_baseline": cpu,
@@ -335,6 +360,8 @@ def main():
     ap.add_argument("--reads", type=int, default=int(os.environ.get("UQ_BENCH_READS", "100000000")), help="reads per GPU")
     ap.add_argument("--cpu-sample", type=int, default=60000)
     ap.add_argument("--ref-sample", type=int, default=20000)
+    ap.add_argument("--multi", default=os.environ.get("UQ_BENCH_MULTI", "global"), choices=["shards", "global"],
+                    help="N>1: independent container shards per rank, or one global container (collectives on the data path)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e without copy/compute overlap (diagnostics)")
     ap.add_argument("--no-cpu", action="store_true")

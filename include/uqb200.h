@@ -90,6 +90,9 @@ int uqb_fastq_adopt(uqb_ctx* ctx, const uint8_t* dev, uint64_t nbytes, uqb_fastq
  * landed: when the call returns, uqb_split / uqb_analyze on the handle only return the cached results.
  * `host` should be pinned (uqb_host_alloc) for the copies to overlap; chunk_bytes 0 = 256 MiB. */
 int uqb_fastq_load_streamed(uqb_ctx* ctx, const uint8_t* host, uint64_t nbytes, uint64_t chunk_bytes, uqb_fastq** out);
+/* the same for a multi-GPU shard (see uqb_fastq_set_reference): rbase > 0 = this shard does not start the file */
+int uqb_fastq_load_streamed_ref(uqb_ctx* ctx, const uint8_t* host, uint64_t nbytes, uint64_t chunk_bytes,
+                                const uint8_t* ref, uint32_t ref_len, uint64_t rbase, uqb_fastq** out);
 int uqb_fastq_free(uqb_ctx* ctx, uqb_fastq* fq);
 int uqb_fastq_download(uqb_ctx* ctx, const uqb_fastq* fq, uint64_t offset, uint8_t* host, uint64_t nbytes);
 int uqb_split(uqb_ctx* ctx, uqb_fastq* fq, uqb_split_info* info);

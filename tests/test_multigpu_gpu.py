@@ -60,6 +60,35 @@ def _worker(rank, world, port, q):
             if json.loads(json.dumps(cfg, default=str)) != json.loads(json.dumps(want_cfg, default=str)):
                 bad.append("config differs")
             results.append((kind, kw, bad))
+    # a larger case generated on the device, loaded through the streamed path with the reference line, async downloads
+    n_each = 700_000
+    dev = ctx.synth("genome", n_each, 150, 1002, first=rank * n_each, genome=200_000, pool=300_000)
+    data = dev.download().copy()
+    dev.free()
+    pin = ctx.pinned_empty(data.size)
+    pin.array[:] = data
+    line1 = comm.all_gather_object(bytes(data[:200]).split(b"\n")[0])[0]
+    fq = ctx.load_fastq_streamed(pin, chunk_bytes=8 << 20, ref=line1, rbase=0 if rank == 0 else 1)
+    bufs = {}
+    def sink(name, nbytes):
+        bufs[name] = ctx.pinned_empty(nbytes)
+        return bufs[name].array
+    res, cfg = mg.encode_sharded(ctx, comm, fq, sort="DNA", sink=sink)
+    members = mg.assemble(comm, {k: np.array(v) for k, v in res.download().items()})
+    res.free(); fq.free()
+    if rank == 0:
+        whole = ctx.synth("genome", 2 * n_each, 150, 1002, first=0, genome=200_000, pool=300_000)
+        wfq = ctx.adopt_fastq(whole)
+        wm, wcfg = host.encode_device(ctx, wfq, sort="DNA")
+        want = wm.download()
+        bad = []
+        for k in want:
+            a, b = members[k], np.asarray(want[k])
+            if a.dtype != b.dtype or a.shape != b.shape or not np.array_equal(a, b):
+                bad.append("%s %s/%s %s/%s" % (k, a.dtype, b.dtype, a.shape, b.shape))
+        if cfg["reads"] != 2 * n_each or cfg["QNAME_columns"] != wcfg["QNAME_columns"]:
+            bad.append("config")
+        results.append(("device synth 1.4M streamed", "sort DNA", bad))
     if rank == 0:
         q.put(results)
     dist.destroy_process_group()

@@ -97,6 +97,7 @@ SIGNATURES = {
     "uqb_fastq_load": (C.c_int, [P, P, C.c_uint64, PP]),
     "uqb_fastq_adopt": (C.c_int, [P, P, C.c_uint64, PP]),
     "uqb_fastq_load_streamed": (C.c_int, [P, P, C.c_uint64, C.c_uint64, PP]),
+    "uqb_fastq_load_streamed_ref": (C.c_int, [P, P, C.c_uint64, C.c_uint64, P, C.c_uint32, C.c_uint64, PP]),
     "uqb_array_download_async": (C.c_int, [P, P, P, C.c_uint64]),
     "uqb_ctx_copy_sync": (C.c_int, [P]),
     "uqb_fastq_free": (C.c_int, [P, P]),

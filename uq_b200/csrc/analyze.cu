@@ -630,6 +630,13 @@ extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
 // done; uqb_split / uqb_analyze on the returned handle return them without touching the data again.
 // ================================================================================================
 extern "C" int uqb_fastq_load_streamed(uqb_ctx* ctx, const uint8_t* host, uint64_t nbytes, uint64_t chunk_bytes, uqb_fastq** out_fq) {
+    return uqb_fastq_load_streamed_ref(ctx, host, nbytes, chunk_bytes, nullptr, 0, 0, out_fq);
+}
+
+// as above for a multi-GPU shard: statistics are measured against the global first QNAME line `ref`; rbase > 0
+// says that this shard does not start the file (its first record takes part in the prefix/suffix statistics)
+extern "C" int uqb_fastq_load_streamed_ref(uqb_ctx* ctx, const uint8_t* host, uint64_t nbytes, uint64_t chunk_bytes,
+                                           const uint8_t* ref, uint32_t ref_len, uint64_t rbase, uqb_fastq** out_fq) {
     if (chunk_bytes == 0) chunk_bytes = 256ull << 20;
     chunk_bytes = (chunk_bytes + UQB_SPLIT_TILE - 1) / UQB_SPLIT_TILE * UQB_SPLIT_TILE;
     cudaStream_t cs;
@@ -640,6 +647,7 @@ extern "C" int uqb_fastq_load_streamed(uqb_ctx* ctx, const uint8_t* host, uint64
     UQB_TRY(uqb_dalloc(ctx, (void**)&d, nbytes + 64));
     fq->d = d; fq->n = nbytes; fq->owned = true; fq->streamed = true;
     UQB_CUDA(cudaMemsetAsync(d + nbytes, 0, 64, ctx->stream));
+    if (ref) UQB_TRY(uqb_fastq_set_reference(ctx, fq, ref, ref_len, rbase));
     const uint64_t nchunks = (nbytes + chunk_bytes - 1) / chunk_bytes;
     // all copies are queued up front; one event per chunk gates the compute stream
     std::vector<cudaEvent_t> ev(nchunks);
@@ -703,6 +711,7 @@ extern "C" int uqb_fastq_load_streamed(uqb_ctx* ctx, const uint8_t* host, uint64
             UQB_TRY(uqb_readback(ctx, offs, fq->line_off, 16));
             flen = offs[1] - offs[0] - 1;
             if (flen > UQB_HDR_MAX) return uqb_fail(ctx, "QNAME line longer than %d bytes is not supported by the device path", UQB_HDR_MAX);
+            if (fq->ref_name) flen = fq->ref_len;
             have_first = true;
             // records of typical short-read files fit the tiles; otherwise the generic kernels run at the end
             tiles_ok = true;
@@ -723,6 +732,7 @@ extern "C" int uqb_fastq_load_streamed(uqb_ctx* ctx, const uint8_t* host, uint64
         UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
         uint64_t fl2 = 0;
         UQB_TRY(stats_names(ctx, fq, st, &fl2));
+        if (fq->ref_name) fl2 = fq->ref_len;
         if (!tiles_ok || fb != 0) UQB_TRY(stats_generic(ctx, fq, s, (uint32_t)fl2));
         rc = stats_finish(ctx, fq, s, st, fl2);
     } else {

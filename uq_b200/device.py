@@ -135,17 +135,25 @@ class Context:
         self.check(self.lib.uqb_fastq_load(self.h, _ptr(arr) if arr.size else None, int(arr.size), C.byref(h)))
         return Fastq(self, h, int(arr.size))
 
-    def load_fastq_streamed(self, data, chunk_bytes=0):
-        """H2D in chunks overlapped with record splitting and the Pass-1 statistics (data: PinnedBuffer or ndarray)."""
+    def load_fastq_streamed(self, data, chunk_bytes=0, ref=None, rbase=0):
+        """H2D in chunks overlapped with record splitting and the Pass-1 statistics (data: PinnedBuffer or ndarray).
+        ref / rbase: multi-GPU shard measured against the global first QNAME line (rbase > 0: not the first shard)."""
         arr = data.array if isinstance(data, PinnedBuffer) else np.ascontiguousarray(data, dtype=np.uint8)
         h = C.c_void_p()
-        rc = self.lib.uqb_fastq_load_streamed(self.h, _ptr(arr) if arr.size else None, int(arr.size), int(chunk_bytes), C.byref(h))
+        if ref is None:
+            rc = self.lib.uqb_fastq_load_streamed(self.h, _ptr(arr) if arr.size else None, int(arr.size), int(chunk_bytes), C.byref(h))
+        else:
+            rb = np.frombuffer(ref, dtype=np.uint8)
+            rc = self.lib.uqb_fastq_load_streamed_ref(self.h, _ptr(arr) if arr.size else None, int(arr.size), int(chunk_bytes),
+                                                      _ptr(rb) if rb.size else None, int(rb.size), int(rbase), C.byref(h))
         if rc:
             msg = self.lib.uqb_last_error(self.h).decode()
             if h:
                 self.lib.uqb_fastq_free(self.h, h)
             raise DeviceError(msg)
-        return Fastq(self, h, int(arr.size))
+        fq = Fastq(self, h, int(arr.size))
+        fq.reference = ref
+        return fq
 
     def copy_sync(self):
         self.check(self.lib.uqb_ctx_copy_sync(self.h))
@@ -316,6 +324,7 @@ class Fastq:
         self.ctx, self.h, self.nbytes = ctx, handle, nbytes
         self.n_reads = None
         self._keep = None
+        self.reference = None
 
     def free(self):
         if self.h:
@@ -358,6 +367,7 @@ class Fastq:
         """multi-GPU shard: measure QNAME statistics against the global first line; rbase = first global record"""
         b = np.frombuffer(name, dtype=np.uint8)
         self.ctx.check(self.ctx.lib.uqb_fastq_set_reference(self.ctx.h, self.h, _ptr(b) if b.size else None, int(b.size), int(rbase)))
+        self.reference = name
 
     def qname_scan(self, prefix_len, suffix_len, separators, col_mode=None):
         seps = np.frombuffer(separators.encode('latin-1'), dtype=np.uint8)

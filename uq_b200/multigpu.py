@@ -286,25 +286,42 @@ class ShardResult:
     """This rank's part of every member.  `slices[name]` = (DeviceArray, kind, dtype or width); members
     concatenate over the ranks in rank order (axis 0)."""
 
-    def __init__(self):
+    def __init__(self, ctx=None, sink=None):
         self.slices = {}
+        self.ctx, self.sink, self.host = ctx, sink, {}
+
+    def add(self, name, arr, kind, meta):
+        """with a sink ((name, nbytes) -> pinned uint8 ndarray) the device->host copy starts right away"""
+        self.slices[name] = (arr, kind, meta)
+        if self.sink is not None:
+            buf = self.sink(name, arr.nbytes)
+            arr.download_async(buf)
+            self.host[name] = buf
+
+    def nbytes(self):
+        return sum(a.nbytes for a, _, _ in self.slices.values())
 
     def download(self):
         out = {}
+        if self.sink is not None:
+            self.ctx.copy_sync()
         for name, (arr, kind, meta) in self.slices.items():
+            flat = self.host[name][:arr.nbytes] if self.sink is not None else arr.download(dtype=np.uint8).reshape(-1)
             if kind == "vector":
-                out[name] = arr.download(dtype=np.uint8).reshape(-1).view(np.dtype(meta)).reshape(-1)
+                out[name] = flat.view(np.dtype(meta)).reshape(-1)
             else:
-                out[name] = arr.download(dtype=np.uint8).reshape(arr.n, arr.width)
+                out[name] = flat.reshape(arr.n, arr.width)
         return out
 
     def free(self):
+        if self.sink is not None and self.ctx is not None:
+            self.ctx.copy_sync()
         for arr, _, _ in self.slices.values():
             arr.free()
         self.slices = {}
 
 
-def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, notricks=False):
+def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, notricks=False, sink=None):
     """fq: this rank's contiguous range of the reads (device.Fastq).  -> (ShardResult, config); config is identical on
     every rank and equal to the single-GPU config of the whole file."""
     sort, raw, pattern = host.normalise_options(sort, raw, pattern)
@@ -329,7 +346,8 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
     first_off = fq.line_offsets(0, 2)
     my_first = fq.download(0, int(first_off[1]) - 1).tobytes()
     ref = comm.all_gather_object(my_first)[0]
-    fq.set_reference(ref, base)
+    if fq.reference != ref:                            # a streamed load may already have measured against it
+        fq.set_reference(ref, base)
     plain = stats_to_plain(fq.analyze())
     parts = comm.all_gather_object((plain, base, n_local))
     parts[0][0]["first_name"] = ref
@@ -378,7 +396,7 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
             cols[c] = ctx.narrow_u32(g, specs[c][1])
             g.free()
     # ---- run_mix over the ranks ----
-    res = ShardResult()
+    res = ShardResult(ctx, sink)
     sorted_on = sort if sort in ('DNA', 'QUAL', 'QNAME') else None
     tables = {'DNA': dna, 'QUAL': qual, 'QNAME': ctx.columns_to_rows(cols)}
     keyed = {t: (t not in raw) for t in tables}
@@ -393,6 +411,13 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
             if keyed[t]:
                 uniq[t] = (g['uniq'], g['n_unique'])
                 payload[t + '.key'] = g['key']
+                if t == 'QNAME':                        # unique rows back to typed columns (uq.py:842-847)
+                    ucols = ctx.rows_to_columns(g['uniq'], [np.dtype(m['dtype']).itemsize for m in columns])
+                    for c, meta in zip(ucols, columns):
+                        res.add(meta['name'], c, 'vector', meta['dtype'])
+                    g['uniq'].free()
+                else:
+                    res.add(t, g['uniq'], 'table', g['uniq'].width)
             else:
                 g['uniq'].free()
                 if t != sorted_on:
@@ -418,18 +443,12 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
             u, nu = uniq[t]
             size = host.key_itemsize(nu)
             k32 = payload[t + '.key']
-            res.slices[t + '.key'] = (ctx.narrow_u32(k32, size), 'vector', 'uint%d' % (8 * size))
-            if t == 'QNAME':
-                ucols = ctx.rows_to_columns(u, [np.dtype(m['dtype']).itemsize for m in columns])
-                for c, meta in zip(ucols, columns):
-                    res.slices[meta['name']] = (c, 'vector', meta['dtype'])
-            else:
-                res.slices[t] = (u, 'table', u.width)
+            res.add(t + '.key', ctx.narrow_u32(k32, size), 'vector', 'uint%d' % (8 * size))
         elif t == 'QNAME':
             for meta in columns:
-                res.slices[meta['name'] + '.raw'] = (payload[meta['name'] + '.raw'], 'vector', meta['dtype'])
+                res.add(meta['name'] + '.raw', payload[meta['name'] + '.raw'], 'vector', meta['dtype'])
         else:
-            res.slices[t + '.raw'] = (payload[t + '.raw'], 'table', tables[t].width)
+            res.add(t + '.raw', payload[t + '.raw'], 'table', tables[t].width)
     config = {
         'base_distribution': dec['base_distribution'], 'qual_distribution': dec['qual_distribution'],
         'reads': n_total, 'bases': dec['bases'], 'qualities': dec['qualities'],
