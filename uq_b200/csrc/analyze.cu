@@ -376,6 +376,7 @@ struct pt_smem {
     unsigned priv_q[PT_WORDS * PT_THREADS];
     unsigned hist_b[PT_LO + 4 * PT_WORDS], hist_q[PT_LO + 4 * PT_WORDS];
     int state[256];                 // per base byte: -1 unseen, 0..255 its only quality so far, 256 = several
+    uint2 lut[257];                 // byte value (256 = inactive lane) -> {byte offset of its counter word row, increment}
 };
 
 // Flush of the private counters of one warp: the four 8-bit fields of a word are widened to two words
@@ -395,10 +396,12 @@ __device__ __forceinline__ void pt_flush(unsigned* priv, unsigned* blk_hist, uns
                 o += __shfl_xor_sync(0xffffffffu, o, sh);
             }
             if (lane == 0) {
-                if (e & 0xFFFFu) atomicAdd(&blk_hist[PT_LO + 4 * w + 0], e & 0xFFFFu);
-                if (o & 0xFFFFu) atomicAdd(&blk_hist[PT_LO + 4 * w + 1], o & 0xFFFFu);
-                if (e >> 16) atomicAdd(&blk_hist[PT_LO + 4 * w + 2], e >> 16);
-                if (o >> 16) atomicAdd(&blk_hist[PT_LO + 4 * w + 3], o >> 16);
+                // counter (word w, field f) belongs to byte value 32 + f*24 + w (w < 24); word 24 holds the two dummies
+                const unsigned i0 = w < 24 ? PT_LO + w : PT_LO + 96u, st = w < 24 ? 24u : 1u;
+                if (e & 0xFFFFu) atomicAdd(&blk_hist[i0], e & 0xFFFFu);
+                if (o & 0xFFFFu) atomicAdd(&blk_hist[i0 + st], o & 0xFFFFu);
+                if (e >> 16) atomicAdd(&blk_hist[i0 + 2 * st], e >> 16);
+                if (o >> 16) atomicAdd(&blk_hist[i0 + 3 * st], o >> 16);
             }
         }
     }
@@ -413,11 +416,19 @@ __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* _
     for (unsigned i = tid; i < PT_WORDS * PT_THREADS; i += PT_THREADS) { S->priv_b[i] = 0; S->priv_q[i] = 0; }
     for (unsigned i = tid; i < PT_LO + 4 * PT_WORDS; i += PT_THREADS) { S->hist_b[i] = 0; S->hist_q[i] = 0; }
     S->state[tid] = -1;
+    for (unsigned v = tid; v < 257; v += PT_THREADS) {
+        const unsigned idx = v == 256 ? PT_IDLE : min(v - PT_LO, PT_OOR);      // clamp: out of range -> slot 96, inactive -> 97
+        // neighbouring byte values go to DIFFERENT counter words (word = idx % 24, field = idx / 24): a thread that
+        // sees A,C,A,C... or two adjacent qualities does not read a word it has just stored (no store forwarding)
+        const unsigned word = idx < 96u ? idx % 24u : 24u, field = idx < 96u ? idx / 24u : idx - 96u;
+        S->lut[v] = make_uint2(word << 10, 1u << (field << 3));
+    }
     tile_init(&S->T);
     __syncthreads();
     unsigned* const pb = S->priv_b + tid;
     unsigned* const pq = S->priv_q + tid;
     const uint32_t bytes_a = smem_u32(S->T.bytes), pb_a = smem_u32(pb), pq_a = smem_u32(pq), state_a = smem_u32(S->state);
+    const uint32_t lut_a = smem_u32(S->lut);
     static_assert(PT_THREADS == 256, "private counter rows are 1024 bytes apart");
     const uint64_t ntiles = (n_reads - r_begin + TL_R - 1) / TL_R;
     unsigned phase = 0, since_flush = 0;
@@ -447,9 +458,9 @@ __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* _
                     if ((it & 127u) == 127u) { pt_flush(S->priv_b, S->hist_b, tid); pt_flush(S->priv_q, S->hist_q, tid); }
                     if (p < len) {
                         const unsigned b = dna[it * 32], q = qual[it * 32];
-                        const unsigned bi = min(b - PT_LO, PT_OOR), qi = min(q - PT_LO, PT_OOR);
-                        pb[(bi >> 2) * PT_THREADS] += 1u << ((bi & 3u) * 8u);
-                        pq[(qi >> 2) * PT_THREADS] += 1u << ((qi & 3u) * 8u);
+                        const uint2 eb = S->lut[b], eq = S->lut[q];
+                        pb[eb.x >> 2] += eb.y;                  // eb.x is a byte offset of the [word][thread] row
+                        pq[eq.x >> 2] += eq.y;
                         const int f = S->state[b];
                         if (f != 256 && f != (int)q) {
                             if (f < 0) { const int old = atomicCAS(&S->state[b], -1, (int)q); if (old >= 0 && old != (int)q) S->state[b] = 256; }
@@ -461,15 +472,21 @@ __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* _
                 continue;
             }
             const uint32_t dna_a = bytes_a + o1 + lane, qual_a = bytes_a + o3 + lane;
+            // software pipelined: the bytes and LUT entries of iteration it+1 are fetched before the counter
+            // read-modify-writes of iteration it, and the two RMWs issue their loads back to back
+            bool act = lane < len;
+            unsigned b = act ? lds_u8(dna_a) : 256u, q = act ? lds_u8(qual_a) : 256u;
+            uint2 eb = lds_u64(lut_a + (b << 3)), eq = lds_u64(lut_a + (q << 3));
             for (uint32_t it = 0; it < iters; it++) {
-                const bool act = it * 32 + lane < len;
-                const unsigned b = act ? lds_u8(dna_a + it * 32) : (PT_LO + PT_IDLE);
-                const unsigned q = act ? lds_u8(qual_a + it * 32) : (PT_LO + PT_IDLE);
-                const unsigned bi = min(b - PT_LO, act ? PT_OOR : PT_IDLE), qi = min(q - PT_LO, act ? PT_OOR : PT_IDLE);
-                const uint32_t wb = pb_a + ((bi >> 2) << 10), wq = pq_a + ((qi >> 2) << 10);     // [word][thread], 256 threads * 4 B
-                sts_u32(wb, lds_u32(wb) + (1u << ((bi & 3u) << 3)));
-                sts_u32(wq, lds_u32(wq) + (1u << ((qi & 3u) << 3)));
-                const int f = (int)lds_u32(state_a + (b << 2));
+                const bool nact = (it + 1) * 32 + lane < len;
+                const unsigned nb = nact ? lds_u8(dna_a + (it + 1) * 32) : 256u;
+                const unsigned nq = nact ? lds_u8(qual_a + (it + 1) * 32) : 256u;
+                const uint32_t wb = pb_a + eb.x, wq = pq_a + eq.x;                               // [word][thread], 256 threads * 4 B
+                const uint32_t cb = lds_u32(wb), cq = lds_u32(wq);
+                const int f = (int)lds_u32(state_a + ((b & 255u) << 2));
+                const uint2 neb = lds_u64(lut_a + (nb << 3)), neq = lds_u64(lut_a + (nq << 3));
+                sts_u32(wb, cb + eb.y);
+                sts_u32(wq, cq + eq.y);
                 if (act && f != 256 && f != (int)q) {
                     if (f < 0) {
                         const int old = atomicCAS(&S->state[b], -1, (int)q);
@@ -478,6 +495,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* _
                         S->state[b] = 256;
                     }
                 }
+                act = nact; b = nb; q = nq; eb = neb; eq = neq;
             }
         }
     }
