@@ -75,33 +75,156 @@ __global__ void __launch_bounds__(ST) k_active_flags(const uint32_t* __restrict_
 // count is returned so that the host can stop as soon as there are none.
 #define SG_MAX 32
 #define SG_STAGE_BYTES 256
-#define SG_PAIRS (SG_MAX * (SG_MAX - 1) / 2)
 
-// pair q = b(b-1)/2 + a, a < b: all pairs of a group of sz rows are q < sz(sz-1)/2
-struct sg_pairs_t { uint8_t a[SG_PAIRS], b[SG_PAIRS]; };
-__constant__ sg_pairs_t c_sg_pairs;
-static bool g_sg_pairs_ready[64] = {false};
-
-static int sg_upload_pairs(uqb_ctx* ctx) {
-    if (ctx->device < 64 && g_sg_pairs_ready[ctx->device]) return 0;
-    sg_pairs_t h;
-    int q = 0;
-    for (int b = 1; b < SG_MAX; b++)
-        for (int a = 0; a < b; a++) { h.a[q] = (uint8_t)a; h.b[q] = (uint8_t)b; q++; }
-    UQB_CUDA(cudaMemcpyToSymbolAsync(c_sg_pairs, &h, sizeof(h), 0, cudaMemcpyHostToDevice, ctx->stream));
-    UQB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->device < 64) g_sg_pairs_ready[ctx->device] = true;
-    return 0;
-}
-
-template <bool STAGED>
+// Staged variant.  SUB lanes work on one row (SUB = 8, 16 or 32; 32 / SUB rows at a time).
+//   staging   the remaining bytes of every row are fetched as ALIGNED 32-bit words (two per lane, funnel
+//             shifted to the row's byte phase) and stored big-endian, zero padded, `pitch` words per row;
+//   sorting   three-way quicksort with warp-uniform control: the first row of the first unresolved segment
+//             is the pivot, every other row of the segment is compared with it word-parallel (ballots give
+//             the first differing word), and a STABLE partition (ballot + popc) moves the rows to
+//             less | equal | greater.  The equal range is final; ranges of one row are final.  A group of
+//             identical rows costs size-1 compares (the common case for duplicated reads / qualities), a
+//             group of distinct rows O(size log size) instead of all size(size-1)/2 pairs.
+// Stable partitions keep equal rows in their current (= input) order.
+template <int SUB>
 __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
                                                     uint32_t* __restrict__ perm, uint32_t* __restrict__ head, uint8_t* __restrict__ done,
                                                     const uint32_t* __restrict__ headpos, const uint32_t* __restrict__ d_ngroups,
                                                     uint32_t pitch, unsigned long long* __restrict__ large_rows) {
     extern __shared__ uint32_t sg_smem[];
+    constexpr uint32_t NP = 32u / SUB;
+    constexpr uint32_t SUBMASK = SUB == 32 ? 0xffffffffu : ((1u << (SUB & 31)) - 1u);
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const unsigned sg = lane / SUB, sl = lane % SUB;
     uint32_t* srows = sg_smem + (size_t)w * (SG_MAX * pitch + 64);
+    uint32_t* sord = srows + SG_MAX * pitch;
+    const uint32_t G = *d_ngroups;
+    const uint32_t rem = width - off;
+    const uint64_t warps_total = (uint64_t)gridDim.x * (ST / 32);
+    const uint32_t ltm = (1u << lane) - 1u;
+    unsigned long long my_large = 0;
+    for (uint64_t g0 = ((uint64_t)blockIdx.x * (ST / 32) + w) * 32; g0 < G; g0 += warps_total * 32) {
+        const uint64_t g = g0 + lane;
+        uint32_t start = 0, size = 0;
+        if (g < G) { start = headpos[g]; size = headpos[g + 1] - start; }
+        const bool fin = size >= 2 && done[start];
+        if (size > SG_MAX && !fin) my_large += size;
+        unsigned need = __ballot_sync(0xffffffffu, size >= 2 && size <= SG_MAX && !fin);
+        // The rows of a group sit at random places of the table, and a warp works on one group at a time:
+        // to keep many DRAM requests in flight, the rows of the NEXT eight groups are prefetched into L2
+        // (four lanes per group) while the current eight are sorted.
+        const unsigned need_all = need;
+        auto prefetch_sub = [&](unsigned b) {
+            const unsigned gi = 8u * b + (lane >> 2);
+            const uint32_t st = __shfl_sync(0xffffffffu, start, gi), szz = __shfl_sync(0xffffffffu, size, gi);
+            if ((need_all >> gi) & 1u) {
+                for (uint32_t t = lane & 3u; t < szz; t += 4) {
+                    const uint64_t A = (uint64_t)(uintptr_t)rows + (uint64_t)perm[st + t] * width + off;
+                    for (uint64_t q = A & ~31ull; q < A + rem; q += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+                }
+            }
+        };
+        if (need & 0x000000ffu) prefetch_sub(0);
+        unsigned fetched = 1u;                                             // sub-batches already prefetched
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            while (fetched < 4u && fetched <= ((unsigned)src >> 3) + 1u) {      // stay one sub-batch ahead
+                if ((need_all >> (8u * fetched)) & 0xffu) prefetch_sub(fetched);
+                fetched++;
+            }
+            const uint32_t s = __shfl_sync(0xffffffffu, start, src), sz = __shfl_sync(0xffffffffu, size, src);
+            const uint32_t r = lane < sz ? perm[s + lane] : 0u;
+            // ---- stage ----
+#pragma unroll 2
+            for (uint32_t j0 = 0; j0 < sz; j0 += NP) {
+                const uint32_t j = j0 + sg;
+                const uint32_t rj = __shfl_sync(0xffffffffu, r, j & 31u);
+                if (j < sz) {
+                    const uint64_t A = (uint64_t)(uintptr_t)rows + (uint64_t)rj * width + off;
+                    const uint32_t ph = (uint32_t)A & 3u;
+                    const uint32_t* base = reinterpret_cast<const uint32_t*>(A - ph);
+                    for (uint32_t wd = sl; wd < pitch; wd += SUB) {
+                        const uint32_t lo = __ldg(base + wd);
+                        // the next aligned word is needed only when its first byte still belongs to the row
+                        const uint32_t hi = (ph != 0u && 4u * wd + 4u - ph < rem) ? __ldg(base + wd + 1) : 0u;
+                        uint32_t v = __byte_perm(__funnelshift_r(lo, hi, ph * 8u), 0u, 0x0123);
+                        const uint32_t nvalid = rem - 4u * wd;
+                        if (nvalid < 4u) v &= 0xffffffffu << ((4u - nvalid) * 8u);
+                        srows[j * pitch + wd] = v;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- sort ----
+            uint32_t ord = lane;                                           // staged row at position `lane`
+            uint32_t B = 1u;                                               // segment starts (finally: distinct-row starts)
+            uint32_t R = sz < 32u ? ~((1u << sz) - 1u) : 0u;               // resolved positions
+            while (~R) {
+                const uint32_t lo = (uint32_t)__ffs((int)~R) - 1u;
+                const uint32_t above = B & ~((2u << lo) - 1u);
+                const uint32_t hi = above ? (uint32_t)__ffs((int)above) - 1u : sz;
+                const uint32_t piv = __shfl_sync(0xffffffffu, ord, lo);
+                int c = 0;                                                 // memcmp(row at my position, pivot)
+                for (uint32_t q0 = lo + 1; q0 < hi; q0 += NP) {
+                    const uint32_t pp = q0 + sg;
+                    const bool pv = pp < hi;
+                    const uint32_t a = __shfl_sync(0xffffffffu, ord, pp & 31u);
+                    int cc = 0;
+                    for (uint32_t w0 = 0; w0 < pitch; w0 += SUB) {         // warp-uniform trip count
+                        const uint32_t wd = w0 + sl;
+                        uint32_t x = 0, y = 0;
+                        if (pv && wd < pitch) { x = srows[a * pitch + wd]; y = srows[piv * pitch + wd]; }
+                        const unsigned ne = (__ballot_sync(0xffffffffu, x != y) >> (sg * SUB)) & SUBMASK;
+                        const unsigned lt = (__ballot_sync(0xffffffffu, x < y) >> (sg * SUB)) & SUBMASK;
+                        if (cc == 0 && ne) cc = ((lt >> (__ffs((int)ne) - 1)) & 1u) ? -1 : 1;
+                    }
+                    if (NP == 1) {
+                        if (lane == q0) c = cc;
+                    } else {
+                        const int got = __shfl_sync(0xffffffffu, cc, ((lane - q0) * SUB) & 31u);
+                        if (lane >= q0 && lane < q0 + NP && lane < hi) c = got;
+                    }
+                }
+                const bool inr = lane >= lo && lane < hi;
+                const unsigned less = __ballot_sync(0xffffffffu, inr && c < 0);
+                const unsigned eq = __ballot_sync(0xffffffffu, inr && c == 0);
+                const unsigned gt = __ballot_sync(0xffffffffu, inr && c > 0);
+                const uint32_t nl = __popc(less), neq = __popc(eq);
+                uint32_t np = lane;
+                if (inr) np = c < 0 ? lo + __popc(less & ltm) : (c == 0 ? lo + nl + __popc(eq & ltm) : lo + nl + neq + __popc(gt & ltm));
+                sord[np] = ord;
+                __syncwarp();
+                ord = sord[lane];
+                __syncwarp();
+                const uint32_t e0 = lo + nl, h0 = e0 + neq;                // equal range [e0, h0), greater range [h0, hi)
+                B |= 1u << e0;
+                if (h0 < hi) B |= 1u << h0;
+                R |= (uint32_t)((1ull << h0) - (1ull << e0));
+                if (nl == 1u) R |= 1u << lo;
+                if (hi - h0 == 1u) R |= 1u << h0;
+            }
+            const uint32_t rfin = __shfl_sync(0xffffffffu, r, ord & 31u);
+            if (lane < sz) {
+                perm[s + lane] = rfin;
+                if (lane > 0) head[s + lane] = (B >> lane) & 1u;
+                done[s + lane] = 1;
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_large += __shfl_xor_sync(0xffffffffu, my_large, o);
+    if (lane == 0 && my_large) atomicAdd(large_rows, my_large);
+}
+
+// Rows whose remainder is wider than SG_STAGE_BYTES: lane i ranks row i against the others straight from
+// global memory (rare: only very long variable-length reads get here).
+__global__ void __launch_bounds__(ST) k_small_groups_gmem(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
+                                                         uint32_t* __restrict__ perm, uint32_t* __restrict__ head, uint8_t* __restrict__ done,
+                                                         const uint32_t* __restrict__ headpos, const uint32_t* __restrict__ d_ngroups,
+                                                         unsigned long long* __restrict__ large_rows) {
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t G = *d_ngroups;
     const uint32_t rem = width - off;
     const uint64_t warps_total = (uint64_t)gridDim.x * (ST / 32);
@@ -118,58 +241,8 @@ __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__
             need &= need - 1;
             const uint32_t s = __shfl_sync(0xffffffffu, start, src), sz = __shfl_sync(0xffffffffu, size, src);
             const uint32_t r = lane < sz ? perm[s + lane] : 0u;
-            if (STAGED) {
-                for (uint32_t j = 0; j < sz; j++) {
-                    const uint32_t rj = __shfl_sync(0xffffffffu, r, j);
-                    const uint8_t* src_row = rows + (uint64_t)rj * width + off;
-                    for (uint32_t wd = lane; wd < pitch; wd += 32) {
-                        uint32_t v = 0;
-#pragma unroll
-                        for (uint32_t b = 0; b < 4; b++) {
-                            const uint32_t idx = wd * 4 + b;
-                            v = (v << 8) | (idx < rem ? (uint32_t)__ldg(src_row + idx) : 0u);
-                        }
-                        srows[j * pitch + wd] = v;
-                    }
-                }
-                __syncwarp();
-            }
             uint32_t rank = 0;
             bool eq_before = false;
-            if (STAGED) {
-                // all pairs (a < b) of the group, `np` pairs at a time: a sub-group of `sub` lanes compares
-                // the two rows word-parallel; ballots give the first differing word and its order
-                uint32_t* srank = srows + SG_MAX * pitch;          // [32] rank, [32] equal-to-an-earlier-row
-                srank[lane] = 0; srank[32 + lane] = 0;
-                __syncwarp();
-                const uint32_t sub = pitch <= 8 ? 8u : (pitch <= 16 ? 16u : 32u);
-                const uint32_t np = 32u / sub, sg = lane / sub, sl = lane % sub;
-                const uint32_t submask = sub == 32u ? 0xffffffffu : ((1u << sub) - 1u);
-                const uint32_t npairs = sz * (sz - 1) / 2;
-                for (uint32_t q0 = 0; q0 < npairs; q0 += np) {
-                    const uint32_t q = q0 + sg;
-                    const bool pv = q < npairs;
-                    const uint32_t a = pv ? c_sg_pairs.a[q] : 0u, b = pv ? c_sg_pairs.b[q] : 0u;
-                    int c = 0;            // memcmp(row_a, row_b), known to the whole sub-group
-                    for (uint32_t w0 = 0; w0 < pitch; w0 += sub) {          // warp-uniform trip count
-                        const uint32_t wd = w0 + sl;
-                        uint32_t x = 0, y = 0;
-                        if (pv && wd < pitch) { x = srows[a * pitch + wd]; y = srows[b * pitch + wd]; }
-                        const unsigned ne = (__ballot_sync(0xffffffffu, x != y) >> (sg * sub)) & submask;
-                        const unsigned lt = (__ballot_sync(0xffffffffu, x < y) >> (sg * sub)) & submask;
-                        if (c == 0 && ne) c = ((lt >> (__ffs(ne) - 1)) & 1u) ? -1 : 1;
-                    }
-                    if (pv && sl == 0) {
-                        if (c > 0) atomicAdd(&srank[a], 1u);                 // row_b < row_a
-                        else atomicAdd(&srank[b], 1u);                       // row_a <= row_b: a stays in front (stable)
-                        if (c == 0) srank[32 + b] = 1u;
-                    }
-                }
-                __syncwarp();
-                rank = srank[lane];
-                eq_before = srank[32 + lane] != 0u;
-                __syncwarp();
-            } else
             for (uint32_t j = 0; j < sz; j++) {
                 const uint32_t rj = __shfl_sync(0xffffffffu, r, j);
                 if (lane < sz && j != lane) {
@@ -278,8 +351,6 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
         UQB_TRY(uqb_dalloc_t(ctx, &done, n));
         UQB_TRY(uqb_dalloc_t(ctx, &d_large, 1));
         UQB_CUDA(cudaMemsetAsync(done, 0, n, ctx->stream));
-        auto k_small_groups_smem = k_small_groups<true>;
-        auto k_small_groups_gmem = k_small_groups<false>;
         for (uint32_t c = 1; c < nchunks; c++) {
             const uint32_t off = 8 * c;
             UQB_TRY(uqb_scan_u32(ctx, head, excl, n, d_tot));
@@ -289,13 +360,19 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
             const uint32_t rem = width - off;
             const unsigned sg_grid = uqb_grid(ctx, n, ST, 16);
             if (rem <= SG_STAGE_BYTES) {
-                UQB_TRY(sg_upload_pairs(ctx));
                 const uint32_t pitch = (rem + 3) / 4;
                 const size_t smem = (size_t)(ST / 32) * (SG_MAX * pitch + 64) * 4;
-                UQB_CUDA(cudaFuncSetAttribute(k_small_groups_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                UQB_LAUNCH(k_small_groups_smem, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
+                if (pitch <= 8) {
+                    UQB_LAUNCH(k_small_groups<8>, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
+                } else if (pitch <= 16) {
+                    UQB_LAUNCH(k_small_groups<16>, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
+                } else {
+                    auto k_small_groups_32 = k_small_groups<32>;
+                    UQB_CUDA(cudaFuncSetAttribute(k_small_groups_32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    UQB_LAUNCH(k_small_groups_32, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
+                }
             } else {
-                UQB_LAUNCH(k_small_groups_gmem, sg_grid, ST, 0, rows, width, off, perm, head, done, headpos, d_tot, 1u, d_large);
+                UQB_LAUNCH(k_small_groups_gmem, sg_grid, ST, 0, rows, width, off, perm, head, done, headpos, d_tot, d_large);
             }
             unsigned long long large = 0;
             UQB_TRY(uqb_readback(ctx, &large, d_large, 8));
@@ -367,6 +444,71 @@ __global__ void __launch_bounds__(ST) k_gather_rows(const uint8_t* __restrict__ 
     }
 }
 
+// rows of 17..GR_MAXW bytes: a warp produces the output of 32 consecutive rows, which is ONE contiguous,
+// 32-byte aligned range.  Lanes walk that range in 32-bit words (coalesced word stores); the four bytes of
+// a word come from one source row or, at a row seam, from two.  Several words per lane are in flight
+// (unrolled), so the random row reads overlap.
+#define GR_MAXW 1024
+__global__ void __launch_bounds__(ST) k_gather_rows32(const uint8_t* __restrict__ table, uint32_t width, uint32_t q128, uint32_t m128,
+                                                     const uint32_t* __restrict__ idx, uint64_t nrows, uint8_t* __restrict__ out) {
+    __shared__ uint32_t sidx[ST / 32][32];
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint64_t nblk = (nrows + 31) / 32, wstride = (uint64_t)gridDim.x * (ST / 32);
+    for (uint64_t blk = (uint64_t)blockIdx.x * (ST / 32) + w; blk < nblk; blk += wstride) {
+        const uint64_t i0 = blk * 32;
+        const uint32_t nr = (uint32_t)(nrows - i0 < 32 ? nrows - i0 : 32);
+        __syncwarp();
+        sidx[w][lane] = lane < nr ? __ldg(idx + i0 + lane) : 0u;
+        __syncwarp();
+        const uint32_t total = nr * width, nwords = total >> 2;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + i0 * width);
+        uint32_t r = (4u * lane) / width, o = 4u * lane - r * width;
+#pragma unroll 4
+        for (uint32_t k = lane; k < nwords; k += 32) {
+            const uint8_t* s = table + (uint64_t)sidx[w][r] * width + o;
+            uint32_t v;
+            if (o + 4u <= width) {
+                v = (uint32_t)__ldg(s) | ((uint32_t)__ldg(s + 1) << 8) | ((uint32_t)__ldg(s + 2) << 16) | ((uint32_t)__ldg(s + 3) << 24);
+            } else {
+                const uint32_t n0 = width - o;                                  // 1..3 bytes from row r, the rest from row r + 1
+                const uint8_t* s2 = table + (uint64_t)sidx[w][(r + 1) & 31u] * width;
+                v = 0;
+#pragma unroll
+                for (uint32_t b = 0; b < 4; b++) v |= (uint32_t)(b < n0 ? __ldg(s + b) : __ldg(s2 + (b - n0))) << (8 * b);
+            }
+            dst[k] = v;
+            o += m128; r += q128;
+            if (o >= width) { o -= width; r++; }
+        }
+        if (lane < (total & 3u)) {                                            // last partial word (last block only)
+            const uint32_t bo = (nwords << 2) + lane, rr = bo / width;
+            out[i0 * width + bo] = __ldg(table + (uint64_t)sidx[w][rr] * width + (bo - rr * width));
+        }
+    }
+}
+
+// rows of 3..16 bytes (not 1, 2, 4, 8): one thread per row reads its row, the CTA's 256 rows are staged in
+// shared memory and leave as coalesced 32-bit words
+__global__ void __launch_bounds__(ST) k_gather_narrow(const uint8_t* __restrict__ table, uint32_t width, const uint32_t* __restrict__ idx,
+                                                     uint64_t nrows, uint8_t* __restrict__ out) {
+    __shared__ __align__(16) uint8_t stage[ST * 16];
+    const uint64_t nblk = (nrows + ST - 1) / ST;
+    for (uint64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const uint64_t i0 = blk * ST, i = i0 + threadIdx.x;
+        const uint32_t nr = (uint32_t)(nrows - i0 < ST ? nrows - i0 : ST);
+        __syncthreads();
+        if (i < nrows) {
+            const uint8_t* s = table + (uint64_t)__ldg(idx + i) * width;
+            for (uint32_t b = 0; b < width; b++) stage[threadIdx.x * width + b] = __ldg(s + b);
+        }
+        __syncthreads();
+        const uint32_t total = nr * width;
+        uint8_t* dst = out + i0 * width;                                      // ST * width bytes per block: 4-byte aligned
+        for (uint32_t k = threadIdx.x; k < (total >> 2); k += ST) reinterpret_cast<uint32_t*>(dst)[k] = reinterpret_cast<const uint32_t*>(stage)[k];
+        if (threadIdx.x < (total & 3u)) dst[(total & ~3u) + threadIdx.x] = stage[(total & ~3u) + threadIdx.x];
+    }
+}
+
 // narrow rows (1, 2, 4, 8 bytes): one thread per row, typed loads
 template <typename T>
 __global__ void __launch_bounds__(ST) k_gather_items(const T* __restrict__ table, const uint32_t* __restrict__ idx, uint64_t n, T* __restrict__ out) {
@@ -382,6 +524,16 @@ static int gather_rows_impl(uqb_ctx* ctx, const void* table, uint32_t width, con
         case 2: UQB_LAUNCH_B(ab, k_gather_items<uint16_t>, g, ST, 0, (const uint16_t*)table, idx, n, (uint16_t*)out); return 0;
         case 4: UQB_LAUNCH_B(ab, k_gather_items<uint32_t>, g, ST, 0, (const uint32_t*)table, idx, n, (uint32_t*)out); return 0;
         case 8: UQB_LAUNCH_B(ab, k_gather_items<uint64_t>, g, ST, 0, (const uint64_t*)table, idx, n, (uint64_t*)out); return 0;
+    }
+    if ((reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+        if (width <= 16) {
+            UQB_LAUNCH_B(ab, k_gather_narrow, uqb_grid(ctx, n, ST, 16), ST, 0, (const uint8_t*)table, width, idx, n, (uint8_t*)out);
+            return 0;
+        }
+        if (width <= GR_MAXW) {
+            UQB_LAUNCH_B(ab, k_gather_rows32, uqb_grid(ctx, n, ST, 16), ST, 0, (const uint8_t*)table, width, 128u / width, 128u % width, idx, n, (uint8_t*)out);
+            return 0;
+        }
     }
     UQB_LAUNCH_B(ab, k_gather_rows, uqb_grid(ctx, n, ST / 32, 16), ST, 0, (const uint8_t*)table, width, idx, n, (uint8_t*)out);
     return 0;
