@@ -86,11 +86,22 @@ __global__ void __launch_bounds__(ST) k_active_flags(const uint32_t* __restrict_
 //             identical rows costs size-1 compares (the common case for duplicated reads / qualities), a
 //             group of distinct rows O(size log size) instead of all size(size-1)/2 pairs.
 // Stable partitions keep equal rows in their current (= input) order.
-template <int SUB>
+// The first pass (pivot = first row of the group) is fused with the staging: the pivot's words stay in
+// registers and every row is compared with them the moment it arrives, so a group of identical rows is
+// finished without reading shared memory at all.
+__device__ __forceinline__ void sg_prefetch(const uint8_t* rows, uint32_t width, uint32_t off, uint32_t rem, const uint32_t* perm,
+                                            uint32_t st, uint32_t szz, unsigned lane) {
+    for (uint32_t t = lane & 3u; t < szz; t += 4) {
+        const uint64_t A = (uint64_t)(uintptr_t)rows + (uint64_t)perm[st + t] * width + off;
+        for (uint64_t q = A & ~31ull; q < A + rem; q += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    }
+}
+
+template <int SUB, int TRIPS>      // TRIPS = ceil(pitch / SUB): 1, or 2 for SUB == 32 and 33..64 words
 __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
                                                     uint32_t* __restrict__ perm, uint32_t* __restrict__ head, uint8_t* __restrict__ done,
                                                     const uint32_t* __restrict__ headpos, const uint32_t* __restrict__ d_ngroups,
-                                                    uint32_t pitch, unsigned long long* __restrict__ large_rows) {
+                                                    uint32_t pitch, uint32_t lookahead, unsigned long long* __restrict__ large_rows) {
     extern __shared__ uint32_t sg_smem[];
     constexpr uint32_t NP = 32u / SUB;
     constexpr uint32_t SUBMASK = SUB == 32 ? 0xffffffffu : ((1u << (SUB & 31)) - 1u);
@@ -102,6 +113,16 @@ __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__
     const uint32_t rem = width - off;
     const uint64_t warps_total = (uint64_t)gridDim.x * (ST / 32);
     const uint32_t ltm = (1u << lane) - 1u;
+    // per-lane constants of the staging: word index, validity, mask of the row's last (partial) word
+    uint32_t tailmask[TRIPS];
+    bool wvalid[TRIPS];
+#pragma unroll
+    for (int t = 0; t < TRIPS; t++) {
+        const uint32_t wd = t * SUB + sl;
+        wvalid[t] = wd < pitch;
+        const uint32_t nvalid = wvalid[t] ? rem - 4u * wd : 0u;
+        tailmask[t] = nvalid >= 4u ? 0xffffffffu : (nvalid ? 0xffffffffu << ((4u - nvalid) * 8u) : 0u);
+    }
     unsigned long long my_large = 0;
     for (uint64_t g0 = ((uint64_t)blockIdx.x * (ST / 32) + w) * 32; g0 < G; g0 += warps_total * 32) {
         const uint64_t g = g0 + lane;
@@ -111,48 +132,62 @@ __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__
         if (size > SG_MAX && !fin) my_large += size;
         unsigned need = __ballot_sync(0xffffffffu, size >= 2 && size <= SG_MAX && !fin);
         // The rows of a group sit at random places of the table, and a warp works on one group at a time:
-        // to keep many DRAM requests in flight, the rows of the NEXT eight groups are prefetched into L2
-        // (four lanes per group) while the current eight are sorted.
+        // optionally the rows of the NEXT eight groups are prefetched into L2 (four lanes per group) while the
+        // current eight are sorted.
         const unsigned need_all = need;
-        auto prefetch_sub = [&](unsigned b) {
-            const unsigned gi = 8u * b + (lane >> 2);
-            const uint32_t st = __shfl_sync(0xffffffffu, start, gi), szz = __shfl_sync(0xffffffffu, size, gi);
-            if ((need_all >> gi) & 1u) {
-                for (uint32_t t = lane & 3u; t < szz; t += 4) {
-                    const uint64_t A = (uint64_t)(uintptr_t)rows + (uint64_t)perm[st + t] * width + off;
-                    for (uint64_t q = A & ~31ull; q < A + rem; q += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-                }
-            }
-        };
-        if (need & 0x000000ffu) prefetch_sub(0);
-        unsigned fetched = 1u;                                             // sub-batches already prefetched
+        unsigned fetched = 4u;
+        if (lookahead) {
+            const uint32_t st = __shfl_sync(0xffffffffu, start, lane >> 2), szz = __shfl_sync(0xffffffffu, size, lane >> 2);
+            if ((need_all >> (lane >> 2)) & 1u) sg_prefetch(rows, width, off, rem, perm, st, szz, lane);
+            fetched = 1u;
+        }
         while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
             while (fetched < 4u && fetched <= ((unsigned)src >> 3) + 1u) {      // stay one sub-batch ahead
-                if ((need_all >> (8u * fetched)) & 0xffu) prefetch_sub(fetched);
+                const unsigned gi = 8u * fetched + (lane >> 2);
+                const uint32_t st = __shfl_sync(0xffffffffu, start, gi), szz = __shfl_sync(0xffffffffu, size, gi);
+                if ((need_all >> gi) & 1u) sg_prefetch(rows, width, off, rem, perm, st, szz, lane);
                 fetched++;
             }
             const uint32_t s = __shfl_sync(0xffffffffu, start, src), sz = __shfl_sync(0xffffffffu, size, src);
             const uint32_t r = lane < sz ? perm[s + lane] : 0u;
-            // ---- stage ----
+            // ---- stage, and compare with the first row ----
+            uint32_t pvw[TRIPS];                                           // the pivot's words of this lane
+            int c = 0;                                                     // memcmp(row at my position, pivot)
 #pragma unroll 2
             for (uint32_t j0 = 0; j0 < sz; j0 += NP) {
                 const uint32_t j = j0 + sg;
                 const uint32_t rj = __shfl_sync(0xffffffffu, r, j & 31u);
-                if (j < sz) {
-                    const uint64_t A = (uint64_t)(uintptr_t)rows + (uint64_t)rj * width + off;
-                    const uint32_t ph = (uint32_t)A & 3u;
-                    const uint32_t* base = reinterpret_cast<const uint32_t*>(A - ph);
-                    for (uint32_t wd = sl; wd < pitch; wd += SUB) {
-                        const uint32_t lo = __ldg(base + wd);
-                        // the next aligned word is needed only when its first byte still belongs to the row
-                        const uint32_t hi = (ph != 0u && 4u * wd + 4u - ph < rem) ? __ldg(base + wd + 1) : 0u;
-                        uint32_t v = __byte_perm(__funnelshift_r(lo, hi, ph * 8u), 0u, 0x0123);
-                        const uint32_t nvalid = rem - 4u * wd;
-                        if (nvalid < 4u) v &= 0xffffffffu << ((4u - nvalid) * 8u);
-                        srows[j * pitch + wd] = v;
-                    }
+                const uint64_t A = (uint64_t)(uintptr_t)rows + (uint64_t)rj * width + off;
+                const uint32_t ph = (uint32_t)A & 3u;
+                const uint32_t* base = reinterpret_cast<const uint32_t*>(A - ph) + sl;
+                const bool jv = j < sz;
+                uint32_t v[TRIPS];
+#pragma unroll
+                for (int t = 0; t < TRIPS; t++) {
+                    uint32_t lo = 0, hi = 0;
+                    // the word after the row's last one may be read (never used): every table has >= 8 bytes of slack
+                    if (jv && wvalid[t]) { lo = __ldg(base + t * SUB); hi = __ldg(base + t * SUB + 1); }
+                    v[t] = __byte_perm(__funnelshift_r(lo, hi, ph * 8u), 0u, 0x0123) & tailmask[t];
+                    if (jv && wvalid[t]) srows[j * pitch + t * SUB + sl] = v[t];
+                }
+                if (j0 == 0) {
+#pragma unroll
+                    for (int t = 0; t < TRIPS; t++) pvw[t] = NP == 1 ? v[t] : __shfl_sync(0xffffffffu, v[t], sl);
+                }
+                int cc = 0;
+#pragma unroll
+                for (int t = 0; t < TRIPS; t++) {
+                    const unsigned ne = (__ballot_sync(0xffffffffu, jv && v[t] != pvw[t]) >> (sg * SUB)) & SUBMASK;
+                    const unsigned lt = (__ballot_sync(0xffffffffu, v[t] < pvw[t]) >> (sg * SUB)) & SUBMASK;
+                    if (cc == 0 && ne) cc = ((lt >> (__ffs((int)ne) - 1)) & 1u) ? -1 : 1;
+                }
+                if (NP == 1) {
+                    if (lane == j0) c = cc;
+                } else {
+                    const int got = __shfl_sync(0xffffffffu, cc, ((lane - j0) * SUB) & 31u);
+                    if (lane >= j0 && lane < j0 + NP) c = got;
                 }
             }
             __syncwarp();
@@ -160,44 +195,52 @@ __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__
             uint32_t ord = lane;                                           // staged row at position `lane`
             uint32_t B = 1u;                                               // segment starts (finally: distinct-row starts)
             uint32_t R = sz < 32u ? ~((1u << sz) - 1u) : 0u;               // resolved positions
+            bool have_c = true;
             while (~R) {
                 const uint32_t lo = (uint32_t)__ffs((int)~R) - 1u;
                 const uint32_t above = B & ~((2u << lo) - 1u);
                 const uint32_t hi = above ? (uint32_t)__ffs((int)above) - 1u : sz;
-                const uint32_t piv = __shfl_sync(0xffffffffu, ord, lo);
-                int c = 0;                                                 // memcmp(row at my position, pivot)
-                for (uint32_t q0 = lo + 1; q0 < hi; q0 += NP) {
-                    const uint32_t pp = q0 + sg;
-                    const bool pv = pp < hi;
-                    const uint32_t a = __shfl_sync(0xffffffffu, ord, pp & 31u);
-                    int cc = 0;
-                    for (uint32_t w0 = 0; w0 < pitch; w0 += SUB) {         // warp-uniform trip count
-                        const uint32_t wd = w0 + sl;
-                        uint32_t x = 0, y = 0;
-                        if (pv && wd < pitch) { x = srows[a * pitch + wd]; y = srows[piv * pitch + wd]; }
-                        const unsigned ne = (__ballot_sync(0xffffffffu, x != y) >> (sg * SUB)) & SUBMASK;
-                        const unsigned lt = (__ballot_sync(0xffffffffu, x < y) >> (sg * SUB)) & SUBMASK;
-                        if (cc == 0 && ne) cc = ((lt >> (__ffs((int)ne) - 1)) & 1u) ? -1 : 1;
-                    }
-                    if (NP == 1) {
-                        if (lane == q0) c = cc;
-                    } else {
-                        const int got = __shfl_sync(0xffffffffu, cc, ((lane - q0) * SUB) & 31u);
-                        if (lane >= q0 && lane < q0 + NP && lane < hi) c = got;
+                if (!have_c) {
+                    const uint32_t piv = __shfl_sync(0xffffffffu, ord, lo);
+                    uint32_t y[TRIPS];
+#pragma unroll
+                    for (int t = 0; t < TRIPS; t++) y[t] = wvalid[t] ? srows[piv * pitch + t * SUB + sl] : 0u;
+                    c = 0;
+                    for (uint32_t q0 = lo + 1; q0 < hi; q0 += NP) {
+                        const uint32_t pp = q0 + sg;
+                        const bool pv = pp < hi;
+                        const uint32_t a = __shfl_sync(0xffffffffu, ord, pp & 31u);
+                        int cc = 0;
+#pragma unroll
+                        for (int t = 0; t < TRIPS; t++) {
+                            const uint32_t x = (pv && wvalid[t]) ? srows[a * pitch + t * SUB + sl] : y[t];
+                            const unsigned ne = (__ballot_sync(0xffffffffu, x != y[t]) >> (sg * SUB)) & SUBMASK;
+                            const unsigned lt = (__ballot_sync(0xffffffffu, x < y[t]) >> (sg * SUB)) & SUBMASK;
+                            if (cc == 0 && ne) cc = ((lt >> (__ffs((int)ne) - 1)) & 1u) ? -1 : 1;
+                        }
+                        if (NP == 1) {
+                            if (lane == q0) c = cc;
+                        } else {
+                            const int got = __shfl_sync(0xffffffffu, cc, ((lane - q0) * SUB) & 31u);
+                            if (lane >= q0 && lane < q0 + NP && lane < hi) c = got;
+                        }
                     }
                 }
+                have_c = false;
                 const bool inr = lane >= lo && lane < hi;
                 const unsigned less = __ballot_sync(0xffffffffu, inr && c < 0);
                 const unsigned eq = __ballot_sync(0xffffffffu, inr && c == 0);
-                const unsigned gt = __ballot_sync(0xffffffffu, inr && c > 0);
                 const uint32_t nl = __popc(less), neq = __popc(eq);
-                uint32_t np = lane;
-                if (inr) np = c < 0 ? lo + __popc(less & ltm) : (c == 0 ? lo + nl + __popc(eq & ltm) : lo + nl + neq + __popc(gt & ltm));
-                sord[np] = ord;
-                __syncwarp();
-                ord = sord[lane];
-                __syncwarp();
                 const uint32_t e0 = lo + nl, h0 = e0 + neq;                // equal range [e0, h0), greater range [h0, hi)
+                if (nl | (hi - h0)) {                                      // anything to move?
+                    const unsigned gt = ((hi < 32u ? (1u << hi) : 0u) - (1u << lo)) & ~(less | eq);
+                    uint32_t np = lane;
+                    if (inr) np = c < 0 ? lo + __popc(less & ltm) : (c == 0 ? e0 + __popc(eq & ltm) : h0 + __popc(gt & ltm));
+                    sord[np] = ord;
+                    __syncwarp();
+                    ord = sord[lane];
+                    __syncwarp();
+                }
                 B |= 1u << e0;
                 if (h0 < hi) B |= 1u << h0;
                 R |= (uint32_t)((1ull << h0) - (1ull << e0));
@@ -362,14 +405,22 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
             if (rem <= SG_STAGE_BYTES) {
                 const uint32_t pitch = (rem + 3) / 4;
                 const size_t smem = (size_t)(ST / 32) * (SG_MAX * pitch + 64) * 4;
+                static const char* la_env = getenv("UQB_SG_LOOKAHEAD");
+                const uint32_t la = la_env ? (uint32_t)atoi(la_env) : 0u;
                 if (pitch <= 8) {
-                    UQB_LAUNCH(k_small_groups<8>, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
+                    auto k_small_groups_8 = k_small_groups<8, 1>;
+                    UQB_LAUNCH(k_small_groups_8, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, la, d_large);
                 } else if (pitch <= 16) {
-                    UQB_LAUNCH(k_small_groups<16>, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
-                } else {
-                    auto k_small_groups_32 = k_small_groups<32>;
+                    auto k_small_groups_16 = k_small_groups<16, 1>;
+                    UQB_LAUNCH(k_small_groups_16, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, la, d_large);
+                } else if (pitch <= 32) {
+                    auto k_small_groups_32 = k_small_groups<32, 1>;
                     UQB_CUDA(cudaFuncSetAttribute(k_small_groups_32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    UQB_LAUNCH(k_small_groups_32, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
+                    UQB_LAUNCH(k_small_groups_32, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, la, d_large);
+                } else {
+                    auto k_small_groups_64 = k_small_groups<32, 2>;
+                    UQB_CUDA(cudaFuncSetAttribute(k_small_groups_64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    UQB_LAUNCH(k_small_groups_64, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, la, d_large);
                 }
             } else {
                 UQB_LAUNCH(k_small_groups_gmem, sg_grid, ST, 0, rows, width, off, perm, head, done, headpos, d_tot, d_large);
