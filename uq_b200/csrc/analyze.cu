@@ -359,27 +359,51 @@ __global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __re
     if (tid < (unsigned)nslots && S->last_mis[tid]) atomicMax(&s->last_count_mismatch[S->slot_char[tid]], (long long)S->last_mis[tid] - 1);
 }
 
-// base / quality histograms from record tiles.  Private packed 8-bit counters per thread (word w of a
-// thread holds the counters of byte values 32+4w .. 32+4w+3; layout [word][thread] is bank-conflict
-// free), updated branch-free: values outside 32..127 are clamped to a dummy counter that the host
-// reads as "fall back to the generic kernels", inactive lanes to a second dummy.  The counters are
-// flushed every 254 warp iterations through a warp-shuffle reduction (pt_flush).
-#define PT_THREADS 256
+// base / quality histograms from record tiles (one warp per record, lane = position mod 32).
+//
+// Qualities: private packed 8-bit counters per thread in shared memory ([word][thread] layout, bank-conflict
+// free), addressed through a LUT that puts neighbouring byte values into different words, flushed through a
+// warp-shuffle reduction before a counter can wrap (pt_flush).  Bytes outside 32..127 go to a dummy counter
+// that the host reads as "use the generic kernels".
+//
+// Bases: a thread sees very few distinct base bytes, so its counters stay in REGISTERS: the LUT maps a byte to
+// a group of eight byte values (A C G T N U . - share one group) and to its 8-bit field in a 64-bit pending
+// counter; only when a thread meets a byte of another group (or the fields could wrap) are the pending counts
+// added to the CTA histogram.  The common case costs a LUT load, a compare and two adds per base.
+//
+// "Does this base always carry one single quality?" (the N-trick): state[b] = -1 unseen, 0..255 its only quality
+// so far, 256 several.  A base whose state is not yet 256 carries a CHECK bit in its LUT group, which never
+// equals the current group, so exactly those bases take the slow path that compares the quality.
+#define PT_THREADS 512
 #define PT_WORDS 25
 #define PT_LO 32u
-#define PT_OOR 96u           // clamped index of out-of-range bytes  -> histogram slot 128
-#define PT_IDLE 97u          // index used by inactive lanes          -> histogram slot 129
+#define PT_OOR 96u           // clamped index of out-of-range quality bytes -> histogram slot 128
+#define PT_ROW (PT_THREADS * 4)
+#define PT_GROUPS 35         // base groups: 1, 2 special, 3 + (v >> 3) generic
+#define PT_CHECK 0x80000000u
 
 struct pt_smem {
     tile_smem T;
-    unsigned priv_b[PT_WORDS * PT_THREADS];
     unsigned priv_q[PT_WORDS * PT_THREADS];
-    unsigned hist_b[PT_LO + 4 * PT_WORDS], hist_q[PT_LO + 4 * PT_WORDS];
+    unsigned hist_b[256], hist_q[PT_LO + 4 * PT_WORDS];
     int state[256];                 // per base byte: -1 unseen, 0..255 its only quality so far, 256 = several
-    uint2 lut[257];                 // byte value (256 = inactive lane) -> {byte offset of its counter word row, increment}
+    uint2 lutb[256];                // base byte -> {group | PT_CHECK, PRMT selectors of its field: low / high half}
+    unsigned lutq[256];             // quality byte -> (byte offset of its counter word row) << 16 | PRMT selector
+    uint8_t rev[PT_GROUPS * 8];     // (group, field) -> base byte
 };
 
-// Flush of the private counters of one warp: the four 8-bit fields of a word are widened to two words
+__device__ __forceinline__ void pt_base_group(unsigned v, unsigned* grp, unsigned* field) {
+    const char* g1 = "ACGTNU.-";
+    const char* g2 = "acgtnu*X";
+    *grp = 3u + (v >> 3); *field = v & 7u;
+#pragma unroll
+    for (unsigned f = 0; f < 8; f++) {
+        if (v == (unsigned)(unsigned char)g1[f]) { *grp = 1u; *field = f; }
+        if (v == (unsigned)(unsigned char)g2[f]) { *grp = 2u; *field = f; }
+    }
+}
+
+// Flush of the private quality counters of one warp: the four 8-bit fields of a word are widened to two words
 // of two 16-bit fields (32 lanes x 255 < 65536), summed across the warp with shuffles, and lane 0 adds
 // the four sums to the CTA histogram.  Must be called by all 32 lanes.
 __device__ __forceinline__ void pt_flush(unsigned* priv, unsigned* blk_hist, unsigned tid) {
@@ -396,7 +420,7 @@ __device__ __forceinline__ void pt_flush(unsigned* priv, unsigned* blk_hist, uns
                 o += __shfl_xor_sync(0xffffffffu, o, sh);
             }
             if (lane == 0) {
-                // counter (word w, field f) belongs to byte value 32 + f*24 + w (w < 24); word 24 holds the two dummies
+                // counter (word w, field f) belongs to byte value 32 + f*24 + w (w < 24); word 24 holds the dummy
                 const unsigned i0 = w < 24 ? PT_LO + w : PT_LO + 96u, st = w < 24 ? 24u : 1u;
                 if (e & 0xFFFFu) atomicAdd(&blk_hist[i0], e & 0xFFFFu);
                 if (o & 0xFFFFu) atomicAdd(&blk_hist[i0 + st], o & 0xFFFFu);
@@ -407,31 +431,98 @@ __device__ __forceinline__ void pt_flush(unsigned* priv, unsigned* blk_hist, uns
     }
 }
 
-__global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
+// pending base counters of one thread -> CTA histogram
+__device__ __forceinline__ void pt_base_flush(pt_smem* S, unsigned cur, unsigned& pa, unsigned& pb) {
+    if (cur < PT_GROUPS) {
+#pragma unroll
+        for (unsigned f = 0; f < 4; f++) {
+            const unsigned ca = (pa >> (8 * f)) & 255u, cb = (pb >> (8 * f)) & 255u;
+            if (ca) atomicAdd(&S->hist_b[S->rev[cur * 8 + f]], ca);
+            if (cb) atomicAdd(&S->hist_b[S->rev[cur * 8 + 4 + f]], cb);
+        }
+    }
+    pa = 0; pb = 0;
+}
+
+// the same for a whole warp (all 32 lanes call it): one shuffle reduction when every lane is in the same group
+__device__ __forceinline__ void pt_base_flush_warp(pt_smem* S, unsigned cur, unsigned& pa, unsigned& pb, unsigned lane) {
+    const unsigned cur0 = __shfl_sync(0xffffffffu, cur, 0);
+    if (__all_sync(0xffffffffu, cur == cur0)) {
+        if (cur0 < PT_GROUPS) {
+            unsigned v[4] = {pa & 0x00FF00FFu, (pa >> 8) & 0x00FF00FFu, pb & 0x00FF00FFu, (pb >> 8) & 0x00FF00FFu};
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) v[k] += __shfl_xor_sync(0xffffffffu, v[k], sh);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (unsigned k = 0; k < 4; k++) {           // v[k]: fields (k&1) and (k&1)+2 of half k>>1
+                    const unsigned f0 = (k >> 1) * 4 + (k & 1u);
+                    if (v[k] & 0xFFFFu) atomicAdd(&S->hist_b[S->rev[cur0 * 8 + f0]], v[k] & 0xFFFFu);
+                    if (v[k] >> 16) atomicAdd(&S->hist_b[S->rev[cur0 * 8 + f0 + 2]], v[k] >> 16);
+                }
+            }
+        }
+        pa = 0; pb = 0;
+    } else {
+        pt_base_flush(S, cur, pa, pb);
+    }
+}
+
+// slow path of one base: single-quality state, change of the pending group
+__device__ __forceinline__ void pt_base_slow(pt_smem* S, unsigned b, unsigned q, uint2 e, unsigned& cur, unsigned& pa, unsigned& pb) {
+    const unsigned grp = e.x & ~PT_CHECK;
+    if (e.x & PT_CHECK) {
+        int f = S->state[b];
+        if (f != 256 && f != (int)q) {
+            if (f < 0) {
+                const int old = atomicCAS(&S->state[b], -1, (int)q);
+                if (old >= 0 && old != (int)q) { S->state[b] = 256; f = 256; }
+            } else {
+                S->state[b] = 256; f = 256;
+            }
+        }
+        if (f == 256) S->lutb[b].x = grp;                       // several qualities: no more checks for this base
+    }
+    if (grp != cur) {
+        pt_base_flush(S, cur, pa, pb);
+        cur = grp;
+    }
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 2) k_pair_hist_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
                                                                const uint64_t* __restrict__ line_off, uint64_t r_begin, uint64_t n_reads,
                                                                an_dev* __restrict__ s, unsigned int* __restrict__ fallback) {
     extern __shared__ __align__(128) uint8_t pt_raw[];
     pt_smem* S = reinterpret_cast<pt_smem*>(pt_raw);
     const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    for (unsigned i = tid; i < PT_WORDS * PT_THREADS; i += PT_THREADS) { S->priv_b[i] = 0; S->priv_q[i] = 0; }
-    for (unsigned i = tid; i < PT_LO + 4 * PT_WORDS; i += PT_THREADS) { S->hist_b[i] = 0; S->hist_q[i] = 0; }
-    S->state[tid] = -1;
-    for (unsigned v = tid; v < 257; v += PT_THREADS) {
-        const unsigned idx = v == 256 ? PT_IDLE : min(v - PT_LO, PT_OOR);      // clamp: out of range -> slot 96, inactive -> 97
-        // neighbouring byte values go to DIFFERENT counter words (word = idx % 24, field = idx / 24): a thread that
-        // sees A,C,A,C... or two adjacent qualities does not read a word it has just stored (no store forwarding)
-        const unsigned word = idx < 96u ? idx % 24u : 24u, field = idx < 96u ? idx / 24u : idx - 96u;
-        S->lut[v] = make_uint2(word << 10, 1u << (field << 3));
+    for (unsigned i = tid; i < PT_WORDS * PT_THREADS; i += PT_THREADS) S->priv_q[i] = 0;
+    for (unsigned i = tid; i < PT_LO + 4 * PT_WORDS; i += PT_THREADS) S->hist_q[i] = 0;
+    for (unsigned i = tid; i < PT_GROUPS * 8; i += PT_THREADS) S->rev[i] = 0;
+    if (tid < 256) { S->hist_b[tid] = 0; S->state[tid] = -1; }
+    __syncthreads();
+    if (tid < 256) {
+        const unsigned v = tid;
+        unsigned grp, field;
+        pt_base_group(v, &grp, &field);
+        const unsigned sel = 0x1111u ^ (1u << (4u * (field & 3u)));          // PRMT(1, 0, sel): byte (field & 3) = 1
+        S->lutb[v] = make_uint2(grp | PT_CHECK, field < 4 ? (sel | 0x11110000u) : (0x1111u | (sel << 16)));
+        S->rev[grp * 8 + field] = (uint8_t)v;
+        // qualities: neighbouring byte values go to DIFFERENT counter words (word = idx % 24, field = idx / 24): a
+        // thread that meets two adjacent qualities in a row does not read a word it has just stored
+        const unsigned idx = min(v - PT_LO, PT_OOR);                          // out of range -> slot 96
+        const unsigned word = idx < 96u ? idx % 24u : 24u, qf = idx < 96u ? idx / 24u : 0u;
+        S->lutq[v] = ((word * PT_ROW) << 16) | (0x1111u ^ (1u << (4u * qf)));
     }
     tile_init(&S->T);
     __syncthreads();
-    unsigned* const pb = S->priv_b + tid;
-    unsigned* const pq = S->priv_q + tid;
-    const uint32_t bytes_a = smem_u32(S->T.bytes), pb_a = smem_u32(pb), pq_a = smem_u32(pq), state_a = smem_u32(S->state);
-    const uint32_t lut_a = smem_u32(S->lut);
-    static_assert(PT_THREADS == 256, "private counter rows are 1024 bytes apart");
+    const uint32_t bytes_a = smem_u32(S->T.bytes), pq_a = smem_u32(S->priv_q + tid);
+    const uint32_t lutb_a = smem_u32(S->lutb), lutq_a = smem_u32(S->lutq);
+    static_assert(PT_WORDS * PT_ROW < 65536, "counter row offsets must fit 16 bits");
     const uint64_t ntiles = (n_reads - r_begin + TL_R - 1) / TL_R;
     unsigned phase = 0, since_flush = 0;
+    unsigned cur = 0xffffu, pa = 0, pb = 0;                  // pending base group (none yet) and its 8 counters
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint64_t r0 = r_begin + t * TL_R, r1 = (r0 + TL_R < n_reads) ? r0 + TL_R : n_reads;
         uint64_t a0;
@@ -443,78 +534,76 @@ __global__ void __launch_bounds__(PT_THREADS) k_pair_hist_tiles(const uint8_t* _
             uint32_t len = o2 - o1 - 1;
             const uint32_t qlen = o4 - o3 - 1;
             if (qlen < len) len = qlen;            // malformed records are reported by the record-stats kernel
-            const uint8_t* dna = S->T.bytes + o1 + lane;
-            const uint8_t* qual = S->T.bytes + o3 + lane;
-            const uint32_t iters = (len + 31) >> 5;
+            const uint32_t full = len >> 5, tail = len & 31u, iters = full + (tail ? 1u : 0u);
+            uint32_t dna_a = bytes_a + o1 + lane, qual_a = bytes_a + o3 + lane;
+            if (iters > 254u) {
+                // a single read longer than 254*32 bases (only when the rest of the tile is tiny): plain shared atomics
+                pt_base_flush_warp(S, cur, pa, pb, lane);
+                for (uint32_t p = lane; p < len; p += 32) {
+                    const unsigned b = lds_u8(dna_a + (p - lane)), q = lds_u8(qual_a + (p - lane));
+                    atomicAdd(&S->hist_b[b], 1u);
+                    atomicAdd(&S->hist_q[q - PT_LO < 96u ? q : PT_LO + PT_OOR], 1u);
+                    const uint2 e = S->lutb[b];
+                    if (e.x & PT_CHECK) { unsigned c2 = 0xffffu, x = 0, y = 0; pt_base_slow(S, b, q, e, c2, x, y); }
+                }
+                continue;
+            }
             if (since_flush + iters > 254u) {      // warp-uniform; a counter is bumped at most once per iteration
-                pt_flush(S->priv_b, S->hist_b, tid);
                 pt_flush(S->priv_q, S->hist_q, tid);
+                pt_base_flush_warp(S, cur, pa, pb, lane);
                 since_flush = 0;
             }
             since_flush += iters;
-            if (iters > 254u) {                    // a single read longer than 254*32 bases: flush inside the loop
-                for (uint32_t it = 0; it < iters; it++) {
-                    const uint32_t p = it * 32 + lane;
-                    if ((it & 127u) == 127u) { pt_flush(S->priv_b, S->hist_b, tid); pt_flush(S->priv_q, S->hist_q, tid); }
-                    if (p < len) {
-                        const unsigned b = dna[it * 32], q = qual[it * 32];
-                        const uint2 eb = S->lut[b], eq = S->lut[q];
-                        pb[eb.x >> 2] += eb.y;                  // eb.x is a byte offset of the [word][thread] row
-                        pq[eq.x >> 2] += eq.y;
-                        const int f = S->state[b];
-                        if (f != 256 && f != (int)q) {
-                            if (f < 0) { const int old = atomicCAS(&S->state[b], -1, (int)q); if (old >= 0 && old != (int)q) S->state[b] = 256; }
-                            else S->state[b] = 256;
-                        }
-                    }
+            if (full) {
+                // software pipelined: the bytes and LUT entries of chunk it+1 are fetched before the counter
+                // read-modify-write of chunk it
+                unsigned b = lds_u8(dna_a), q = lds_u8(qual_a);
+                uint2 eb = lds_u64(lutb_a + (b << 3));
+                unsigned eq = lds_u32(lutq_a + (q << 2));
+                for (uint32_t it = 0; it < full; it++) {
+                    const uint32_t step = it + 1 < full ? 32u : 0u;           // the last chunk re-reads itself (unused)
+                    const unsigned nb = lds_u8(dna_a + step), nq = lds_u8(qual_a + step);
+                    const uint32_t wq = pq_a + (eq >> 16);
+                    const uint32_t cq = lds_u32(wq);
+                    const uint2 neb = lds_u64(lutb_a + (nb << 3));
+                    const unsigned neq = lds_u32(lutq_a + (nq << 2));
+                    sts_u32(wq, cq + __byte_perm(1u, 0u, eq));
+                    if (eb.x != cur) pt_base_slow(S, b, q, eb, cur, pa, pb);
+                    pa += __byte_perm(1u, 0u, eb.y);
+                    pb += __byte_perm(1u, 0u, eb.y >> 16);
+                    dna_a += step; qual_a += step;
+                    b = nb; q = nq; eb = neb; eq = neq;
                 }
-                since_flush = 255;
-                continue;
+                dna_a += 32; qual_a += 32;
             }
-            const uint32_t dna_a = bytes_a + o1 + lane, qual_a = bytes_a + o3 + lane;
-            // software pipelined: the bytes and LUT entries of iteration it+1 are fetched before the counter
-            // read-modify-writes of iteration it, and the two RMWs issue their loads back to back
-            bool act = lane < len;
-            unsigned b = act ? lds_u8(dna_a) : 256u, q = act ? lds_u8(qual_a) : 256u;
-            uint2 eb = lds_u64(lut_a + (b << 3)), eq = lds_u64(lut_a + (q << 3));
-            for (uint32_t it = 0; it < iters; it++) {
-                const bool nact = (it + 1) * 32 + lane < len;
-                const unsigned nb = nact ? lds_u8(dna_a + (it + 1) * 32) : 256u;
-                const unsigned nq = nact ? lds_u8(qual_a + (it + 1) * 32) : 256u;
-                const uint32_t wb = pb_a + eb.x, wq = pq_a + eq.x;                               // [word][thread], 256 threads * 4 B
-                const uint32_t cb = lds_u32(wb), cq = lds_u32(wq);
-                const int f = (int)lds_u32(state_a + ((b & 255u) << 2));
-                const uint2 neb = lds_u64(lut_a + (nb << 3)), neq = lds_u64(lut_a + (nq << 3));
-                sts_u32(wb, cb + eb.y);
-                sts_u32(wq, cq + eq.y);
-                if (act && f != 256 && f != (int)q) {
-                    if (f < 0) {
-                        const int old = atomicCAS(&S->state[b], -1, (int)q);
-                        if (old >= 0 && old != (int)q) S->state[b] = 256;
-                    } else {
-                        S->state[b] = 256;
-                    }
-                }
-                act = nact; b = nb; q = nq; eb = neb; eq = neq;
+            if (lane < tail) {
+                const unsigned b = lds_u8(dna_a), q = lds_u8(qual_a);
+                const uint2 eb = lds_u64(lutb_a + (b << 3));
+                const unsigned eq = lds_u32(lutq_a + (q << 2));
+                const uint32_t wq = pq_a + (eq >> 16);
+                sts_u32(wq, lds_u32(wq) + __byte_perm(1u, 0u, eq));
+                if (eb.x != cur) pt_base_slow(S, b, q, eb, cur, pa, pb);
+                pa += __byte_perm(1u, 0u, eb.y);
+                pb += __byte_perm(1u, 0u, eb.y >> 16);
             }
         }
     }
-    pt_flush(S->priv_b, S->hist_b, tid);
     pt_flush(S->priv_q, S->hist_q, tid);
+    pt_base_flush(S, cur, pa, pb);
     __syncthreads();
-    if (tid < 128) {
+    if (tid < 256) {
         if (S->hist_b[tid]) atomicAdd(&s->base_count[tid], (unsigned long long)S->hist_b[tid]);
-        if (S->hist_q[tid]) atomicAdd(&s->qual_count[tid], (unsigned long long)S->hist_q[tid]);
-    }
-    if (tid == 0 && (S->hist_b[PT_LO + PT_OOR] | S->hist_q[PT_LO + PT_OOR])) atomicOr(fallback, 1u);
-    const int f = S->state[tid];
-    if (f >= 0) {
-        if (f == 256) {
-            s->multi[tid] = 1;
-            atomicCAS(&s->first_q[tid], -1, 0);                 // mark the base as present
-        } else {
-            const int old = atomicCAS(&s->first_q[tid], -1, f);
-            if (old >= 0 && old != f) s->multi[tid] = 1;
+        if (tid < 128 && S->hist_q[tid]) atomicAdd(&s->qual_count[tid], (unsigned long long)S->hist_q[tid]);
+        if (tid == 0 && S->hist_q[PT_LO + PT_OOR]) atomicOr(fallback, 1u);
+        const int f = S->state[tid];
+        if (f >= 0) {
+            if (f == 256) {
+                s->multi[tid] = 1;
+                atomicCAS(&s->first_q[tid], -1, 0);                 // mark the base as present
+            } else {
+                const int old = atomicCAS(&s->first_q[tid], -1, f);
+                if (old >= 0 && old != f) s->multi[tid] = 1;
+            }
         }
     }
 }
