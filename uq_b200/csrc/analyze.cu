@@ -367,9 +367,10 @@ __global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __re
 // that the host reads as "use the generic kernels".
 //
 // Bases: a thread sees very few distinct base bytes, so its counters stay in REGISTERS: the LUT maps a byte to
-// a group of eight byte values (A C G T N U . - share one group) and to its 8-bit field in a 64-bit pending
-// counter; only when a thread meets a byte of another group (or the fields could wrap) are the pending counts
-// added to the CTA histogram.  The common case costs a LUT load, a compare and two adds per base.
+// a group of seven byte values (A C G T N U . share one group) and to the increment of its 8-bit field in a
+// 56-bit pending counter (two registers; the top byte of the second one carries the group id in the LUT and is
+// ignored in the counter); only when a thread meets a byte of another group (or the fields could wrap) are the
+// pending counts added to the CTA histogram.  The common case costs a LUT load, a compare and two adds per base.
 //
 // "Does this base always carry one single quality?" (the N-trick): state[b] = -1 unseen, 0..255 its only quality
 // so far, 256 several.  A base whose state is not yet 256 carries a CHECK bit in its LUT group, which never
@@ -379,25 +380,28 @@ __global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __re
 #define PT_LO 32u
 #define PT_OOR 96u           // clamped index of out-of-range quality bytes -> histogram slot 128
 #define PT_ROW (PT_THREADS * 4)
-#define PT_GROUPS 35         // base groups: 1, 2 special, 3 + (v >> 3) generic
+#define PT_GROUPS 40         // base groups: 1, 2 special, 3 + v / 7 generic
 #define PT_CHECK 0x80000000u
+#define PT_GMASK 0xff000000u
+#define PT_NONE 0x7f000000u  // "no pending group yet"
+#define PT_UN 4              // chunks of 32 positions per unrolled step
 
 struct pt_smem {
     tile_smem T;
     unsigned priv_q[PT_WORDS * PT_THREADS];
     unsigned hist_b[256], hist_q[PT_LO + 4 * PT_WORDS];
     int state[256];                 // per base byte: -1 unseen, 0..255 its only quality so far, 256 = several
-    uint2 lutb[256];                // base byte -> {group | PT_CHECK, PRMT selectors of its field: low / high half}
-    unsigned lutq[256];             // quality byte -> (byte offset of its counter word row) << 16 | PRMT selector
+    uint2 lutb[256];                // base byte -> {increment of fields 0-3, (group | CHECK) << 24 | increment of fields 4-6}
+    uint2 lutq[256];                // quality byte -> {byte offset of its counter word row, increment}
     uint8_t rev[PT_GROUPS * 8];     // (group, field) -> base byte
 };
 
 __device__ __forceinline__ void pt_base_group(unsigned v, unsigned* grp, unsigned* field) {
-    const char* g1 = "ACGTNU.-";
-    const char* g2 = "acgtnu*X";
-    *grp = 3u + (v >> 3); *field = v & 7u;
+    const char* g1 = "ACGTNU.";
+    const char* g2 = "acgtnu-";
+    *grp = 3u + v / 7u; *field = v % 7u;
 #pragma unroll
-    for (unsigned f = 0; f < 8; f++) {
+    for (unsigned f = 0; f < 7; f++) {
         if (v == (unsigned)(unsigned char)g1[f]) { *grp = 1u; *field = f; }
         if (v == (unsigned)(unsigned char)g2[f]) { *grp = 2u; *field = f; }
     }
@@ -431,25 +435,29 @@ __device__ __forceinline__ void pt_flush(unsigned* priv, unsigned* blk_hist, uns
     }
 }
 
-// pending base counters of one thread -> CTA histogram
-__device__ __forceinline__ void pt_base_flush(pt_smem* S, unsigned cur, unsigned& pa, unsigned& pb) {
-    if (cur < PT_GROUPS) {
+// pending base counters of one thread -> CTA histogram (cur = group << 24)
+__device__ __noinline__ void pt_base_flush(pt_smem* S, unsigned cur, unsigned pa, unsigned pb) {
+    const unsigned g = cur >> 24;
+    if (g >= PT_GROUPS) return;
 #pragma unroll
-        for (unsigned f = 0; f < 4; f++) {
-            const unsigned ca = (pa >> (8 * f)) & 255u, cb = (pb >> (8 * f)) & 255u;
-            if (ca) atomicAdd(&S->hist_b[S->rev[cur * 8 + f]], ca);
-            if (cb) atomicAdd(&S->hist_b[S->rev[cur * 8 + 4 + f]], cb);
-        }
+    for (unsigned f = 0; f < 4; f++) {
+        const unsigned ca = (pa >> (8 * f)) & 255u;
+        if (ca) atomicAdd(&S->hist_b[S->rev[g * 8 + f]], ca);
     }
-    pa = 0; pb = 0;
+#pragma unroll
+    for (unsigned f = 0; f < 3; f++) {
+        const unsigned cb = (pb >> (8 * f)) & 255u;
+        if (cb) atomicAdd(&S->hist_b[S->rev[g * 8 + 4 + f]], cb);
+    }
 }
 
 // the same for a whole warp (all 32 lanes call it): one shuffle reduction when every lane is in the same group
 __device__ __forceinline__ void pt_base_flush_warp(pt_smem* S, unsigned cur, unsigned& pa, unsigned& pb, unsigned lane) {
     const unsigned cur0 = __shfl_sync(0xffffffffu, cur, 0);
     if (__all_sync(0xffffffffu, cur == cur0)) {
-        if (cur0 < PT_GROUPS) {
-            unsigned v[4] = {pa & 0x00FF00FFu, (pa >> 8) & 0x00FF00FFu, pb & 0x00FF00FFu, (pb >> 8) & 0x00FF00FFu};
+        const unsigned g = cur0 >> 24;
+        if (g < PT_GROUPS) {
+            unsigned v[4] = {pa & 0x00FF00FFu, (pa >> 8) & 0x00FF00FFu, pb & 0x00FF00FFu, (pb >> 8) & 0x000000FFu};
 #pragma unroll
             for (int sh = 16; sh > 0; sh >>= 1) {
 #pragma unroll
@@ -459,21 +467,20 @@ __device__ __forceinline__ void pt_base_flush_warp(pt_smem* S, unsigned cur, uns
 #pragma unroll
                 for (unsigned k = 0; k < 4; k++) {           // v[k]: fields (k&1) and (k&1)+2 of half k>>1
                     const unsigned f0 = (k >> 1) * 4 + (k & 1u);
-                    if (v[k] & 0xFFFFu) atomicAdd(&S->hist_b[S->rev[cur0 * 8 + f0]], v[k] & 0xFFFFu);
-                    if (v[k] >> 16) atomicAdd(&S->hist_b[S->rev[cur0 * 8 + f0 + 2]], v[k] >> 16);
+                    if (v[k] & 0xFFFFu) atomicAdd(&S->hist_b[S->rev[g * 8 + f0]], v[k] & 0xFFFFu);
+                    if (v[k] >> 16) atomicAdd(&S->hist_b[S->rev[g * 8 + f0 + 2]], v[k] >> 16);
                 }
             }
         }
-        pa = 0; pb = 0;
     } else {
         pt_base_flush(S, cur, pa, pb);
     }
+    pa = 0; pb = 0;
 }
 
 // slow path of one base: single-quality state, change of the pending group
-__device__ __forceinline__ void pt_base_slow(pt_smem* S, unsigned b, unsigned q, uint2 e, unsigned& cur, unsigned& pa, unsigned& pb) {
-    const unsigned grp = e.x & ~PT_CHECK;
-    if (e.x & PT_CHECK) {
+__device__ __noinline__ uint3 pt_base_slow(pt_smem* S, unsigned b, unsigned q, unsigned ey, unsigned cur, unsigned pa, unsigned pb) {
+    if (ey & PT_CHECK) {
         int f = S->state[b];
         if (f != 256 && f != (int)q) {
             if (f < 0) {
@@ -483,11 +490,39 @@ __device__ __forceinline__ void pt_base_slow(pt_smem* S, unsigned b, unsigned q,
                 S->state[b] = 256; f = 256;
             }
         }
-        if (f == 256) S->lutb[b].x = grp;                       // several qualities: no more checks for this base
+        if (f == 256) S->lutb[b].y = ey & ~PT_CHECK;             // several qualities: no more checks for this base
     }
+    const unsigned grp = ey & (PT_GMASK & ~PT_CHECK);
     if (grp != cur) {
         pt_base_flush(S, cur, pa, pb);
-        cur = grp;
+        cur = grp; pa = 0; pb = 0;
+    }
+    return make_uint3(cur, pa, pb);
+}
+
+// K chunks of 32 positions of one record: lane handles positions lane + 32 k
+template <int K>
+__device__ __forceinline__ void pt_chunks(pt_smem* S, uint32_t dna_a, uint32_t qual_a, uint32_t lutb_a, uint32_t lutq_a, uint32_t pq_a,
+                                          unsigned& cur, unsigned& pa, unsigned& pb) {
+    unsigned b[K], q[K];
+    uint2 eb[K], eq[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { b[k] = lds_u8(dna_a + 32 * k); q[k] = lds_u8(qual_a + 32 * k); }
+#pragma unroll
+    for (int k = 0; k < K; k++) { eb[k] = lds_u64(lutb_a + (b[k] << 3)); eq[k] = lds_u64(lutq_a + (q[k] << 3)); }
+#pragma unroll
+    for (int k = 0; k < K; k++) {                    // same-thread shared accesses stay in program order
+        const uint32_t wq = pq_a + eq[k].x;
+        sts_u32(wq, lds_u32(wq) + eq[k].y);
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if ((eb[k].y ^ cur) & PT_GMASK) {
+            const uint3 r = pt_base_slow(S, b[k], q[k], eb[k].y, cur, pa, pb);
+            cur = r.x; pa = r.y; pb = r.z;
+        }
+        pa += eb[k].x;
+        pb += eb[k].y;                               // the top byte collects group ids and is never read
     }
 }
 
@@ -506,23 +541,21 @@ __global__ void __launch_bounds__(PT_THREADS, 2) k_pair_hist_tiles(const uint8_t
         const unsigned v = tid;
         unsigned grp, field;
         pt_base_group(v, &grp, &field);
-        const unsigned sel = 0x1111u ^ (1u << (4u * (field & 3u)));          // PRMT(1, 0, sel): byte (field & 3) = 1
-        S->lutb[v] = make_uint2(grp | PT_CHECK, field < 4 ? (sel | 0x11110000u) : (0x1111u | (sel << 16)));
+        S->lutb[v] = make_uint2(field < 4 ? 1u << (8 * field) : 0u, ((grp << 24) | PT_CHECK) | (field >= 4 ? 1u << (8 * (field - 4)) : 0u));
         S->rev[grp * 8 + field] = (uint8_t)v;
         // qualities: neighbouring byte values go to DIFFERENT counter words (word = idx % 24, field = idx / 24): a
         // thread that meets two adjacent qualities in a row does not read a word it has just stored
         const unsigned idx = min(v - PT_LO, PT_OOR);                          // out of range -> slot 96
         const unsigned word = idx < 96u ? idx % 24u : 24u, qf = idx < 96u ? idx / 24u : 0u;
-        S->lutq[v] = ((word * PT_ROW) << 16) | (0x1111u ^ (1u << (4u * qf)));
+        S->lutq[v] = make_uint2(word * PT_ROW, 1u << (8 * qf));
     }
     tile_init(&S->T);
     __syncthreads();
     const uint32_t bytes_a = smem_u32(S->T.bytes), pq_a = smem_u32(S->priv_q + tid);
     const uint32_t lutb_a = smem_u32(S->lutb), lutq_a = smem_u32(S->lutq);
-    static_assert(PT_WORDS * PT_ROW < 65536, "counter row offsets must fit 16 bits");
     const uint64_t ntiles = (n_reads - r_begin + TL_R - 1) / TL_R;
     unsigned phase = 0, since_flush = 0;
-    unsigned cur = 0xffffu, pa = 0, pb = 0;                  // pending base group (none yet) and its 8 counters
+    unsigned cur = PT_NONE, pa = 0, pb = 0;                  // pending base group (none yet) and its 7 counters
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint64_t r0 = r_begin + t * TL_R, r1 = (r0 + TL_R < n_reads) ? r0 + TL_R : n_reads;
         uint64_t a0;
@@ -543,8 +576,8 @@ __global__ void __launch_bounds__(PT_THREADS, 2) k_pair_hist_tiles(const uint8_t
                     const unsigned b = lds_u8(dna_a + (p - lane)), q = lds_u8(qual_a + (p - lane));
                     atomicAdd(&S->hist_b[b], 1u);
                     atomicAdd(&S->hist_q[q - PT_LO < 96u ? q : PT_LO + PT_OOR], 1u);
-                    const uint2 e = S->lutb[b];
-                    if (e.x & PT_CHECK) { unsigned c2 = 0xffffu, x = 0, y = 0; pt_base_slow(S, b, q, e, c2, x, y); }
+                    const unsigned ey = S->lutb[b].y;
+                    if (ey & PT_CHECK) pt_base_slow(S, b, q, ey, ey & (PT_GMASK & ~PT_CHECK), 0u, 0u);
                 }
                 continue;
             }
@@ -554,38 +587,16 @@ __global__ void __launch_bounds__(PT_THREADS, 2) k_pair_hist_tiles(const uint8_t
                 since_flush = 0;
             }
             since_flush += iters;
-            if (full) {
-                // software pipelined: the bytes and LUT entries of chunk it+1 are fetched before the counter
-                // read-modify-write of chunk it
-                unsigned b = lds_u8(dna_a), q = lds_u8(qual_a);
-                uint2 eb = lds_u64(lutb_a + (b << 3));
-                unsigned eq = lds_u32(lutq_a + (q << 2));
-                for (uint32_t it = 0; it < full; it++) {
-                    const uint32_t step = it + 1 < full ? 32u : 0u;           // the last chunk re-reads itself (unused)
-                    const unsigned nb = lds_u8(dna_a + step), nq = lds_u8(qual_a + step);
-                    const uint32_t wq = pq_a + (eq >> 16);
-                    const uint32_t cq = lds_u32(wq);
-                    const uint2 neb = lds_u64(lutb_a + (nb << 3));
-                    const unsigned neq = lds_u32(lutq_a + (nq << 2));
-                    sts_u32(wq, cq + __byte_perm(1u, 0u, eq));
-                    if (eb.x != cur) pt_base_slow(S, b, q, eb, cur, pa, pb);
-                    pa += __byte_perm(1u, 0u, eb.y);
-                    pb += __byte_perm(1u, 0u, eb.y >> 16);
-                    dna_a += step; qual_a += step;
-                    b = nb; q = nq; eb = neb; eq = neq;
-                }
+            uint32_t it = 0;
+            for (; it + PT_UN <= full; it += PT_UN) {
+                pt_chunks<PT_UN>(S, dna_a, qual_a, lutb_a, lutq_a, pq_a, cur, pa, pb);
+                dna_a += 32 * PT_UN; qual_a += 32 * PT_UN;
+            }
+            for (; it < full; it++) {
+                pt_chunks<1>(S, dna_a, qual_a, lutb_a, lutq_a, pq_a, cur, pa, pb);
                 dna_a += 32; qual_a += 32;
             }
-            if (lane < tail) {
-                const unsigned b = lds_u8(dna_a), q = lds_u8(qual_a);
-                const uint2 eb = lds_u64(lutb_a + (b << 3));
-                const unsigned eq = lds_u32(lutq_a + (q << 2));
-                const uint32_t wq = pq_a + (eq >> 16);
-                sts_u32(wq, lds_u32(wq) + __byte_perm(1u, 0u, eq));
-                if (eb.x != cur) pt_base_slow(S, b, q, eb, cur, pa, pb);
-                pa += __byte_perm(1u, 0u, eb.y);
-                pb += __byte_perm(1u, 0u, eb.y >> 16);
-            }
+            if (lane < tail) pt_chunks<1>(S, dna_a, qual_a, lutb_a, lutq_a, pq_a, cur, pa, pb);
         }
     }
     pt_flush(S->priv_q, S->hist_q, tid);
