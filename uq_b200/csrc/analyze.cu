@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __re
 // "Does this base always carry one single quality?" (the N-trick): state[b] = -1 unseen, 0..255 its only quality
 // so far, 256 several.  A base whose state is not yet 256 carries a CHECK bit in its LUT group, which never
 // equals the current group, so exactly those bases take the slow path that compares the quality.
-#define PT_THREADS 512
+#define PT_THREADS 1024
 #define PT_WORDS 25
 #define PT_LO 32u
 #define PT_OOR 96u           // clamped index of out-of-range quality bytes -> histogram slot 128
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __re
 #define PT_UN 4              // chunks of 32 positions per unrolled step
 
 struct pt_smem {
-    tile_smem T;
+    tile2_smem T;
     unsigned priv_q[PT_WORDS * PT_THREADS];
     unsigned hist_b[256], hist_q[PT_LO + 4 * PT_WORDS];
     int state[256];                 // per base byte: -1 unseen, 0..255 its only quality so far, 256 = several
@@ -503,7 +503,7 @@ __device__ __noinline__ uint3 pt_base_slow(pt_smem* S, unsigned b, unsigned q, u
 // K chunks of 32 positions of one record: lane handles positions lane + 32 k
 template <int K>
 __device__ __forceinline__ void pt_chunks(pt_smem* S, uint32_t dna_a, uint32_t qual_a, uint32_t lutb_a, uint32_t lutq_a, uint32_t pq_a,
-                                          unsigned& cur, unsigned& pa, unsigned& pb) {
+                                          uint32_t state_a, unsigned& cur, unsigned& pa, unsigned& pb) {
     unsigned b[K], q[K];
     uint2 eb[K], eq[K];
 #pragma unroll
@@ -517,7 +517,9 @@ __device__ __forceinline__ void pt_chunks(pt_smem* S, uint32_t dna_a, uint32_t q
     }
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        if ((eb[k].y ^ cur) & PT_GMASK) {
+        const unsigned dd = (eb[k].y ^ cur) & PT_GMASK;
+        // dd == PT_CHECK: a base of the current group that had one single quality so far - still the same one?
+        if (dd && (dd != PT_CHECK || lds_u32(state_a + (b[k] << 2)) != q[k])) {
             const uint3 r = pt_base_slow(S, b[k], q[k], eb[k].y, cur, pa, pb);
             cur = r.x; pa = r.y; pb = r.z;
         }
@@ -526,7 +528,7 @@ __device__ __forceinline__ void pt_chunks(pt_smem* S, uint32_t dna_a, uint32_t q
     }
 }
 
-__global__ void __launch_bounds__(PT_THREADS, 2) k_pair_hist_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
+__global__ void __launch_bounds__(PT_THREADS, 1) k_pair_hist_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
                                                                const uint64_t* __restrict__ line_off, uint64_t r_begin, uint64_t n_reads,
                                                                an_dev* __restrict__ s, unsigned int* __restrict__ fallback) {
     extern __shared__ __align__(128) uint8_t pt_raw[];
@@ -549,21 +551,19 @@ __global__ void __launch_bounds__(PT_THREADS, 2) k_pair_hist_tiles(const uint8_t
         const unsigned word = idx < 96u ? idx % 24u : 24u, qf = idx < 96u ? idx / 24u : 0u;
         S->lutq[v] = make_uint2(word * PT_ROW, 1u << (8 * qf));
     }
-    tile_init(&S->T);
     __syncthreads();
-    const uint32_t bytes_a = smem_u32(S->T.bytes), pq_a = smem_u32(S->priv_q + tid);
-    const uint32_t lutb_a = smem_u32(S->lutb), lutq_a = smem_u32(S->lutq);
-    const uint64_t ntiles = (n_reads - r_begin + TL_R - 1) / TL_R;
-    unsigned phase = 0, since_flush = 0;
+    const uint32_t pq_a = smem_u32(S->priv_q + tid);
+    const uint32_t lutb_a = smem_u32(S->lutb), lutq_a = smem_u32(S->lutq), state_a = smem_u32(S->state);
+    unsigned since_flush = 0;
     unsigned cur = PT_NONE, pa = 0, pb = 0;                  // pending base group (none yet) and its 7 counters
-    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const uint64_t r0 = r_begin + t * TL_R, r1 = (r0 + TL_R < n_reads) ? r0 + TL_R : n_reads;
-        uint64_t a0;
-        const uint32_t nrec = tile_load(&S->T, d, n_bytes, line_off, r0, r1, phase, &a0);
+    tile2_pipe<PT_THREADS> P;
+    for (P.begin(&S->T, d, n_bytes, line_off, r_begin, n_reads); P.valid(); P.finish()) {
+        const uint32_t nrec = P.acquire();
         if (!nrec) { if (tid == 0) atomicOr(fallback, 1u); continue; }
-        phase ^= 1u;
+        const uint32_t bytes_a = smem_u32(P.bytes());
+        const uint32_t* loff = P.loff();
         for (uint32_t i = wid; i < nrec; i += PT_THREADS / 32) {
-            const uint32_t o1 = S->T.loff[4 * i + 1], o2 = S->T.loff[4 * i + 2], o3 = S->T.loff[4 * i + 3], o4 = S->T.loff[4 * i + 4];
+            const uint32_t o1 = loff[4 * i + 1], o2 = loff[4 * i + 2], o3 = loff[4 * i + 3], o4 = loff[4 * i + 4];
             uint32_t len = o2 - o1 - 1;
             const uint32_t qlen = o4 - o3 - 1;
             if (qlen < len) len = qlen;            // malformed records are reported by the record-stats kernel
@@ -589,14 +589,14 @@ __global__ void __launch_bounds__(PT_THREADS, 2) k_pair_hist_tiles(const uint8_t
             since_flush += iters;
             uint32_t it = 0;
             for (; it + PT_UN <= full; it += PT_UN) {
-                pt_chunks<PT_UN>(S, dna_a, qual_a, lutb_a, lutq_a, pq_a, cur, pa, pb);
+                pt_chunks<PT_UN>(S, dna_a, qual_a, lutb_a, lutq_a, pq_a, state_a, cur, pa, pb);
                 dna_a += 32 * PT_UN; qual_a += 32 * PT_UN;
             }
             for (; it < full; it++) {
-                pt_chunks<1>(S, dna_a, qual_a, lutb_a, lutq_a, pq_a, cur, pa, pb);
+                pt_chunks<1>(S, dna_a, qual_a, lutb_a, lutq_a, pq_a, state_a, cur, pa, pb);
                 dna_a += 32; qual_a += 32;
             }
-            if (lane < tail) pt_chunks<1>(S, dna_a, qual_a, lutb_a, lutq_a, pq_a, cur, pa, pb);
+            if (lane < tail) pt_chunks<1>(S, dna_a, qual_a, lutb_a, lutq_a, pq_a, state_a, cur, pa, pb);
         }
     }
     pt_flush(S->priv_q, S->hist_q, tid);
@@ -626,7 +626,8 @@ static int stats_tiles_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsig
     UQB_CUDA(cudaFuncSetAttribute(k_record_stats_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rs_smem)));
     UQB_CUDA(cudaFuncSetAttribute(k_pair_hist_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pt_smem)));
     const unsigned g1 = (unsigned)(ntiles < (uint64_t)ctx->sm_count * 3 ? ntiles : (uint64_t)ctx->sm_count * 3);
-    const unsigned g2 = (unsigned)(ntiles < (uint64_t)ctx->sm_count * 2 ? ntiles : (uint64_t)ctx->sm_count * 2);
+    const unsigned g2 = (unsigned)(ntiles < (uint64_t)ctx->sm_count ? ntiles : (uint64_t)ctx->sm_count);      // one 1024-thread CTA per SM
+    static_assert(sizeof(pt_smem) <= 227 * 1024, "pair histogram shared memory");
     const uint64_t ab = (uint64_t)((double)fq->n * (double)(r1 - r0) / (double)(fq->n_reads ? fq->n_reads : 1)) + 32 * (r1 - r0);
     UQB_LAUNCH_B(ab, k_record_stats_tiles, g1, TL_R, sizeof(rs_smem), fq->d, fq->n, fq->line_off, r0, r1,
                  fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb);
