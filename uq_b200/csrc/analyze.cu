@@ -219,97 +219,112 @@ __global__ void __launch_bounds__(PH_THREADS) k_pair_hist(const uint8_t* __restr
 // ================================================================================================
 #define RS_SLOTS 64
 
-struct rs_smem {
-    tile_smem T;
+// ---- record statistics, names only ----------------------------------------------------------------
+// The per-record statistics need the line offsets, the QNAME line and the first byte of line 3 - not the
+// bases and qualities - so this kernel does not stage whole records: one thread per record reads its
+// name in aligned 8-byte words (about 100 of the 340 bytes of a record cross the memory system: its
+// offsets, the sectors of the name and of the '+').  Per name byte: one compare with line 1 (while the
+// common prefix still runs) and one read-modify-write of a private packed 8-bit counter in shared
+// memory ([word][thread] layout, conflict free; the LUT gives word and increment, bytes that do not
+// occur in line 1 add zero).  Needs <= 64 distinct bytes in line 1 and names of <= 255 bytes, else
+// `fallback` is raised and the host uses the generic kernel.
+#define RD_THREADS 256
+#define RD_WORDS (RS_SLOTS / 4)
+
+struct rd_smem {
     uint8_t first[UQB_HDR_MAX];
     uint8_t slot_of[256];
     uint8_t slot_char[RS_SLOTS];
-    unsigned long long first_packed[RS_SLOTS / 8];
+    uint32_t lut[256];                  // byte -> (byte offset of its counter word row) << 16 | PRMT selector of its field
+    uint32_t first_words[RD_WORDS];     // packed counts of line 1
+    uint32_t cnt[RD_WORDS * RD_THREADS];
     uint32_t lcp_first[UQB_HDR_MAX + 1], lcs_first[UQB_HDR_MAX + 1], sp_first[UQB_HDR_MAX + 1], ss_first[UQB_HDR_MAX + 1];
-    uint32_t last_mis[RS_SLOTS];          // record index + 1 of the last mismatch, 0 = none
+    uint32_t last_mis[RS_SLOTS];        // record index + 1 of the last mismatch, 0 = none
     int nslots;
 };
 
-__global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
-                                                            const uint64_t* __restrict__ line_off, uint64_t r_begin, uint64_t n_reads,
-                                                            const uint8_t* __restrict__ ref, uint64_t rbase,
-                                                            uint32_t first_len, an_dev* __restrict__ s, unsigned int* __restrict__ fallback) {
-    extern __shared__ __align__(128) uint8_t rs_raw[];
-    rs_smem* S = reinterpret_cast<rs_smem*>(rs_raw);
+__global__ void __launch_bounds__(RD_THREADS) k_record_stats_names(const uint8_t* __restrict__ d, const uint64_t* __restrict__ line_off,
+                                                                  uint64_t r_begin, uint64_t n_reads, const uint8_t* __restrict__ ref,
+                                                                  uint64_t rbase, uint32_t first_len, an_dev* __restrict__ s,
+                                                                  unsigned int* __restrict__ fallback) {
+    extern __shared__ __align__(16) uint8_t rd_raw[];
+    rd_smem* S = reinterpret_cast<rd_smem*>(rd_raw);
     const unsigned tid = threadIdx.x, lane = tid & 31u;
-    for (unsigned i = tid; i < first_len; i += TL_R) S->first[i] = ref[i];
-    for (unsigned i = tid; i < 256; i += TL_R) S->slot_of[i] = 255;
-    for (unsigned i = tid; i <= UQB_HDR_MAX; i += TL_R) { S->lcp_first[i] = S->lcs_first[i] = S->sp_first[i] = S->ss_first[i] = 0xFFFFFFFFu; }
+    for (unsigned i = tid; i < first_len && i < UQB_HDR_MAX; i += RD_THREADS) S->first[i] = ref[i];
+    S->slot_of[tid] = 255;
+    S->lut[tid] = 0x1111u;                                   // word 0, increment 0
+    for (unsigned i = tid; i <= UQB_HDR_MAX; i += RD_THREADS) { S->lcp_first[i] = S->lcs_first[i] = S->sp_first[i] = S->ss_first[i] = 0xFFFFFFFFu; }
     if (tid < RS_SLOTS) S->last_mis[tid] = 0;
-    if (tid < RS_SLOTS / 8) S->first_packed[tid] = 0;
-    tile_init(&S->T);
+    if (tid < RD_WORDS) S->first_words[tid] = 0;
+    for (unsigned i = tid; i < RD_WORDS * RD_THREADS; i += RD_THREADS) S->cnt[i] = 0;
     __syncthreads();
     if (tid == 0) {
         int ns = 0;
         bool over = false;
-        for (unsigned i = 0; i < first_len; i++) {
+        for (unsigned i = 0; i < first_len && i < UQB_HDR_MAX; i++) {
             const uint8_t c = S->first[i];
             if (S->slot_of[c] == 255) {
-                if (ns < RS_SLOTS) { S->slot_of[c] = (uint8_t)ns; S->slot_char[ns] = c; ns++; } else over = true;
+                if (ns < RS_SLOTS) {
+                    S->slot_of[c] = (uint8_t)ns; S->slot_char[ns] = c;
+                    S->lut[c] = (((unsigned)(ns >> 2) * RD_THREADS * 4u) << 16) | (0x1111u ^ (1u << (4u * (ns & 3))));
+                    ns++;
+                } else over = true;
             }
             const uint8_t sl = S->slot_of[c];
-            if (sl != 255) S->first_packed[sl >> 3] += 1ull << ((sl & 7) * 8);
+            if (sl != 255) S->first_words[sl >> 2] += 1u << ((sl & 3) * 8);
         }
         if (over || first_len > 255) atomicOr(fallback, 1u);
         S->nslots = ns;
     }
     __syncthreads();
     const int nslots = S->nslots;
-    unsigned long long fp[RS_SLOTS / 8];
-#pragma unroll
-    for (int k = 0; k < RS_SLOTS / 8; k++) fp[k] = S->first_packed[k];
+    const int nwords = (nslots + 3) >> 2;
+    const uint32_t cnt_a = smem_u32(S->cnt + tid), lut_a = smem_u32(S->lut), first_a = smem_u32(S->first);
 
     unsigned long long mn = ~0ull, mx = 0ull;
     unsigned nm = 0;
     long long bad_plus = LLONG_MAX, bad_len = LLONG_MAX;
-    const uint64_t ntiles = (n_reads - r_begin + TL_R - 1) / TL_R;
-    unsigned phase = 0;
-    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const uint64_t r0 = r_begin + t * TL_R, r1 = (r0 + TL_R < n_reads) ? r0 + TL_R : n_reads;
-        uint64_t a0;
-        const uint32_t nrec = tile_load(&S->T, d, n_bytes, line_off, r0, r1, phase, &a0);
-        if (!nrec) { if (tid == 0) atomicOr(fallback, 1u); continue; }
-        phase ^= 1u;
-        const bool active = tid < nrec;
-        const uint64_t r = r0 + tid;
-        unsigned long long cnt[RS_SLOTS / 8];
-#pragma unroll
-        for (int k = 0; k < RS_SLOTS / 8; k++) cnt[k] = 0;
+    const uint64_t nblk = (n_reads - r_begin + RD_THREADS - 1) / RD_THREADS;
+    for (uint64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const uint64_t r = r_begin + blk * RD_THREADS + tid;
+        const bool active = r < n_reads;
         unsigned lcp = 0, lcs = 0, name_len = 0;
         if (active) {
-            const uint32_t o0 = S->T.loff[4 * tid], o1 = S->T.loff[4 * tid + 1], o2 = S->T.loff[4 * tid + 2];
-            const uint32_t o3 = S->T.loff[4 * tid + 3], o4 = S->T.loff[4 * tid + 4];
+            const ulonglong2 oa = __ldg(reinterpret_cast<const ulonglong2*>(line_off + 4 * r));
+            const ulonglong2 ob = __ldg(reinterpret_cast<const ulonglong2*>(line_off + 4 * r + 2));
+            const uint64_t o0 = oa.x, o1 = oa.y, o2 = ob.x, o3 = ob.y, o4 = __ldg(line_off + 4 * r + 4);
             const uint64_t dlen = o2 - o1 - 1, qlen = o4 - o3 - 1;
-            if (o3 - o2 < 2 || S->T.bytes[o2] != '+') bad_plus = bad_plus < (long long)r ? bad_plus : (long long)r;
+            if (o3 - o2 < 2 || __ldg(d + o2) != '+') bad_plus = bad_plus < (long long)r ? bad_plus : (long long)r;
             if (dlen != qlen) bad_len = bad_len < (long long)r ? bad_len : (long long)r;
             mn = dlen < mn ? dlen : mn; mx = dlen > mx ? dlen : mx;
-            const uint8_t* name = S->T.bytes + o0;
-            name_len = o1 - o0 - 1;
+            const uint64_t nl64 = o1 - o0 - 1;
+            name_len = nl64 > 0xFFFFu ? 0xFFFFu : (unsigned)nl64;
             nm = name_len > nm ? name_len : nm;
-            const unsigned lim = name_len < first_len ? name_len : first_len;
-            bool run = true;
-            for (unsigned i = 0; i < name_len; i++) {
-                const uint8_t c = name[i];
-                if (run && i < lim && c == S->first[i]) lcp = i + 1; else run = false;
-                const unsigned sl = S->slot_of[c];
-                if (sl != 255u) {
-                    const unsigned wi = sl >> 3;
-                    const unsigned long long inc = 1ull << ((sl & 7u) * 8u);
-#pragma unroll
-                    for (int k = 0; k < RS_SLOTS / 8; k++) if (wi == (unsigned)k) cnt[k] += inc;
+            if (name_len > 255) {
+                atomicOr(fallback, 1u);                      // 8-bit packed counters could wrap
+            } else {
+                const unsigned lim = name_len < first_len ? name_len : first_len;
+                const uint64_t addr = (uint64_t)(uintptr_t)d + o0;
+                const uint64_t* q = reinterpret_cast<const uint64_t*>(addr & ~7ull);
+                unsigned avail = 8u - (unsigned)(addr & 7ull);
+                uint64_t w = __ldg(q) >> ((addr & 7ull) * 8ull);
+                bool run = true;
+                for (unsigned i = 0; i < name_len; i++) {
+                    if (avail == 0) { w = __ldg(++q); avail = 8; }
+                    const unsigned c = (unsigned)w & 255u;
+                    w >>= 8; avail--;
+                    if (run) { if (i < lim && c == lds_u8(first_a + i)) lcp = i + 1; else run = false; }
+                    const uint32_t e = lds_u32(lut_a + (c << 2));
+                    const uint32_t wa = cnt_a + (e >> 16);
+                    sts_u32(wa, lds_u32(wa) + __byte_perm(1u, 0u, e));
                 }
+                const uint8_t* name = d + o0;
+                while (lcs < lim && __ldg(name + name_len - 1 - lcs) == S->first[first_len - 1 - lcs]) lcs++;
             }
-            while (lcs < lim && name[name_len - 1 - lcs] == S->first[first_len - 1 - lcs]) lcs++;
-            if (name_len > 255) atomicOr(fallback, 1u);          // 8-bit packed counters could wrap
         }
         // first record per lcp / lcs value: the lowest lane of each match group is the lowest record
         {
-            const bool part = active && r + rbase >= 1;
+            const bool part = active && name_len <= 255 && r + rbase >= 1;
             const unsigned key1 = part ? lcp : 0xFFFFu, key2 = part ? lcs : 0xFFFFu;
             const unsigned m1 = __match_any_sync(0xffffffffu, key1), m2 = __match_any_sync(0xffffffffu, key2);
             if (part && (int)lane == __ffs(m1) - 1) atomicMin(&S->lcp_first[lcp], (uint32_t)r);
@@ -318,18 +333,17 @@ __global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __re
             if (part && lcs == name_len && name_len < first_len) atomicMin(&S->ss_first[name_len], (uint32_t)r);
         }
         // last record whose count of a tracked byte differs from line 1's
-        unsigned long long diff[RS_SLOTS / 8];
-        bool anydiff = false;
+        const uint64_t rw = r_begin + blk * RD_THREADS + (tid & ~31u);            // record of lane 0
+        for (int wd = 0; wd < nwords; wd++) {
+            const uint32_t x = S->cnt[wd * RD_THREADS + tid];
+            S->cnt[wd * RD_THREADS + tid] = 0;
+            const uint32_t diff = (active && name_len <= 255) ? (x ^ S->first_words[wd]) : 0u;
+            if (__any_sync(0xffffffffu, diff != 0u)) {
 #pragma unroll
-        for (int k = 0; k < RS_SLOTS / 8; k++) { diff[k] = active ? (cnt[k] ^ fp[k]) : 0ull; anydiff |= diff[k] != 0ull; }
-        if (__any_sync(0xffffffffu, anydiff)) {
-            for (int sl = 0; sl < nslots; sl++) {
-                unsigned long long w = 0;
-#pragma unroll
-                for (int k = 0; k < RS_SLOTS / 8; k++) if ((sl >> 3) == k) w = diff[k];
-                const bool mis = ((w >> ((sl & 7) * 8)) & 0xFFull) != 0ull;
-                const unsigned m = __ballot_sync(0xffffffffu, mis);
-                if (m && lane == 0) atomicMax(&S->last_mis[sl], (uint32_t)(r0 + (tid & ~31u) + (31 - __clz(m))) + 1u);
+                for (int f = 0; f < 4; f++) {
+                    const unsigned m = __ballot_sync(0xffffffffu, ((diff >> (8 * f)) & 255u) != 0u);
+                    if (m && lane == 0) atomicMax(&S->last_mis[wd * 4 + f], (uint32_t)(rw + (31 - __clz(m))) + 1u);
+                }
             }
         }
     }
@@ -350,7 +364,7 @@ __global__ void __launch_bounds__(TL_R) k_record_stats_tiles(const uint8_t* __re
         if (bad_len != LLONG_MAX) atomicMin(&s->bad_len, bad_len);
     }
     __syncthreads();
-    for (unsigned j = tid; j <= first_len; j += TL_R) {
+    for (unsigned j = tid; j <= first_len && j <= UQB_HDR_MAX; j += RD_THREADS) {
         if (S->lcp_first[j] != 0xFFFFFFFFu) atomicMin(&s->first_lcp_eq[j], (long long)S->lcp_first[j]);
         if (S->lcs_first[j] != 0xFFFFFFFFu) atomicMin(&s->first_lcs_eq[j], (long long)S->lcs_first[j]);
         if (S->sp_first[j] != 0xFFFFFFFFu) atomicMin(&s->first_short_prefix[j], (long long)S->sp_first[j]);
@@ -623,13 +637,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_pair_hist_tiles(const uint8_t
 static int stats_tiles_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsigned int* d_fb, uint32_t flen, uint64_t r0, uint64_t r1) {
     if (r1 <= r0) return 0;
     const uint64_t ntiles = (r1 - r0 + TL_R - 1) / TL_R;
-    UQB_CUDA(cudaFuncSetAttribute(k_record_stats_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rs_smem)));
     UQB_CUDA(cudaFuncSetAttribute(k_pair_hist_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pt_smem)));
-    const unsigned g1 = (unsigned)(ntiles < (uint64_t)ctx->sm_count * 3 ? ntiles : (uint64_t)ctx->sm_count * 3);
     const unsigned g2 = (unsigned)(ntiles < (uint64_t)ctx->sm_count ? ntiles : (uint64_t)ctx->sm_count);      // one 1024-thread CTA per SM
     static_assert(sizeof(pt_smem) <= 227 * 1024, "pair histogram shared memory");
     const uint64_t ab = (uint64_t)((double)fq->n * (double)(r1 - r0) / (double)(fq->n_reads ? fq->n_reads : 1)) + 32 * (r1 - r0);
-    UQB_LAUNCH_B(ab, k_record_stats_tiles, g1, TL_R, sizeof(rs_smem), fq->d, fq->n, fq->line_off, r0, r1,
+    // names only: 32 B of offsets, the name's sectors and the '+' sector per record
+    UQB_LAUNCH_B((r1 - r0) * 128, k_record_stats_names, uqb_grid(ctx, r1 - r0, RD_THREADS, 8), RD_THREADS, sizeof(rd_smem), fq->d, fq->line_off, r0, r1,
                  fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb);
     UQB_LAUNCH_B(ab, k_pair_hist_tiles, g2, PT_THREADS, sizeof(pt_smem), fq->d, fq->n, fq->line_off, r0, r1, s, d_fb);
     return 0;
