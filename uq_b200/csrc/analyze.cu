@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(RD_THREADS) k_record_stats_names(const uint8_t
             const ulonglong2 ob = __ldg(reinterpret_cast<const ulonglong2*>(line_off + 4 * r + 2));
             const uint64_t o0 = oa.x, o1 = oa.y, o2 = ob.x, o3 = ob.y, o4 = __ldg(line_off + 4 * r + 4);
             const uint64_t dlen = o2 - o1 - 1, qlen = o4 - o3 - 1;
-            if (o3 - o2 < 2 || __ldg(d + o2) != '+') bad_plus = bad_plus < (long long)r ? bad_plus : (long long)r;
+            const unsigned plus = o3 - o2 < 2 ? 0u : (unsigned)__ldg(d + o2);           // used after the name loop
             if (dlen != qlen) bad_len = bad_len < (long long)r ? bad_len : (long long)r;
             mn = dlen < mn ? dlen : mn; mx = dlen > mx ? dlen : mx;
             const uint64_t nl64 = o1 - o0 - 1;
@@ -306,21 +306,48 @@ __global__ void __launch_bounds__(RD_THREADS) k_record_stats_names(const uint8_t
                 const unsigned lim = name_len < first_len ? name_len : first_len;
                 const uint64_t addr = (uint64_t)(uintptr_t)d + o0;
                 const uint64_t* q = reinterpret_cast<const uint64_t*>(addr & ~7ull);
-                unsigned avail = 8u - (unsigned)(addr & 7ull);
-                uint64_t w = __ldg(q) >> ((addr & 7ull) * 8ull);
+                const unsigned ph = (unsigned)(addr & 7ull);
+                // the first 64 bytes of the aligned window are fetched at once (independent loads), then consumed
+                // from registers; longer names continue word by word
+                const unsigned nw8 = (ph + name_len + 7u) >> 3;
+                uint64_t W[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) W[k] = (unsigned)k < nw8 ? __ldg(q + k) : 0ull;
                 bool run = true;
-                for (unsigned i = 0; i < name_len; i++) {
-                    if (avail == 0) { w = __ldg(++q); avail = 8; }
-                    const unsigned c = (unsigned)w & 255u;
-                    w >>= 8; avail--;
-                    if (run) { if (i < lim && c == lds_u8(first_a + i)) lcp = i + 1; else run = false; }
-                    const uint32_t e = lds_u32(lut_a + (c << 2));
-                    const uint32_t wa = cnt_a + (e >> 16);
-                    sts_u32(wa, lds_u32(wa) + __byte_perm(1u, 0u, e));
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if ((unsigned)k < nw8) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const unsigned i = (unsigned)(8 * k + j) - ph;             // wraps for window bytes before the name
+                            if (i < name_len) {
+                                const unsigned c = (unsigned)(W[k] >> (8 * j)) & 255u;
+                                if (run) { if (i < lim && c == lds_u8(first_a + i)) lcp = i + 1; else run = false; }
+                                const uint32_t e = lds_u32(lut_a + (c << 2));
+                                const uint32_t wa = cnt_a + (e >> 16);
+                                sts_u32(wa, lds_u32(wa) + __byte_perm(1u, 0u, e));
+                            }
+                        }
+                    }
+                }
+                if (nw8 > 8) {
+                    q += 8;
+                    unsigned avail = 0;
+                    uint64_t w = 0;
+                    for (unsigned i = 64u - ph; i < name_len; i++) {
+                        if (avail == 0) { w = __ldg(q++); avail = 8; }
+                        const unsigned c = (unsigned)w & 255u;
+                        w >>= 8; avail--;
+                        if (run) { if (i < lim && c == lds_u8(first_a + i)) lcp = i + 1; else run = false; }
+                        const uint32_t e = lds_u32(lut_a + (c << 2));
+                        const uint32_t wa = cnt_a + (e >> 16);
+                        sts_u32(wa, lds_u32(wa) + __byte_perm(1u, 0u, e));
+                    }
                 }
                 const uint8_t* name = d + o0;
                 while (lcs < lim && __ldg(name + name_len - 1 - lcs) == S->first[first_len - 1 - lcs]) lcs++;
             }
+            if (plus != '+') bad_plus = bad_plus < (long long)r ? bad_plus : (long long)r;
         }
         // first record per lcp / lcs value: the lowest lane of each match group is the lowest record
         {
