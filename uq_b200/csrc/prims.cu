@@ -180,41 +180,56 @@ __global__ void __launch_bounds__(PR_THREADS) k_radix_hist(const uint64_t* __res
     ghist[(uint64_t)threadIdx.x * nblk + blockIdx.x] = hist[threadIdx.x];
 }
 
-// Stable scatter.  Every warp owns 512 consecutive items of the tile and ranks them 32 at a time with
-// match_any, so the order inside a digit bucket is (CTA, warp, round, lane) = input order.  The tile is
-// then re-ordered by digit in shared memory and written out as one contiguous run per digit, which
-// turns 4096 scattered 8/4-byte stores into ~256 coalesced runs (the random-digit passes went from
-// 0.74 TB/s to the speed of the already-clustered passes).
+// Stable scatter.  512 threads take one tile of PR_TILE items; every warp owns 256 consecutive items and
+// ranks them 32 at a time with match_any, so the order inside a digit bucket is (CTA, warp, round, lane) =
+// input order.  Keys, values (and aux words) are loaded ONCE, up front, and stay in registers through the
+// ranking; the tile is then re-ordered by digit in shared memory and written out as one contiguous run per
+// digit, which turns 4096 scattered 8/4-byte stores into ~256 coalesced runs.
+#define RS_THREADS 512
+#define RS_ITEMS (PR_TILE / RS_THREADS)
+#define RS_WARPS (RS_THREADS / 32)
 struct rs_stage {
-    uint32_t whist[PR_THREADS / 32][256];     // per-warp digit counts, then per-warp exclusive prefix
+    uint32_t whist[RS_WARPS][256];            // per-warp digit counts, then per-warp exclusive prefix
     uint32_t dstart[256];                     // first tile-local slot of every digit
     uint32_t gbase[256];                      // first global slot of this CTA's run of every digit
-    uint32_t wtot[PR_THREADS / 32];
+    uint32_t wtot[8];
     uint64_t key[PR_TILE];
     uint32_t val[PR_TILE];
     uint32_t aux[PR_TILE];
 };
 
 template <bool AUXDIGIT, bool HASAUX>
-__global__ void __launch_bounds__(PR_THREADS) k_radix_scatter(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ ain,
-                                                             const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
-                                                             uint32_t* __restrict__ aout, uint32_t* __restrict__ vout, uint64_t n,
-                                                             int shift, const uint32_t* __restrict__ goff, uint32_t nblk) {
+__global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ ain,
+                                                                const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
+                                                                uint32_t* __restrict__ aout, uint32_t* __restrict__ vout, uint64_t n,
+                                                                int shift, const uint32_t* __restrict__ goff, uint32_t nblk) {
     extern __shared__ __align__(16) uint8_t rs_raw[];
     rs_stage* S = reinterpret_cast<rs_stage*>(rs_raw);
     const unsigned tid = threadIdx.x, w = tid >> 5, lane = tid & 31u;
-    for (unsigned i = tid; i < (PR_THREADS / 32) * 256; i += PR_THREADS) (&S->whist[0][0])[i] = 0;
-    __syncthreads();
     const uint64_t tile0 = (uint64_t)blockIdx.x * PR_TILE;
-    const uint64_t warp0 = tile0 + (uint64_t)w * (32 * PR_ITEMS);
+    const uint64_t warp0 = tile0 + (uint64_t)w * (32 * RS_ITEMS);
     const uint32_t ntile = (uint32_t)((n - tile0 < PR_TILE) ? (n - tile0) : PR_TILE);
-    uint32_t rk[PR_ITEMS];
+    uint64_t key[RS_ITEMS];
+    uint32_t val[RS_ITEMS], aux[RS_ITEMS];
 #pragma unroll
-    for (int j = 0; j < PR_ITEMS; j++) {
+    for (int j = 0; j < RS_ITEMS; j++) {
+        const uint64_t idx = warp0 + (uint64_t)j * 32 + lane;
+        key[j] = 0; val[j] = 0; aux[j] = 0;
+        if (idx < n) {
+            key[j] = kin[idx];
+            val[j] = vin[idx];
+            if (HASAUX) aux[j] = ain[idx];
+        }
+    }
+    for (unsigned i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&S->whist[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t rk[RS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
         const uint64_t idx = warp0 + (uint64_t)j * 32 + lane;
         const bool valid = idx < n;
         uint32_t d = 256u;    // sentinel digit for lanes beyond the end
-        if (valid) d = AUXDIGIT ? ((ain[idx] >> shift) & 255u) : (uint32_t)((kin[idx] >> shift) & 255ull);
+        if (valid) d = AUXDIGIT ? ((aux[j] >> shift) & 255u) : (uint32_t)((key[j] >> shift) & 255ull);
         const unsigned m = __match_any_sync(0xffffffffu, d);
         const unsigned r = __popc(m & ((1u << lane) - 1u));
         const int leader = __ffs(m) - 1;
@@ -224,30 +239,32 @@ __global__ void __launch_bounds__(PR_THREADS) k_radix_scatter(const uint64_t* __
             S->whist[w][d] = old + __popc(m);
         }
         old = __shfl_sync(0xffffffffu, old, leader);
-        rk[j] = (d << 16) | (old + r);     // old + r < 512
+        rk[j] = (d << 16) | (old + r);     // old + r < 256
         __syncwarp();
     }
     __syncthreads();
     // digit totals -> per-warp exclusive prefixes, tile-local digit starts (256-wide scan), global bases
-    {
-        uint32_t tot = 0;
+    uint32_t tot = 0, incl = 0;
+    if (tid < 256) {
 #pragma unroll
-        for (int w2 = 0; w2 < PR_THREADS / 32; w2++) {
+        for (int w2 = 0; w2 < RS_WARPS; w2++) {
             const uint32_t c = S->whist[w2][tid];
             S->whist[w2][tid] = tot;
             tot += c;
         }
-        uint32_t incl = tot;
+        incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= (unsigned)o) incl += t;
         }
         if (lane == 31) S->wtot[w] = incl;
-        __syncthreads();
+    }
+    __syncthreads();
+    if (tid < 256) {
         uint32_t wb = 0;
 #pragma unroll
-        for (int i = 0; i < PR_THREADS / 32; i++) if ((unsigned)i < w) wb += S->wtot[i];
+        for (int i = 0; i < 8; i++) if ((unsigned)i < w) wb += S->wtot[i];
         const uint32_t start = wb + incl - tot;
         S->dstart[tid] = start;
         S->gbase[tid] = goff[(uint64_t)tid * nblk + blockIdx.x] - start;      // global slot = gbase[d] + tile-local slot
@@ -255,24 +272,24 @@ __global__ void __launch_bounds__(PR_THREADS) k_radix_scatter(const uint64_t* __
     __syncthreads();
     // stage the tile in digit order
 #pragma unroll
-    for (int j = 0; j < PR_ITEMS; j++) {
+    for (int j = 0; j < RS_ITEMS; j++) {
         const uint64_t idx = warp0 + (uint64_t)j * 32 + lane;
         if (idx < n) {
             const uint32_t d = rk[j] >> 16;
             const uint32_t slot = S->dstart[d] + S->whist[w][d] + (rk[j] & 0xffffu);
-            S->key[slot] = kin[idx];
-            S->val[slot] = vin[idx];
-            if (HASAUX) S->aux[slot] = ain[idx];
+            S->key[slot] = key[j];
+            S->val[slot] = val[j];
+            if (HASAUX) S->aux[slot] = aux[j];
         }
     }
     __syncthreads();
     // contiguous runs out
-    for (uint32_t i = tid; i < ntile; i += PR_THREADS) {
-        const uint64_t key = S->key[i];
+    for (uint32_t i = tid; i < ntile; i += RS_THREADS) {
+        const uint64_t k = S->key[i];
         const uint32_t a = HASAUX ? S->aux[i] : 0u;
-        const uint32_t d = AUXDIGIT ? ((a >> shift) & 255u) : (uint32_t)((key >> shift) & 255ull);
+        const uint32_t d = AUXDIGIT ? ((a >> shift) & 255u) : (uint32_t)((k >> shift) & 255ull);
         const uint32_t pos = S->gbase[d] + i;
-        kout[pos] = key;
+        kout[pos] = k;
         if (HASAUX) aout[pos] = a;
         vout[pos] = S->val[i];
     }
@@ -348,9 +365,9 @@ int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux) {
         UQB_CUDA(cudaFuncSetAttribute(k_radix_scatter_aux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
         UQB_CUDA(cudaFuncSetAttribute(k_radix_scatter_key_aux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
         UQB_CUDA(cudaFuncSetAttribute(k_radix_scatter_key, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
-        if (auxd)         UQB_LAUNCH_B(n * 32, k_radix_scatter_aux, nblk, PR_THREADS, rs_smem, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
-        else if (has_aux) UQB_LAUNCH_B(n * 32, k_radix_scatter_key_aux, nblk, PR_THREADS, rs_smem, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
-        else              UQB_LAUNCH_B(n * 24, k_radix_scatter_key, nblk, PR_THREADS, rs_smem, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        if (auxd)         UQB_LAUNCH_B(n * 32, k_radix_scatter_aux, nblk, RS_THREADS, rs_smem, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        else if (has_aux) UQB_LAUNCH_B(n * 32, k_radix_scatter_key_aux, nblk, RS_THREADS, rs_smem, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        else              UQB_LAUNCH_B(n * 24, k_radix_scatter_key, nblk, RS_THREADS, rs_smem, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
         sb->cur = o;
     }
     UQB_TRY(uqb_dfree(ctx, ghist, hist_n * 4));
