@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(PKT_THREADS) k_pack_tiles(const uint8_t* __res
     tile_init(T);
     __syncthreads();
     const uint32_t pad_d = wd * 8u - L * bb, pad_q = wq * 8u - L * bq;
-    const uint32_t chunks = (L + 15) / 16;
+    const uint32_t fullc = L / 16, tailn = L % 16;
     const uint64_t ntiles = (n_reads + TL_R - 1) / TL_R;
     unsigned phase = 0;
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -186,58 +186,48 @@ __global__ void __launch_bounds__(PKT_THREADS) k_pack_tiles(const uint8_t* __res
         for (uint32_t i = tid; i < words_d; i += PKT_THREADS) stage_d[i] = 0;
         for (uint32_t i = tid; i < words_q; i += PKT_THREADS) stage_q[i] = 0;
         __syncthreads();
-        for (uint32_t item = tid; item < nrec * chunks; item += PKT_THREADS) {
-            const uint32_t i = item / chunks, c = item - i * chunks;
+        // work items: one chunk of 16 positions of one record.  All full chunks come first, then the (shorter) last
+        // chunks of the records, so that only the warps of that last group pay for masking the unused codes.
+        const uint32_t items_full = nrec * fullc, items = items_full + (tailn ? nrec : 0u);
+        for (uint32_t item = tid; item < items; item += PKT_THREADS) {
+            uint32_t i, c, nsym;
+            if (item < items_full) { i = item / fullc; c = item - i * fullc; nsym = 16; }
+            else { i = item - items_full; c = fullc; nsym = tailn; }
             const uint32_t o1 = T->loff[4 * i + 1], o2 = T->loff[4 * i + 2], o3 = T->loff[4 * i + 3];
             if (o2 - o1 - 1 != L) { atomicOr(fallback, 2u); continue; }      // not a fixed-length file after all
-            const uint8_t* dna = T->bytes + o1;
-            const uint8_t* qual = T->bytes + o3;
-            const uint32_t p0 = c * 16, p1 = (p0 + 16 < L) ? p0 + 16 : L;
-            uint32_t gd = (i * wd) * 8u + pad_d + p0 * bb;      // bit position in the tile's DNA staging area
-            uint32_t gq = (i * wq) * 8u + pad_q + p0 * bq;
-            uint32_t accd = 0, nd = 0, accq = 0, nq = 0;
-#define PKT_SYMBOL(BYTE_D, BYTE_Q)                                                              \
-            {                                                                                   \
-                const uint32_t be = lut->base[(BYTE_D)];                                        \
-                const uint32_t cd = be & 0xFFu, tq = be >> 8;                                   \
-                const uint32_t cq = tq != 0xFFu ? tq : lut->qual[(BYTE_Q)];                     \
-                if (nd + bb > 32u) { or_bits(stage_d, gd, accd, nd); gd += nd; accd = 0; nd = 0; } \
-                accd = (accd << bb) | cd; nd += bb;                                             \
-                if (nq + bq > 32u) { or_bits(stage_q, gq, accq, nq); gq += nq; accq = 0; nq = 0; } \
-                accq = (accq << bq) | cq; nq += bq;                                             \
-            }
-            if (p1 - p0 == 16) {
-                // full chunk: 2 x 16 bytes through aligned 32-bit shared loads + funnel shifts, fully unrolled
-                uint32_t xd[5], xq[5];
-                const uint32_t ad = o1 + p0, aq = o3 + p0;
-                const uint32_t* wdp = reinterpret_cast<const uint32_t*>(T->bytes + (ad & ~3u));
-                const uint32_t* wqp = reinterpret_cast<const uint32_t*>(T->bytes + (aq & ~3u));
+            const uint32_t p0 = c * 16;
+            const uint32_t gd = (i * wd) * 8u + pad_d + p0 * bb;      // bit position in the tile's DNA staging area
+            const uint32_t gq = (i * wq) * 8u + pad_q + p0 * bq;
+            // 2 x 16 bytes through aligned 32-bit shared loads + funnel shifts, fully unrolled.  A last chunk reads
+            // past the end of its line (still inside the tile); those codes are zeroed, and OR-ing zero bits into
+            // the staging area changes nothing.
+            uint32_t xd[5], xq[5];
+            const uint32_t ad = o1 + p0, aq = o3 + p0;
+            const uint32_t* wdp = reinterpret_cast<const uint32_t*>(T->bytes + (ad & ~3u));
+            const uint32_t* wqp = reinterpret_cast<const uint32_t*>(T->bytes + (aq & ~3u));
 #pragma unroll
-                for (int k = 0; k < 5; k++) { xd[k] = wdp[k]; xq[k] = wqp[k]; }
-                const uint32_t sd = (ad & 3u) * 8u, sq = (aq & 3u) * 8u;
-                uint32_t cdv[16], cqv[16];
+            for (int k = 0; k < 5; k++) { xd[k] = wdp[k]; xq[k] = wqp[k]; }
+            const uint32_t sd = (ad & 3u) * 8u, sq = (aq & 3u) * 8u;
+            uint32_t cdv[16], cqv[16];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t vd = __funnelshift_r(xd[k], xd[k + 1], sd), vq = __funnelshift_r(xq[k], xq[k + 1], sq);
+            for (int k = 0; k < 4; k++) {
+                const uint32_t vd = __funnelshift_r(xd[k], xd[k + 1], sd), vq = __funnelshift_r(xq[k], xq[k + 1], sq);
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        // branch-free: both LUTs are always read, the N-trick code is a select
-                        const uint32_t be = lut->base[__byte_perm(vd, 0, 0x4440 + b)];
-                        const uint32_t ql = lut->qual[__byte_perm(vq, 0, 0x4440 + b)];
-                        const uint32_t tq = be >> 8;
-                        cdv[4 * k + b] = be & 0xFFu;
-                        cqv[4 * k + b] = (tq != 0xFFu) ? tq : ql;
-                    }
+                for (int b = 0; b < 4; b++) {
+                    // branch-free: both LUTs are always read, the N-trick code is a select
+                    const uint32_t be = lut->base[__byte_perm(vd, 0, 0x4440 + b)];
+                    const uint32_t ql = lut->qual[__byte_perm(vq, 0, 0x4440 + b)];
+                    const uint32_t tq = be >> 8;
+                    cdv[4 * k + b] = be & 0xFFu;
+                    cqv[4 * k + b] = (tq != 0xFFu) ? tq : ql;
                 }
-                place_chunk16_any(bb, cdv, stage_d, gd);
-                place_chunk16_any(bq, cqv, stage_q, gq);
-                continue;
-            } else {
-                for (uint32_t p = p0; p < p1; p++) PKT_SYMBOL(dna[p], qual[p])
             }
-#undef PKT_SYMBOL
-            if (nd) or_bits(stage_d, gd, accd, nd);
-            if (nq) or_bits(stage_q, gq, accq, nq);
+            if (nsym < 16u) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) if ((uint32_t)k >= nsym) { cdv[k] = 0; cqv[k] = 0; }
+            }
+            place_chunk16_any(bb, cdv, stage_d, gd);
+            place_chunk16_any(bq, cqv, stage_q, gq);
         }
         __syncthreads();
         // staging (big-endian words) -> global bytes
