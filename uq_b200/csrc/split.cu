@@ -64,14 +64,21 @@ __global__ void __launch_bounds__(SP_THREADS) k_newline_count(const uint8_t* __r
 __global__ void __launch_bounds__(SP_THREADS) k_newline_write(const uint8_t* __restrict__ d, uint64_t n, uint64_t tile0, uint64_t line_base,
                                                             const uint64_t* __restrict__ tile_base, uint64_t* __restrict__ line_off) {
     uint64_t pos = (tile0 + blockIdx.x) * SP_TILE + (uint64_t)threadIdx.x * SP_BYTES_PER_THREAD;
-    unsigned w[16];
-    unsigned c = 0;
+    // bit b of `nl` = byte b of this thread's 64-byte chunk is a newline: four mask bits per word, gathered with
+    // one multiply (the 0x01 bits of the byte mask land in bits 24..27)
+    unsigned long long nl = 0;
     if (pos < n) {
+        unsigned w[16];
         load_chunk(d, n, pos, w);
+        unsigned lo = 0, hi = 0;
 #pragma unroll
-        for (int i = 0; i < 16; i++) c += __popc(nl_mask(w[i]));
-        c >>= 3;
+        for (int i = 0; i < 8; i++) {
+            lo |= (((nl_mask(w[i]) & 0x01010101u) * 0x01020408u) >> 24) << (4 * i);
+            hi |= (((nl_mask(w[8 + i]) & 0x01010101u) * 0x01020408u) >> 24) << (4 * i);
+        }
+        nl = ((unsigned long long)hi << 32) | lo;
     }
+    const unsigned c = __popcll(nl);
     // exclusive scan of c over the CTA
     __shared__ unsigned ws[SP_THREADS / 32];
     unsigned lane = lane_id(), wid = threadIdx.x >> 5;
@@ -96,18 +103,12 @@ __global__ void __launch_bounds__(SP_THREADS) k_newline_write(const uint8_t* __r
     const uint64_t out0 = line_base + tile_base[tile0 + blockIdx.x] + 1;      // +1: line_off[0] = 0 is the first line
     unsigned k = wbase + incl - c;
     const bool staged = total <= SP_STAGE;
-    if (c) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            unsigned m = nl_mask(w[i]);
-            while (m) {
-                int b = (__ffs(m) - 1) >> 3;
-                const uint64_t v = pos + 4 * i + b + 1;                      // the next line starts after the newline
-                if (staged) stage[k] = v; else line_off[out0 + k] = v;
-                k++;
-                m &= ~(0xFFu << (8 * b));
-            }
-        }
+    while (nl) {
+        const int b = __ffsll((long long)nl) - 1;
+        nl &= nl - 1;
+        const uint64_t v = pos + b + 1;                                      // the next line starts after the newline
+        if (staged) stage[k] = v; else line_off[out0 + k] = v;
+        k++;
     }
     if (staged) {
         __syncthreads();
