@@ -189,6 +189,36 @@ def run_ours(args):
     top5 = [{"kernel": k, "launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / ms, 4),
              "GBps": round(v[2] / 1e9 / (v[1] / 1e3), 1) if v[1] > 0 and v[2] else None} for k, v in kern[:8]]
 
+    # ---- decode: logical tables resident in HBM -> FASTQ text resident in HBM, N = 1 only ----
+    decode = None
+    if world == 1 and not args.no_decode:
+        used, free, total = ctx.mem_info()
+        if free > 2.6 * fbytes:
+            fq = ctx.adopt_fastq(dev)
+            st = {}
+            dmembers, dcfg = host.encode_device(ctx, fq, sort="None", raw=["DNA", "QUAL", "QNAME"], stages=st)
+            text = host.decode_device(ctx, st["dna"], st["qual"], st["cols"], dcfg)       # warm-up
+            same = text.first_difference(dev) == -1
+            text.free()
+            ctx.sync()
+            ctx.span_begin()
+            for _ in range(args.steps):
+                text = host.decode_device(ctx, st["dna"], st["qual"], st["cols"], dcfg)
+                text.free()
+            dms = ctx.span_end() / args.steps
+            tab_bytes = st["dna"].nbytes + st["qual"].nbytes + sum(c.nbytes for c in st["cols"])
+            decode = {"value": n / (dms / 1e3), "unit": "reads/s", "ms_per_step": round(dms, 3),
+                      "gb_per_s_fastq": round(fbytes / 1e9 / (dms / 1e3), 2),
+                      "algorithmic_GBps": round((tab_bytes + fbytes) / 1e9 / (dms / 1e3), 1),
+                      "frac_of_peak": round((tab_bytes + fbytes) / 1e9 / (dms / 1e3) / peak, 4),
+                      "byte_exact": bool(same),
+                      "workload": "uQ -> FASTQ of the same %d reads: packed DNA / QUAL tables and QNAME columns resident in HBM -> "
+                                  "FASTQ text resident in HBM, compared byte for byte with the input on the device" % n}
+            dmembers.free()
+            fq.free()
+        else:
+            decode = {"value": None, "note": "skipped: needs %.0f GB of free HBM" % (2.6 * fbytes / 1e9)}
+
     # ---- end to end: host buffers, H2D + D2H inside the timed region ----
     e2e = None
     e2e_skip = None
@@ -300,7 +330,7 @@ def run_ours(args):
                                     "independent read ranges per rank, one container shard per rank (no data-path collective)")},
             "gb_per_s": round(total_fbytes / 1e9 / t, 2),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "pipeline_roofline": pipeline, "kernels": top5, "cpu_baseline": cpu,
+            "pipeline_roofline": pipeline, "kernels": top5, "decode": decode, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -363,6 +393,7 @@ def main():
     ap.add_argument("--multi", default=os.environ.get("UQ_BENCH_MULTI", "global"), choices=["shards", "global"],
                     help="N>1: independent container shards per rank, or one global container (collectives on the data path)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e without copy/compute overlap (diagnostics)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
