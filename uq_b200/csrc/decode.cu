@@ -41,8 +41,21 @@ __device__ __forceinline__ unsigned long long load_le(const uint8_t* p, uint32_t
 __device__ __forceinline__ uint32_t dec_digits(long long v) {
     uint32_t n = v < 0 ? 1u : 0u;
     unsigned long long a = v < 0 ? (unsigned long long)(-(v + 1)) + 1ull : (unsigned long long)v;
+    if (a < (1ull << 32)) {                     // the usual case: no 64-bit divisions
+        const uint32_t x = (uint32_t)a;
+        return n + 1u + (x >= 10u) + (x >= 100u) + (x >= 1000u) + (x >= 10000u) + (x >= 100000u) + (x >= 1000000u) +
+               (x >= 10000000u) + (x >= 100000000u) + (x >= 1000000000u);
+    }
     do { n++; a /= 10ull; } while (a);
     return n;
+}
+
+// decimal digits of a (nd of them) -> w[0 .. nd)
+__device__ __forceinline__ void dec_write(uint8_t* w, unsigned long long a, uint32_t nd) {
+    uint32_t i = nd;
+    while (a >= (1ull << 32)) { w[--i] = (uint8_t)('0' + a % 10ull); a /= 10ull; }
+    uint32_t x = (uint32_t)a;
+    while (i) { w[--i] = (uint8_t)('0' + x % 10u); x /= 10u; }
 }
 
 // read length of a variable-length row: the first set bit is the marker's
@@ -140,7 +153,7 @@ __global__ void __launch_bounds__(DC) k_decode_write(const dec_params* __restric
                 } else {
                     unsigned long long a = v < 0 ? (unsigned long long)(-(v + 1)) + 1ull : (unsigned long long)v;
                     if (v < 0) w[0] = '-';
-                    for (uint32_t i = 0; i < body - (v < 0 ? 1u : 0u); i++) { w[body - 1 - i] = (uint8_t)('0' + a % 10ull); a /= 10ull; }
+                    dec_write(w + (v < 0 ? 1u : 0u), a, body - (v < 0 ? 1u : 0u));
                 }
                 if (c < P.nseps) w[body] = P.seps[c];
             }
@@ -165,6 +178,175 @@ __global__ void __launch_bounds__(DC) k_decode_write(const dec_params* __restric
             oq[i] = qual_char[qcode];
         }
         if (lane == 0) { od[len] = '\n'; od[len + 1] = '+'; od[len + 2] = '\n'; oq[len] = '\n'; }
+    }
+}
+
+// ---- tiled decode of fixed-length reads -----------------------------------------------------------
+// A CTA takes DT_R consecutive records.  Their packed rows are two contiguous byte ranges (coalesced 16-byte
+// loads into shared memory, stored as big-endian words) and their text is ONE contiguous range of the output,
+// which is assembled in shared memory and leaves as aligned 16-byte stores.  Work items are chunks of 16
+// positions (record index fastest, so that the byte stores of a warp fall into different banks): the codes of
+// a chunk are cut out of the bit string with compile-time shifts (the mirror image of pack.cu's
+// place_chunk16), mapped through the LUTs and written to the DNA and QUAL lines; one thread per record
+// formats the QNAME.
+#define DT_R 64
+#define DT_THREADS 256
+#define DT_TEXT_CAP (28 * 1024)
+#define DT_IN_CAP (24 * 1024)
+
+template <int BITS>
+__device__ __forceinline__ void extract_chunk16(const uint32_t* __restrict__ words, uint32_t gbit, uint32_t (&code)[16]) {
+    constexpr int NW = (16 * BITS + 31) / 32;
+    const uint32_t sh = gbit & 31u, w0 = gbit >> 5;
+    uint32_t x[NW + 1], w[NW];
+#pragma unroll
+    for (int k = 0; k <= NW; k++) x[k] = words[w0 + k];
+#pragma unroll
+    for (int k = 0; k < NW; k++) w[k] = __funnelshift_l(x[k + 1], x[k], sh);      // bits gbit + 32k .. of the big-endian string
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int off = k * BITS, wi = off >> 5, o = off & 31;
+        uint32_t v;
+        if (o + BITS <= 32) v = w[wi] >> (32 - o - BITS);
+        else v = (w[wi] << (o + BITS - 32)) | (w[wi + 1 < NW ? wi + 1 : wi] >> (64 - o - BITS));
+        code[k] = v & ((1u << BITS) - 1u);
+    }
+}
+
+__device__ __forceinline__ void extract_chunk16_any(uint32_t bits, const uint32_t* words, uint32_t gbit, uint32_t (&code)[16]) {
+    switch (bits) {          // warp-uniform
+        case 1: extract_chunk16<1>(words, gbit, code); break;
+        case 2: extract_chunk16<2>(words, gbit, code); break;
+        case 3: extract_chunk16<3>(words, gbit, code); break;
+        case 4: extract_chunk16<4>(words, gbit, code); break;
+        case 5: extract_chunk16<5>(words, gbit, code); break;
+        case 6: extract_chunk16<6>(words, gbit, code); break;
+        case 7: extract_chunk16<7>(words, gbit, code); break;
+        default: extract_chunk16<8>(words, gbit, code); break;
+    }
+}
+
+// QNAME text of record r -> w (prefix, columns with separators, suffix, newline); returns its length
+__device__ __forceinline__ uint32_t qname_write(const dec_params& P, uint64_t r, uint8_t* w) {
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < P.prefix_len; i++) w[n++] = P.prefix[i];
+    for (uint32_t c = 0; c < P.ncols; c++) {
+        const dec_col& dc = P.cols[c];
+        const unsigned long long raw = load_le(dc.data + r * dc.itemsize, dc.itemsize);
+        if (dc.format == 0) {
+            if (raw < dc.dict_count) {
+                const uint32_t tl = dc.dict_len[raw];
+                const uint8_t* sp = dc.dict + raw * dc.dict_width;
+                for (uint32_t i = 0; i < tl; i++) w[n++] = sp[i];
+            }
+        } else {
+            const long long v = (long long)raw + (dc.offset ? dc.min_val : 0ll);
+            unsigned long long a = v < 0 ? (unsigned long long)(-(v + 1)) + 1ull : (unsigned long long)v;
+            const uint32_t nd = dec_digits(v);
+            if (v < 0) w[n] = '-';
+            dec_write(w + n + (v < 0 ? 1u : 0u), a, nd - (v < 0 ? 1u : 0u));
+            n += nd;
+        }
+        if (c < P.nseps) w[n++] = P.seps[c];
+    }
+    for (uint32_t i = 0; i < P.suffix_len; i++) w[n++] = P.suffix[i];
+    w[n++] = '\n';
+    return n;
+}
+
+struct dt_smem {
+    alignas(16) uint8_t text[DT_TEXT_CAP + 32];
+    alignas(16) uint32_t in_d[DT_IN_CAP / 4 + 8];
+    uint8_t base_char[256];
+    uint16_t qual_lut[256];             // quality character | (restored base + 1) << 8
+    uint32_t toff[DT_R + 1];            // text offset of every record relative to the staged range
+};
+
+__global__ void __launch_bounds__(DT_THREADS) k_decode_tiles(const dec_params* __restrict__ Pp, const uint8_t* __restrict__ dna,
+                                                            const uint8_t* __restrict__ qual, uint64_t n, const uint64_t* __restrict__ rec_off,
+                                                            uint64_t total, uint8_t* __restrict__ out, unsigned int* __restrict__ fallback) {
+    extern __shared__ __align__(16) uint8_t dt_raw[];
+    dt_smem* S = reinterpret_cast<dt_smem*>(dt_raw);
+    const dec_params& P = *Pp;
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid; i < 256; i += DT_THREADS) {
+        S->base_char[i] = P.base_char[i];
+        const int rb = P.qual_to_base[i];
+        S->qual_lut[i] = (uint16_t)(P.qual_char[i] | ((rb >= 0 ? (unsigned)rb + 1u : 0u) << 8));
+    }
+    const uint32_t L = P.dna_max, wd = P.wd, wq = P.wq;
+    const uint32_t pad_d = 8 * wd - P.bb * L, pad_q = 8 * wq - P.bq * L;
+    const uint32_t words_d = (DT_R * wd + 3) / 4 + 4;                     // QUAL words start behind the DNA words
+    uint32_t* in_q = S->in_d + ((words_d + 3) & ~3u);
+    const uint32_t chunks = (L + 15) / 16;
+    const uint64_t ntiles = (n + DT_R - 1) / DT_R;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t r0 = t * DT_R, r1 = (r0 + DT_R < n) ? r0 + DT_R : n;
+        const uint32_t nrec = (uint32_t)(r1 - r0);
+        const uint64_t o0 = rec_off[r0], o1 = r1 < n ? rec_off[r1] : total;
+        const uint64_t a0 = o0 & ~15ull;
+        __syncthreads();                                                   // previous tile fully stored
+        if (o1 - a0 > DT_TEXT_CAP) { if (tid == 0) atomicOr(fallback, 1u); continue; }
+        // ---- packed rows -> shared memory (big-endian words) ----
+        {
+            const uint4* gd = reinterpret_cast<const uint4*>(dna + r0 * wd);      // r0 * width is a multiple of 64
+            const uint4* gq = reinterpret_cast<const uint4*>(qual + r0 * wq);
+            const uint32_t vd = (nrec * wd + 15) / 16, vq = (nrec * wq + 15) / 16;   // tables carry 64 bytes of slack
+            for (uint32_t v = tid; v < vd; v += DT_THREADS) {
+                const uint4 x = __ldg(gd + v);
+                uint32_t* dst = S->in_d + 4 * v;
+                dst[0] = __byte_perm(x.x, 0, 0x0123); dst[1] = __byte_perm(x.y, 0, 0x0123); dst[2] = __byte_perm(x.z, 0, 0x0123); dst[3] = __byte_perm(x.w, 0, 0x0123);
+            }
+            for (uint32_t v = tid; v < vq; v += DT_THREADS) {
+                const uint4 x = __ldg(gq + v);
+                uint32_t* dst = in_q + 4 * v;
+                dst[0] = __byte_perm(x.x, 0, 0x0123); dst[1] = __byte_perm(x.y, 0, 0x0123); dst[2] = __byte_perm(x.z, 0, 0x0123); dst[3] = __byte_perm(x.w, 0, 0x0123);
+            }
+            for (uint32_t i = tid; i <= nrec; i += DT_THREADS) S->toff[i] = (uint32_t)((i < nrec ? rec_off[r0 + i] : o1) - a0);
+        }
+        __syncthreads();
+        // ---- work items: chunks of 16 positions (record index fastest), then one QNAME line per item ----
+        const uint32_t nsymitems = nrec * chunks;
+        for (uint32_t item = tid; item < nsymitems + nrec; item += DT_THREADS) {
+            if (item >= nsymitems) {
+                const uint32_t i = item - nsymitems;
+                uint8_t* w = S->text + S->toff[i];
+                const uint32_t hl = qname_write(P, r0 + i, w);
+                w[hl + L] = '\n'; w[hl + L + 1] = '+'; w[hl + L + 2] = '\n'; w[hl + 2 * L + 3] = '\n';
+                continue;
+            }
+            const uint32_t c = item / nrec, i = item - c * nrec;
+            const uint32_t p0 = c * 16, nsym = (p0 + 16 <= L) ? 16u : L - p0;
+            uint32_t cd[16], cq[16];
+            extract_chunk16_any(P.bb, S->in_d, (i * wd) * 8u + pad_d + p0 * P.bb, cd);
+            extract_chunk16_any(P.bq, in_q, (i * wq) * 8u + pad_q + p0 * P.bq, cq);
+            const uint32_t hl = S->toff[i + 1] - S->toff[i] - 2u * L - 4u;      // record length - (2 L + 4) = QNAME line length
+            uint8_t* od = S->text + S->toff[i] + hl + p0;
+            uint8_t* oq = od + L + 3;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if ((uint32_t)k < nsym) {
+                    const uint32_t ql = S->qual_lut[cq[k]];
+                    od[k] = (ql >> 8) ? (uint8_t)((ql >> 8) - 1u) : S->base_char[cd[k]];       // qual_N (uq.py:1036)
+                    oq[k] = (uint8_t)ql;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- text out: aligned 16-byte units inside [o0, o1), bytes at the two edges ----
+        {
+            const uint32_t lo = (uint32_t)(o0 - a0), hi = (uint32_t)(o1 - a0);
+            const uint32_t v0 = (lo + 15) / 16, v1 = hi / 16;
+            uint4* gout = reinterpret_cast<uint4*>(out + a0);
+            const uint4* sin = reinterpret_cast<const uint4*>(S->text);
+            for (uint32_t v = v0 + tid; v < v1; v += DT_THREADS) gout[v] = sin[v];
+            if (v0 <= v1) {
+                for (uint32_t b = lo + tid; b < v0 * 16 && b < hi; b += DT_THREADS) out[a0 + b] = S->text[b];
+                for (uint32_t b = v1 * 16 + tid; b < hi; b += DT_THREADS) if (b >= lo) out[a0 + b] = S->text[b];
+            } else {
+                for (uint32_t b = lo + tid; b < hi; b += DT_THREADS) out[a0 + b] = S->text[b];
+            }
+        }
     }
 }
 
@@ -237,7 +419,24 @@ extern "C" int uqb_decode(uqb_ctx* ctx, const uqb_array* dna, const uqb_array* q
     UQB_TRY(uqb_scan_u32_to_u64(ctx, rec_len, rec_off, n, d_total));
     UQB_TRY(uqb_readback(ctx, &total, d_total, 8));
     UQB_TRY(uqb_new_array(ctx, total, 1, fastq));
-    if (n) UQB_LAUNCH(k_decode_write, uqb_grid(ctx, n, DC / 32, 16), DC, 0, dp, (const uint8_t*)dna->d, (const uint8_t*)qual->d, n, rec_off, (uint8_t*)(*fastq)->d);
+    bool done = false;
+    const uint32_t in_words = ((DT_R * dna->width + 3) / 4 + 4 + 3) / 4 * 4 + (DT_R * qual->width + 3) / 4 + 8;
+    if (n && !p->variable && (size_t)in_words * 4 <= DT_IN_CAP && total / n < DT_TEXT_CAP / DT_R - 16 && (((uintptr_t)(*fastq)->d) & 15) == 0) {
+        // fixed-length reads whose tiles fit shared memory
+        unsigned int* d_fb;
+        UQB_TRY(uqb_dalloc_t(ctx, &d_fb, 1));
+        UQB_CUDA(cudaMemsetAsync(d_fb, 0, 4, ctx->stream));
+        UQB_CUDA(cudaFuncSetAttribute(k_decode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(dt_smem)));
+        uint64_t tab = 0;
+        for (uint32_t c = 0; c < p->ncols; c++) tab += n * cols[c]->width;
+        UQB_LAUNCH_B(n * ((uint64_t)dna->width + qual->width + 8) + tab + total, k_decode_tiles, uqb_grid(ctx, n, DT_R, 4), DT_THREADS, sizeof(dt_smem), dp,
+                     (const uint8_t*)dna->d, (const uint8_t*)qual->d, n, rec_off, total, (uint8_t*)(*fastq)->d, d_fb);
+        unsigned int fb = 0;
+        UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
+        UQB_TRY(uqb_dfree(ctx, d_fb, 4));
+        done = fb == 0;
+    }
+    if (n && !done) UQB_LAUNCH(k_decode_write, uqb_grid(ctx, n, DC / 32, 16), DC, 0, dp, (const uint8_t*)dna->d, (const uint8_t*)qual->d, n, rec_off, (uint8_t*)(*fastq)->d);
     UQB_TRY(uqb_dfree(ctx, rec_len, n * 4));
     UQB_TRY(uqb_dfree(ctx, rec_off, n * 8));
     UQB_TRY(uqb_dfree(ctx, d_total, 8));
