@@ -91,7 +91,30 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print on fd 1 (e.g. the NCCL version banner) goes to stderr; the one JSON line is written
+    to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def run_ours(args):
+    quiet_stdout()
     from uq_b200 import shard
     rank, local_rank, world = shard.world()
     dist = None
@@ -332,7 +355,7 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "pipeline_roofline": pipeline, "kernels": top5, "decode": decode, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -378,7 +401,7 @@ def run_reference(args):
                                    "encode per core, sort over the sample only)" % (cores, s_reads)},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
