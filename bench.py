@@ -122,6 +122,9 @@ def run_ours(args):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
+        # the row exchange of the sample sort is one large send/recv per peer: give NCCL's point-to-point path all channels
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from uq_b200 import host
     from uq_b200.device import Context
@@ -157,6 +160,8 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         out_bytes, cfg = one_step()
+    if global_mode and os.environ.get("UQB_MG_TRACE") == "1" and rank == 0:
+        print("trace (last warm-up step):", multigpu.trace_dump()[-40:], file=sys.stderr)
     ctx.sync()
     ctx.timing(True)
     ctx.timing_reset()

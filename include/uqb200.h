@@ -195,6 +195,13 @@ int uqb_gather_rows(uqb_ctx* ctx, const uqb_array* table, const uqb_array* perm,
 int uqb_add_scalar_u32(uqb_ctx* ctx, uqb_array* a, uint32_t value);   /* a[i] += value, uint32 array */
 /* lower_bound of k host rows in a table sorted in memcmp order (splitter search of the multi-GPU sample sort) */
 int uqb_rows_lower_bound(uqb_ctx* ctx, const uqb_array* sorted_table, const uint8_t* probes_host, uint32_t k, uint64_t* out_host);
+/* partition-first sample sort (multi-GPU, replaces nothing in uq.py: the reference is single process): rows are sent
+ * to rank d = number of splitter keys <= big-endian first 8 bytes of the row.  order = uint32[n] row indices grouped
+ * by destination (stable), counts_host[0..nsplit] = rows per destination */
+int uqb_partition_rows(uqb_ctx* ctx, const uqb_array* table, const uint64_t* split_keys_host, uint32_t nsplit,
+                       uqb_array** order, uint64_t* counts_host);
+/* out[idx[j]] = src[j], uint32 arrays, idx a permutation (inverse of uqb_gather_rows) */
+int uqb_scatter_u32(uqb_ctx* ctx, const uqb_array* src, const uqb_array* idx, uqb_array** out);
 /* uint32 -> little-endian integer of itemsize bytes (key.astype(min_scalar_type(max)), uq.py:790) */
 int uqb_narrow_u32(uqb_ctx* ctx, const uqb_array* a, uint32_t itemsize, uqb_array** out);
 /* QNAME columns <-> rows in sort-key form: columns concatenated big-endian at their own widths,

@@ -35,7 +35,10 @@ def _worker(rank, world, port, q):
     ctx = Context(rank)
     comm = mg.Comm(dist, "cuda:%d" % rank)
     results = []
-    for kind, n, length, kw in CASES:
+    # every case through the partition-first sample sort, and the first three again through the merge variant
+    runs = [(c, "0") for c in CASES] + [(c, "1") for c in CASES[:3]]
+    for (kind, n, length, kw), merge in runs:
+        os.environ["UQB_MG_MERGE"] = merge
         kwg = dict(genome=max(4 * length, n // 6), pool=max(1, n // 7)) if kind == "genome" else {}
         n0 = int(n * 0.55)
         first, cnt = (0, n0) if rank == 0 else (n0, n - n0)
@@ -59,7 +62,8 @@ def _worker(rank, world, port, q):
             import json
             if json.loads(json.dumps(cfg, default=str)) != json.loads(json.dumps(want_cfg, default=str)):
                 bad.append("config differs")
-            results.append((kind, kw, bad))
+            results.append((kind + (" merge" if merge == "1" else ""), kw, bad))
+    os.environ["UQB_MG_MERGE"] = "0"
     # a larger case generated on the device, loaded through the streamed path with the reference line, async downloads
     n_each = 700_000
     dev = ctx.synth("genome", n_each, 150, 1002, first=rank * n_each, genome=200_000, pool=300_000)

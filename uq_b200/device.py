@@ -114,6 +114,21 @@ class Context:
     def add_scalar_u32(self, arr, value):
         self.check(self.lib.uqb_add_scalar_u32(self.h, arr.h, int(value)))
 
+    def partition_rows(self, table, split_keys):
+        """rows -> destination ranks by their big-endian first 8 bytes (dest = number of split_keys <= key).
+        -> (order: uint32[n] row indices grouped by destination, stable; counts per destination)"""
+        keys = np.ascontiguousarray(split_keys, dtype=np.uint64)
+        counts = np.zeros(len(keys) + 1, dtype=np.uint64)
+        h = C.c_void_p()
+        self.check(self.lib.uqb_partition_rows(self.h, table.h, _ptr(keys), len(keys), C.byref(h), _ptr(counts)))
+        return DeviceArray(self, h), [int(c) for c in counts]
+
+    def scatter_u32(self, src, idx):
+        """out[idx[j]] = src[j] (uint32 arrays, idx a permutation)"""
+        h = C.c_void_p()
+        self.check(self.lib.uqb_scatter_u32(self.h, src.h, idx.h, C.byref(h)))
+        return DeviceArray(self, h)
+
     def rows_lower_bound(self, sorted_table, probes):
         """lower_bound of every row of `probes` (uint8 [k][width], host) in a device table sorted in memcmp order"""
         probes = np.ascontiguousarray(probes, dtype=np.uint8)

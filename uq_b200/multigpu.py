@@ -9,16 +9,19 @@ FASTQ file and the result is bit-identical to the single-GPU encode of the whole
   QNAME column typing        all-gather + merge of the per-column statistics and of the dictionaries of the
                              columns that stay 'mapping' (merge_colstats)
   pack / column encode       nothing (per read)
-  sort / unique              sample sort: splitters from gathered samples, ONE all-to-all of each rank's *unique*
-                             rows (NCCL over NVLink), local sort/unique of the received key range, all-to-all of
-                             the global ids back (global_unique)
-  --sort order               all-to-all of the per-record payload (keys / raw rows) to the rank that owns the
-                             record's key range; a stable local sort by key finishes it (global_order)
+  sort / unique              partition-first sample sort: splitters from gathered row samples, every row goes to
+                             the rank whose range holds its first 8 bytes (ONE all-to-all of the rows, NCCL over
+                             NVLink), the rank sorts / uniques its range once, the global ids return through the
+                             reverse all-to-all (global_unique; global_unique_merge is the skew-proof variant)
+  --sort order               the per-record payload (keys / raw rows) follows the rows of the sorted-on table:
+                             same partition, same all-to-all, then the receiver's stable argsort (global_order)
 
 The device collectives go through torch.distributed (NCCL) on zero-copy tensor views of the arena memory
 (`__cuda_array_interface__`); the host-side merges are plain Python over tiny structs and are covered by
 2-rank gloo tests on CPU.
 """
+import os
+
 import numpy as np
 
 from . import _lib as L
@@ -160,6 +163,28 @@ def pick_splitters(all_samples, world):
 
 
 # ------------------------------------------------------------------------------------------------
+# diagnostics: UQB_MG_TRACE=1 prints wall-clock milliseconds per phase on rank 0 (adds device syncs)
+# ------------------------------------------------------------------------------------------------
+import time as _time
+_TRACE = {"on": os.environ.get("UQB_MG_TRACE") == "1", "t": 0.0, "log": []}
+
+
+def _mark(ctx, comm, name):
+    if not _TRACE["on"]:
+        return
+    ctx.sync()
+    now = _time.perf_counter()
+    if name is not None and comm.rank == 0:
+        _TRACE["log"].append((name, round((now - _TRACE["t"]) * 1e3, 2)))
+    _TRACE["t"] = _time.perf_counter()
+
+
+def trace_dump():
+    out, _TRACE["log"] = _TRACE["log"], []
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # communication
 # ------------------------------------------------------------------------------------------------
 class Comm:
@@ -169,12 +194,17 @@ class Comm:
         self.dist, self.device = dist, device
         self.rank = dist.get_rank() if dist else 0
         self.world = dist.get_world_size() if dist else 1
+        # the small object collectives run over gloo next to NCCL: queued on the NCCL communicator they would wait
+        # behind a row exchange that is still in flight and serialise the pipeline of encode_sharded
+        self.obj_group = None
+        if dist and dist.get_backend() == "nccl":
+            self.obj_group = dist.new_group(backend="gloo")
 
     def all_gather_object(self, obj):
         if not self.dist:
             return [obj]
         out = [None] * self.world
-        self.dist.all_gather_object(out, obj)
+        self.dist.all_gather_object(out, obj, group=self.obj_group)
         return out
 
     def exchange_counts(self, send_counts):
@@ -188,43 +218,129 @@ class Comm:
             return torch.empty(0, dtype=torch.uint8, device=self.device)
         return torch.as_tensor(arr, device=self.device)
 
-    def all_to_all_rows(self, ctx, send, send_counts, recv_counts):
-        """send: DeviceArray whose rows are grouped by destination rank in rank order -> DeviceArray holding
-        the rows received from rank 0, 1, ... in that order (NCCL all-to-all over NVLink)."""
+    def all_to_all_rows_start(self, ctx, send, send_counts, recv_counts):
+        """send: DeviceArray whose rows are grouped by destination rank in rank order.  Starts the NCCL all-to-all (over
+        NVLink, on torch's NCCL stream) and returns (recv, work): recv holds the rows of rank 0, 1, ... in that order
+        once all_to_all_rows_wait(work) has returned; `send` must stay alive until then."""
         w = send.width
         recv = ctx.alloc(sum(recv_counts), w)
         if not self.dist:
             raise RuntimeError("all_to_all on a single rank")
-        ctx.sync()
-        self.dist.all_to_all_single(self._tensor(recv), self._tensor(send), [c * w for c in recv_counts], [c * w for c in send_counts])
+        ctx.sync()                                       # the rows are produced on the context's stream
+        work = self.dist.all_to_all_single(self._tensor(recv), self._tensor(send), [c * w for c in recv_counts],
+                                           [c * w for c in send_counts], async_op=True)
+        return recv, work
+
+    def all_to_all_rows_wait(self, work):
         import torch
+        work.wait()
         torch.cuda.current_stream().synchronize()
+
+    def all_to_all_rows(self, ctx, send, send_counts, recv_counts):
+        recv, work = self.all_to_all_rows_start(ctx, send, send_counts, recv_counts)
+        self.all_to_all_rows_wait(work)
         return recv
 
 
 # ------------------------------------------------------------------------------------------------
 # distributed sort / unique
 # ------------------------------------------------------------------------------------------------
-SAMPLES_PER_RANK = 256
+SAMPLES_PER_RANK = 1024
+SKEW_LIMIT = 2.0          # a rank may receive at most this many times the largest local table, else the merge variant runs
+
+
+def row_key64(rows):
+    """uint8 [m][w] -> uint64: the first 8 bytes of every row as a big-endian integer (zero padded) - the partition key"""
+    m, w = rows.shape
+    buf = np.zeros((m, 8), dtype=np.uint8)
+    buf[:, :min(8, w)] = rows[:, :8]
+    return buf.view(">u8").reshape(-1).astype(np.uint64)
+
+
+def _sample_rows(ctx, table, count):
+    n, w = table.n, table.width
+    if n == 0:
+        return np.zeros((0, w), dtype=np.uint8)
+    idx = np.unique(np.linspace(0, n - 1, num=min(n, count)).astype(np.uint32))
+    d_idx = ctx.upload(idx)
+    d_s = ctx.gather_rows(table, d_idx)
+    out = d_s.download().reshape(len(idx), w) if w else np.zeros((len(idx), 0), np.uint8)
+    d_idx.free(); d_s.free()
+    return out
 
 
 def global_unique(ctx, comm, table, want_perm=False):
-    """-> dict(key: uint32[n] global unique-row index of every local row, uniq: this rank's key range of the
-    global unique table (rows ascending; the ranges concatenate in rank order), n_unique, offset, counts (unique
-    rows per rank), perm: local stable argsort if wanted)."""
-    perm, key_local, uniq_local, nu = ctx.sort_rows(table, want_perm=want_perm, want_key=True, want_uniq=True)
+    """-> dict(key: uint32[n] global unique-row index of every local row, uniq: this rank's key range of the global
+    unique table (rows ascending; the ranges concatenate in rank order), n_unique, counts (unique rows per rank),
+    route: how to bring per-record arrays into the global stable order of this table (see global_order)).
+
+    Partition first, sort once: splitters come from a sample of every rank's rows; a row goes to the rank whose range
+    holds its first 8 bytes (so identical rows, and all rows tied on those bytes, meet on one rank); ONE all-to-all
+    moves the rows over NVLink, each rank sorts / uniques its range exactly like the single-GPU path, and the global
+    ids travel back through the reverse all-to-all.  If the sample is fooled by a very skewed table (one rank would
+    receive more than SKEW_LIMIT times the largest local table) the merge variant below runs instead.
+
+    global_unique_begin / global_unique_end are the two halves around the row exchange: encode_sharded starts the
+    exchange of one table and prepares or finishes another one while the rows are on the wire."""
+    return global_unique_end(ctx, comm, global_unique_begin(ctx, comm, table, want_perm=want_perm))
+
+
+def global_unique_begin(ctx, comm, table, want_perm=False):
     if comm.world == 1:
-        return dict(key=key_local, uniq=uniq_local, n_unique=nu, offset=0, counts=[nu], perm=perm)
-    w = table.width
-    # splitters from evenly spaced samples of every rank's sorted unique rows
-    if nu:
-        idx = np.unique(np.linspace(0, nu - 1, num=min(nu, SAMPLES_PER_RANK)).astype(np.uint32))
-        d_idx = ctx.upload(idx)
-        d_s = ctx.gather_rows(uniq_local, d_idx)
-        samples = d_s.download().reshape(len(idx), w) if w else np.zeros((len(idx), 0), np.uint8)
-        d_idx.free(); d_s.free()
+        perm, key_local, uniq_local, nu = ctx.sort_rows(table, want_perm=want_perm, want_key=True, want_uniq=True)
+        return dict(done=dict(key=key_local, uniq=uniq_local, n_unique=nu, counts=[nu], route=("local", perm)))
+    _mark(ctx, comm, None)
+    samples = _sample_rows(ctx, table, SAMPLES_PER_RANK)
+    gathered = comm.all_gather_object((samples, table.n))
+    _mark(ctx, comm, "gu.sample")
+    splitters = pick_splitters(np.concatenate([g[0] for g in gathered]), comm.world)
+    order, send_counts = ctx.partition_rows(table, np.sort(row_key64(splitters)))
+    send_counts += [0] * (comm.world - len(send_counts))
+    recv_counts = comm.exchange_counts(send_counts)
+    worst = max(comm.all_gather_object(sum(recv_counts)))
+    _mark(ctx, comm, "gu.partition")
+    if worst > SKEW_LIMIT * max(g[1] for g in gathered) + 4096 or os.environ.get("UQB_MG_MERGE") == "1":
+        order.free()
+        return dict(done=global_unique_merge(ctx, comm, table, want_perm=want_perm))
+    send = ctx.gather_rows(table, order)
+    _mark(ctx, comm, "gu.gather_send")
+    recv, work = comm.all_to_all_rows_start(ctx, send, send_counts, recv_counts)
+    return dict(done=None, send=send, recv=recv, work=work, order=order, send_counts=send_counts, recv_counts=recv_counts,
+                want_perm=want_perm)
+
+
+def global_unique_end(ctx, comm, st):
+    if st["done"] is not None:
+        return st["done"]
+    _mark(ctx, comm, None)
+    comm.all_to_all_rows_wait(st["work"])
+    st["send"].free()
+    _mark(ctx, comm, "gu.all_to_all_wait")
+    recv, order, send_counts, recv_counts, want_perm = st["recv"], st["order"], st["send_counts"], st["recv_counts"], st["want_perm"]
+    perm_r, key_r, uniq_range, nr = ctx.sort_rows(recv, want_perm=want_perm, want_key=True, want_uniq=True)
+    recv.free()
+    _mark(ctx, comm, "gu.sort")
+    counts = comm.all_gather_object(nr)
+    ctx.add_scalar_u32(key_r, sum(counts[:comm.rank]))       # global id of every received row
+    ids_back = comm.all_to_all_rows(ctx, key_r, recv_counts, send_counts)        # in the order the rows were sent
+    key_r.free()
+    key_global = ctx.scatter_u32(ids_back, order)
+    ids_back.free()
+    _mark(ctx, comm, "gu.ids_back")
+    if want_perm:
+        route = ("partition", order, send_counts, recv_counts, perm_r)
     else:
-        samples = np.zeros((0, w), dtype=np.uint8)
+        order.free()
+        route = None
+    return dict(key=key_global, uniq=uniq_range, n_unique=sum(counts), counts=counts, route=route)
+
+
+def global_unique_merge(ctx, comm, table, want_perm=False):
+    """The merge variant: every rank sorts / uniques its own rows first, only the locally unique rows travel, and the
+    receiving rank sorts them again.  Twice the sorting, but immune to skew (a table of identical rows sends one row)."""
+    perm, key_local, uniq_local, nu = ctx.sort_rows(table, want_perm=want_perm, want_key=True, want_uniq=True)
+    w = table.width
+    samples = _sample_rows(ctx, uniq_local, 256)
     splitters = pick_splitters(np.concatenate(comm.all_gather_object(samples)), comm.world)
     if len(splitters) == comm.world - 1:
         b = [0] + [int(x) for x in ctx.rows_lower_bound(uniq_local, splitters)] + [nu]
@@ -245,17 +361,36 @@ def global_unique(ctx, comm, table, want_perm=False):
     key_recv.free()
     key_global = ctx.gather_rows(ids_back, key_local)   # ids_back[local unique index]
     ids_back.free(); key_local.free()
-    return dict(key=key_global, uniq=uniq_range, n_unique=sum(counts), offset=offset, counts=counts, perm=perm)
+    route = ("merge", key_global, perm, counts) if want_perm else None
+    return dict(key=key_global, uniq=uniq_range, n_unique=sum(counts), counts=counts, route=route)
 
 
-def global_order(ctx, comm, key_global, perm, counts, payloads):
-    """Stable global sort of the records by `key_global` (a global unique-row index).  `perm` is the local stable
-    argsort of the same table, `counts` the unique rows owned by every rank.  payloads: {name: DeviceArray [n][w]}.
-    Every record goes to the rank that owns its key range; there a stable sort by key finishes the job (the
-    all-to-all delivers source ranks in order, and source rank order is global record order).
-    -> {name: DeviceArray} holding this rank's slice of the globally sorted arrays."""
-    if comm.world == 1:
-        return {k: ctx.gather_rows(v, perm) for k, v in payloads.items()}
+def global_order(ctx, comm, route, payloads):
+    """Bring per-record arrays into the global stable order of the sorted-on table.  payloads: {name: DeviceArray [n][w]}
+    -> {name: DeviceArray} holding this rank's slice of the globally sorted arrays (slices concatenate in rank order).
+    Frees the route's arrays (not the payloads)."""
+    kind = route[0]
+    if kind == "local":
+        perm = route[1]
+        out = {k: ctx.gather_rows(v, perm) for k, v in payloads.items()}
+        perm.free()
+        return out
+    if kind == "partition":
+        # the records follow their rows: same partition, same all-to-all, then the receiving rank's stable argsort.
+        # Source ranks arrive in rank order and every source keeps its record order, so ties end in global record order.
+        _, order, send_counts, recv_counts, perm_r = route
+        out = {}
+        for name, arr in payloads.items():
+            s = ctx.gather_rows(arr, order)
+            r = comm.all_to_all_rows(ctx, s, send_counts, recv_counts)
+            s.free()
+            out[name] = ctx.gather_rows(r, perm_r)
+            r.free()
+        order.free(); perm_r.free()
+        _mark(ctx, comm, "global_order")
+        return out
+    _, key_global, perm, counts = route
+    # merge variant: every record goes to the rank that owns its key range; there a stable sort by key finishes the job
     key_sorted = ctx.gather_rows(key_global, perm)                      # non-decreasing
     key_be = ctx.columns_to_rows([key_sorted])                          # big-endian rows: memcmp order = numeric order
     bounds = np.cumsum(counts)[:-1].astype(">u4").view(np.uint8).reshape(-1, 4)
@@ -275,7 +410,7 @@ def global_order(ctx, comm, key_global, perm, counts, payloads):
         s.free()
         out[name] = ctx.gather_rows(r, perm2)
         r.free()
-    perm2.free()
+    perm2.free(); perm.free()
     return out
 
 
@@ -327,6 +462,7 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
     sort, raw, pattern = host.normalise_options(sort, raw, pattern)
     if pattern != ['0.1', '0.1']:
         raise host.UQError('ERROR: the multi-GPU path writes pattern 0.1 only (other layouts interleave the ranks\' rows)')
+    _mark(ctx, comm, None)
     info = fq.split()
     n_local = int(info.n_reads)
     lines_bad = info.status == 1
@@ -360,16 +496,24 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
         raise host.UQError('ERROR: malformed FASTQ record %d (%s)' % (r, w))
     prefix, suffix, separators = host.derive_qname_layout(st, n_total)
     dec = host.decide_alphabets(st, notricks=notricks, pad=pad)
+    _mark(ctx, comm, "split+pass1")
     # ---- Pass 2: rank 0 decides which columns leave 'mapping' at checkpoint 0, the others skip those dictionaries ----
     ncols = len(separators) + 1
+    # which columns leave 'mapping' at checkpoint 0 is a property of the first 10001 records of the file: rank 0 scans
+    # just that head (a few megabytes) and tells the others, then every rank scans its own range at the same time
+    early = None
     if comm.rank == 0:
-        cols0, bad0 = fq.qname_scan(len(prefix), len(suffix), separators)
-        early = [bool(cols0[c].n_distinct == L.U64_MAX) for c in range(ncols)] if bad0 < 0 else [False] * ncols
-    else:
-        cols0, bad0, early = None, -1, None
+        early = [False] * ncols
+        if n_total > 10000:
+            head_bytes = int(fq.line_offsets(4 * 10001, 1)[0])
+            hfq = ctx.load_fastq(fq.download(0, head_bytes))
+            hfq.split()
+            hcols, hbad = hfq.qname_scan(len(prefix), len(suffix), separators)
+            if hbad < 0:
+                early = [bool(hcols[c].n_distinct == L.U64_MAX) for c in range(ncols)]
+            hfq.free()
     early = comm.all_gather_object(early)[0]
-    if comm.rank != 0:
-        cols0, bad0 = fq.qname_scan(len(prefix), len(suffix), separators, col_mode=[1 if e else 2 for e in early])
+    cols0, bad0 = fq.qname_scan(len(prefix), len(suffix), separators, col_mode=[1 if e else 2 for e in early])
     bads = comm.all_gather_object(bad0)
     if any(b >= 0 for b in bads):
         raise host.UQError('Encoding QNAMEs as strings has not been implimented yet.')
@@ -382,6 +526,7 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
     all_dicts = comm.all_gather_object(my_dicts)
     colstats, gdicts = merge_colstats(all_plain, n_total, early, all_dicts)
     columns = host.decide_columns(colstats, n_total, lambda i: gdicts[i])
+    _mark(ctx, comm, "pass2")
     # ---- pack + column encode (per read) ----
     dna, qual = fq.pack(host.pack_params(dec))
     specs = host.column_specs(columns)
@@ -395,6 +540,7 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
             d_remap.free(); cols[c].free()
             cols[c] = ctx.narrow_u32(g, specs[c][1])
             g.free()
+    _mark(ctx, comm, "pack+cols")
     # ---- run_mix over the ranks ----
     res = ShardResult(ctx, sink)
     sorted_on = sort if sort in ('DNA', 'QUAL', 'QNAME') else None
@@ -402,38 +548,52 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
     keyed = {t: (t not in raw) for t in tables}
     uniq = {}
     payload = {}
-    order_info = None
-    for t in ('QUAL', 'DNA', 'QNAME'):
-        if keyed[t] or t == sorted_on:
-            g = global_unique(ctx, comm, tables[t], want_perm=(t == sorted_on))
-            if t == sorted_on:
-                order_info = (g['key'], g['perm'], g['counts'])
-            if keyed[t]:
-                uniq[t] = (g['uniq'], g['n_unique'])
-                payload[t + '.key'] = g['key']
-                if t == 'QNAME':                        # unique rows back to typed columns (uq.py:842-847)
-                    ucols = ctx.rows_to_columns(g['uniq'], [np.dtype(m['dtype']).itemsize for m in columns])
-                    for c, meta in zip(ucols, columns):
-                        res.add(meta['name'], c, 'vector', meta['dtype'])
-                    g['uniq'].free()
-                else:
-                    res.add(t, g['uniq'], 'table', g['uniq'].width)
-            else:
-                g['uniq'].free()
-                if t != sorted_on:
-                    g['key'].free()
+    route = None
+    for t in ('DNA', 'QUAL', 'QNAME'):
         if not keyed[t]:
             if t == 'QNAME':
                 for c, meta in zip(cols, columns):
                     payload[meta['name'] + '.raw'] = c
             else:
                 payload[t + '.raw'] = tables[t]
-    if order_info is not None:
-        key_x, perm_x, counts_x = order_info
-        moved = global_order(ctx, comm, key_x, perm_x, counts_x, payload)
+
+    def finish(t, st):
+        nonlocal route
+        g = global_unique_end(ctx, comm, st)
+        if t == sorted_on:
+            route = g['route']
+        if keyed[t]:
+            uniq[t] = (g['uniq'], g['n_unique'])
+            payload[t + '.key'] = g['key']
+            if t == 'QNAME':                        # unique rows back to typed columns (uq.py:842-847)
+                ucols = ctx.rows_to_columns(g['uniq'], [np.dtype(m['dtype']).itemsize for m in columns])
+                for c, meta in zip(ucols, columns):
+                    res.add(meta['name'], c, 'vector', meta['dtype'])
+                g['uniq'].free()
+            else:
+                res.add(t, g['uniq'], 'table', g['uniq'].width)
+        else:
+            g['uniq'].free()
+            if not (t == sorted_on and route[0] == 'merge'):      # the merge route still needs the key
+                g['key'].free()
+
+    # software pipeline over the tables: while the rows of one table are on the wire (NCCL stream), the next table is
+    # sampled / partitioned / gathered and the previous one is sorted (context stream).  DNA goes first: its exchange is
+    # the shortest one to leave uncovered, and the long QUAL exchange then hides behind the DNA sort.
+    todo = [t for t in ('DNA', 'QUAL', 'QNAME') if keyed[t] or t == sorted_on]
+    pending = None
+    for t in todo:
+        st = global_unique_begin(ctx, comm, tables[t], want_perm=(t == sorted_on))
+        if pending is not None:
+            finish(*pending)
+        pending = (t, st)
+    if pending is not None:
+        finish(*pending)
+    if route is not None:
+        moved = global_order(ctx, comm, route, payload)
         old = {id(v): v for v in payload.values()}
-        old[id(key_x)] = key_x
-        old[id(perm_x)] = perm_x
+        if route[0] == 'merge':
+            old[id(route[1])] = route[1]
         for v in old.values():
             v.free()
         payload = moved
