@@ -40,8 +40,10 @@ def _worker(rank, world, port, q):
     for (kind, n, length, kw), merge in runs:
         os.environ["UQB_MG_MERGE"] = merge
         kwg = dict(genome=max(4 * length, n // 6), pool=max(1, n // 7)) if kind == "genome" else {}
-        n0 = int(n * 0.55)
-        first, cnt = (0, n0) if rank == 0 else (n0, n - n0)
+        # uneven contiguous ranges; rank 0 is the largest (it must hold the first 10001 reads)
+        wts = [0.55, 0.45] if world == 2 else [0.46] + [0.54 / (world - 1)] * (world - 1)
+        cuts = [0] + [int(n * sum(wts[:k + 1])) for k in range(world - 1)] + [n]
+        first, cnt = cuts[rank], cuts[rank + 1] - cuts[rank]
         shard = synth.make_fastq(kind=kind, n=cnt, length=length, seed=21, first=first, **kwg)
         fq = ctx.load_fastq(shard)
         res, cfg = mg.encode_sharded(ctx, comm, fq, **kw)
@@ -66,6 +68,11 @@ def _worker(rank, world, port, q):
     os.environ["UQB_MG_MERGE"] = "0"
     # a larger case generated on the device, loaded through the streamed path with the reference line, async downloads
     n_each = 700_000
+    if world != 2:
+        if rank == 0:
+            q.put(results)
+        dist.destroy_process_group()
+        return
     dev = ctx.synth("genome", n_each, 150, 1002, first=rank * n_each, genome=200_000, pool=300_000)
     data = dev.download().copy()
     dev.free()
@@ -98,15 +105,16 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_gpu_global_encode_equals_single_gpu():
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_global_encode_equals_single_gpu(world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs: p.start()
     results = q.get(timeout=600)
     for p in procs: p.join(timeout=120)
