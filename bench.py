@@ -221,7 +221,7 @@ def run_ours(args):
     decode = None
     if world == 1 and not args.no_decode:
         used, free, total = ctx.mem_info()
-        if free > 2.6 * fbytes:
+        if total - used > 2.8 * fbytes:             # the arena keeps what it mapped: room = total - bytes in use
             fq = ctx.adopt_fastq(dev)
             st = {}
             dmembers, dcfg = host.encode_device(ctx, fq, sort="None", raw=["DNA", "QUAL", "QNAME"], stages=st)

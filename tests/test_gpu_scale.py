@@ -163,3 +163,123 @@ def test_full_size_roundtrip_on_device(ctx):
     for a in (text, other, ref):
         a.free()
     members.free(); fq.free(); dev.free()
+
+
+# ---- BASELINE.json full sizes through size-independent properties (everything stays in HBM) ----------------------
+def _logical_tables(ctx, members, cfg):
+    """keyed / raw members in HBM -> logical DNA and QUAL tables and QNAME columns in record order (uq.py:947-973)"""
+    it = members.items
+    def table(name):
+        if name + ".raw" in it:
+            return it[name + ".raw"][0], False
+        return ctx.gather_rows(it[name][0], it[name + ".key"][0]), True
+    dna, fd = table("DNA")
+    qual, fq_ = table("QUAL")
+    cols, fc = [], []
+    for meta in cfg["QNAME_columns"]:
+        nm = meta["name"]
+        if nm + ".raw" in it:
+            cols.append(it[nm + ".raw"][0]); fc.append(False)
+        else:
+            cols.append(ctx.gather_rows(it[nm][0], it["QNAME.key"][0])); fc.append(True)
+    return dna, qual, cols, [a for a, f in [(dna, fd), (qual, fq_)] + list(zip(cols, fc)) if f]
+
+
+def _assert_idempotent(ctx, dev, **opts):
+    """encode -> decode -> encode gives the same container, member by member, compared on the device; the decoded
+    text has the size of the input.  (With --sort the decoded records come out in sorted order, so the second encode
+    sees a different file with the same multiset of records - its sorted / keyed output must not change.)"""
+    from uq_b200 import host
+    fq = ctx.adopt_fastq(dev)
+    m1, cfg1 = host.encode_device(ctx, fq, **opts)
+    fq.free()
+    dna, qual, cols, tmp = _logical_tables(ctx, m1, cfg1)
+    text = host.decode_device(ctx, dna, qual, cols, cfg1)
+    for a in tmp:
+        a.free()
+    assert text.nbytes == dev.nbytes
+    fq2 = ctx.adopt_fastq(text)
+    m2, cfg2 = host.encode_device(ctx, fq2, **opts)
+    fq2.free()
+    for k in ("reads", "bases", "qualities", "N_qual", "bits_per_base", "bits_per_quality", "dna_max", "variable_read_lengths",
+              "QNAME_prefix", "QNAME_suffix", "QNAME_separators", "base_distribution", "qual_distribution"):
+        assert cfg2[k] == cfg1[k], k
+    assert [(c["format"], c["dtype"]) for c in cfg2["QNAME_columns"]] == [(c["format"], c["dtype"]) for c in cfg1["QNAME_columns"]]
+    assert sorted(m1.items) == sorted(m2.items)
+    for name in m1.items:
+        a, b = m1.items[name][0], m2.items[name][0]
+        assert (a.n, a.width) == (b.n, b.width), name
+        assert a.first_difference(b) == -1, name
+    return m1, cfg1, m2, text
+
+
+def test_config3_full_size_sort_qname(ctx):
+    """50 M CASAVA-1.8 reads, --sort QNAME: column typing, sorted unique QNAME table, monotone key, idempotence."""
+    n = 50_000_000
+    used, free, total = ctx.mem_info()
+    if total - used < 100 << 30:                 # the arena keeps what it mapped: room = total - bytes in use
+        pytest.skip("needs ~100 GB of free HBM")
+    dev = ctx.synth("casava", n, 100, 1003)
+    m1, cfg, m2, text = _assert_idempotent(ctx, dev, sort="QNAME")
+    assert cfg["reads"] == n and cfg["QNAME_prefix"] == "@EAS139:136:FC706VJ:" and cfg["QNAME_separators"] == "::: :::"
+    assert [(c["format"], c["dtype"]) for c in cfg["QNAME_columns"]] == [
+        ("integers", "uint8"), ("integers", "uint16"), ("integers", "uint16"), ("integers", "uint32"),
+        ("integers", "uint8"), ("mapping", "uint8"), ("integers", "uint8"), ("mapping", "uint8")]
+    out = {k: m1.items[k][0].download(dtype=np.dtype(m1.items[k][2]) if m1.items[k][1] == "vector" else np.uint8)
+           for k in ["QNAME.key"] + ["QNAME_%d" % (i + 1) for i in range(8)]}
+    key = out["QNAME.key"]
+    assert np.all(key[1:] >= key[:-1])                                   # --sort QNAME: keys in sorted order
+    # the unique table is strictly increasing in column-lexicographic order
+    lt = np.zeros(len(out["QNAME_1"]) - 1, dtype=bool)
+    eq = np.ones(len(lt), dtype=bool)
+    for i in range(8):
+        c = out["QNAME_%d" % (i + 1)].astype(np.int64)
+        lt |= eq & (c[:-1] < c[1:])
+        eq &= c[:-1] == c[1:]
+    assert bool(np.all(lt)) and not bool(np.any(eq))
+    m1.free(); m2.free(); text.free(); dev.free()
+
+
+@pytest.mark.parametrize("pad,notricks", [(False, False), (True, True)])
+def test_config4_full_size_layouts(ctx, pad, notricks):
+    """20 M reads: each of the 8 layouts written by the encode is undone on the device and compared with the packed
+    table; two of them are decoded back to the input text."""
+    from uq_b200 import host
+    n = 20_000_000
+    dev = ctx.synth("illumina", n, 100, 1004)
+    for i, p in enumerate(PATTERNS):
+        pq = PATTERNS[(i + 3) % 8]
+        fq = ctx.adopt_fastq(dev)
+        st = {}
+        m, cfg = host.encode_device(ctx, fq, sort="None", raw=["DNA", "QUAL", "QNAME"], pattern=[p, pq], pad=pad, notricks=notricks, stages=st)
+        fq.free()
+        for name, tab, pat in (("DNA.raw", st["dna"], p), ("QUAL.raw", st["qual"], pq)):
+            back = ctx.unlayout(m.items[name][0], tab.n, tab.width, pat)
+            assert back.first_difference(tab) == -1, (name, pat)
+            back.free()
+        if i in (2, 5):
+            text = host.decode_device(ctx, st["dna"], st["qual"], st["cols"], cfg)
+            assert text.nbytes == dev.nbytes and text.first_difference(dev) == -1
+            text.free()
+        keep = {id(a) for a, _, _ in m.items.values()}
+        for a in [st["dna"], st["qual"]] + st["cols"]:
+            if id(a) not in keep:
+                a.free()
+        m.free()
+    dev.free()
+
+
+def test_config5_full_size_variable_length(ctx):
+    """1 M reads of 1-20 kb (12.7 GB of FASTQ, 5 GB + 17.5 GB tables), --sort QUAL: idempotence on the device."""
+    from oracle import synth
+    used, free, total = ctx.mem_info()
+    if total - used < 150 << 30:
+        pytest.skip("needs ~150 GB of free HBM")
+    tab = synth.ont_length_table(1000, 20000)
+    dev = ctx.synth("ont", 1_000_000, (1000, 20000), 1005, len_table=tab)
+    assert dev.nbytes > 8 << 30              # log-uniform lengths: about 12.7 GB of FASTQ, offsets far beyond 32 bits
+    m1, cfg, m2, text = _assert_idempotent(ctx, dev, sort="QUAL")
+    assert cfg["variable_read_lengths"] is True and cfg["reads"] == 1_000_000
+    key = m1.items["QUAL.key"][0].download(dtype=np.uint32)
+    assert np.all(key[1:] >= key[:-1])
+    m1.free(); m2.free(); text.free(); dev.free()
