@@ -23,10 +23,65 @@ __global__ void __launch_bounds__(ST) k_chunk0_keys(const uint8_t* __restrict__ 
     val[i] = (uint32_t)i;
 }
 
-__global__ void __launch_bounds__(ST) k_mark_heads(const uint64_t* __restrict__ key, uint64_t n, uint32_t* __restrict__ head) {
+// Wide rows (variable-length reads are right aligned: a read of half the maximum length starts with thousands of zero
+// bytes) are compared from their first non-zero byte: zoff[i] = number of leading zero bytes of row i (one warp per
+// row, 16-byte loads when the row is aligned).  memcmp order = fewer significant bytes first, then the significant
+// bytes, so round 0 sorts by (significant length, first 8 significant bytes) and the refinement rounds take their
+// 8-byte chunks relative to zoff; rows of one tie group always share their zoff.
+#define SORT_ZOFF_MIN_WIDTH 256
+__global__ void __launch_bounds__(ST) k_leading_zero_bytes(const uint8_t* __restrict__ rows, uint64_t n, uint32_t width,
+                                                          uint32_t* __restrict__ zoff) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t wstride = (uint64_t)gridDim.x * (ST / 32);
+    for (uint64_t i = (uint64_t)blockIdx.x * (ST / 32) + (threadIdx.x >> 5); i < n; i += wstride) {
+        const uint8_t* row = rows + i * width;
+        uint32_t z = width;
+        const uint32_t head = (uint32_t)((16u - ((uintptr_t)row & 15u)) & 15u);          // bytes before the first aligned unit
+        // unaligned head, byte by byte
+        for (uint32_t b0 = 0; b0 < head && b0 < width && z == width; b0 += 32) {
+            const uint32_t b = b0 + lane;
+            const bool nz = b < head && b < width && row[b] != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, nz);
+            if (m) z = b0 + (__ffs(m) - 1);
+        }
+        // aligned body, 16 bytes per lane
+        for (uint32_t b0 = head; b0 < width && z == width; b0 += 512) {
+            const uint32_t b = b0 + lane * 16;
+            uint32_t first = 16;
+            if (b + 16 <= width) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + b));
+                if (v.x) first = (__ffs(v.x) - 1) >> 3;
+                else if (v.y) first = 4 + ((__ffs(v.y) - 1) >> 3);
+                else if (v.z) first = 8 + ((__ffs(v.z) - 1) >> 3);
+                else if (v.w) first = 12 + ((__ffs(v.w) - 1) >> 3);
+            } else if (b < width) {
+                for (uint32_t k = 0; k < width - b; k++) if (row[b + k] != 0) { first = k; break; }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, first < 16);
+            if (m) {
+                const int src = __ffs(m) - 1;
+                z = b0 + src * 16 + __shfl_sync(0xffffffffu, first, src);
+            }
+        }
+        if (lane == 0) zoff[i] = z;
+    }
+}
+
+__global__ void __launch_bounds__(ST) k_chunk0_keys_z(const uint8_t* __restrict__ rows, uint64_t n, uint32_t width, const uint32_t* __restrict__ zoff,
+                                                     uint64_t* __restrict__ key, uint32_t* __restrict__ aux, uint32_t* __restrict__ val) {
+    uint64_t i = (uint64_t)blockIdx.x * ST + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t z = zoff[i], sig = width - z;
+    key[i] = load_be64(rows + i * width + z, sig < 8 ? sig : 8);
+    aux[i] = sig;                       // fewer significant bytes = more leading zeros = smaller row
+    val[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(ST) k_mark_heads(const uint64_t* __restrict__ key, const uint32_t* __restrict__ aux, uint64_t n,
+                                                  uint32_t* __restrict__ head) {
     uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
     if (p >= n) return;
-    head[p] = (p == 0 || key[p] != key[p - 1]) ? 1u : 0u;
+    head[p] = (p == 0 || key[p] != key[p - 1] || (aux && aux[p] != aux[p - 1])) ? 1u : 0u;
 }
 
 // gid[p] = excl[p] + head[p] - 1 ; headpos[gid] = p for heads
@@ -40,6 +95,7 @@ __global__ void __launch_bounds__(ST) k_headpos(const uint32_t* __restrict__ hea
 
 // a non-head member that differs from its group's first row in bytes [off, width) marks the group
 __global__ void __launch_bounds__(ST) k_group_diff(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
+                                                  const uint32_t* __restrict__ zoff,
                                                   const uint32_t* __restrict__ perm, const uint32_t* __restrict__ head,
                                                   const uint32_t* __restrict__ excl, const uint32_t* __restrict__ headpos,
                                                   const uint8_t* __restrict__ done, uint64_t n, uint32_t* __restrict__ gdiff) {
@@ -47,9 +103,12 @@ __global__ void __launch_bounds__(ST) k_group_diff(const uint8_t* __restrict__ r
     if (p >= n || head[p] || done[p]) return;
     uint32_t g = excl[p] - 1;           // inclusive scan - 1 with head[p] == 0
     if (gdiff[g]) return;
-    const uint8_t* a = rows + (uint64_t)perm[p] * width + off;
-    const uint8_t* b = rows + (uint64_t)perm[headpos[g]] * width + off;
-    for (uint32_t i = 0; i < width - off; i++) {
+    const uint32_t ra = perm[p], rb = perm[headpos[g]];
+    const uint32_t z = zoff ? zoff[ra] : 0u;          // the rows of a group share their zoff
+    if (z + off >= width) return;
+    const uint8_t* a = rows + (uint64_t)ra * width + z + off;
+    const uint8_t* b = rows + (uint64_t)rb * width + z + off;
+    for (uint32_t i = 0; i < width - z - off; i++) {
         if (__ldg(a + i) != __ldg(b + i)) { gdiff[g] = 1; return; }
     }
 }
@@ -264,12 +323,11 @@ __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__
 // Rows whose remainder is wider than SG_STAGE_BYTES: lane i ranks row i against the others straight from
 // global memory (rare: only very long variable-length reads get here).
 __global__ void __launch_bounds__(ST) k_small_groups_gmem(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
-                                                         uint32_t* __restrict__ perm, uint32_t* __restrict__ head, uint8_t* __restrict__ done,
+                                                         const uint32_t* __restrict__ zoff, uint32_t* __restrict__ perm, uint32_t* __restrict__ head, uint8_t* __restrict__ done,
                                                          const uint32_t* __restrict__ headpos, const uint32_t* __restrict__ d_ngroups,
                                                          unsigned long long* __restrict__ large_rows) {
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t G = *d_ngroups;
-    const uint32_t rem = width - off;
     const uint64_t warps_total = (uint64_t)gridDim.x * (ST / 32);
     unsigned long long my_large = 0;
     for (uint64_t g0 = ((uint64_t)blockIdx.x * (ST / 32) + w) * 32; g0 < G; g0 += warps_total * 32) {
@@ -284,14 +342,17 @@ __global__ void __launch_bounds__(ST) k_small_groups_gmem(const uint8_t* __restr
             need &= need - 1;
             const uint32_t s = __shfl_sync(0xffffffffu, start, src), sz = __shfl_sync(0xffffffffu, size, src);
             const uint32_t r = lane < sz ? perm[s + lane] : 0u;
+            // the rows of a group share their leading-zero count: compare from zoff + off
+            const uint32_t z = __shfl_sync(0xffffffffu, (zoff && lane < sz) ? zoff[r] : 0u, 0);
+            const uint32_t rem = z + off < width ? width - z - off : 0u;
             uint32_t rank = 0;
             bool eq_before = false;
             for (uint32_t j = 0; j < sz; j++) {
                 const uint32_t rj = __shfl_sync(0xffffffffu, r, j);
                 if (lane < sz && j != lane) {
                     int c = 0;       // memcmp(row_j, row_lane)
-                    const uint8_t* pa = rows + (uint64_t)rj * width + off;
-                    const uint8_t* pb = rows + (uint64_t)r * width + off;
+                    const uint8_t* pa = rows + (uint64_t)rj * width + z + off;
+                    const uint8_t* pb = rows + (uint64_t)r * width + z + off;
                     for (uint32_t i = 0; i < rem; i++) {
                         const unsigned a = __ldg(pa + i), b = __ldg(pb + i);
                         if (a != b) { c = a < b ? -1 : 1; break; }
@@ -315,7 +376,7 @@ __global__ void __launch_bounds__(ST) k_small_groups_gmem(const uint8_t* __restr
 }
 
 __global__ void __launch_bounds__(ST) k_compact_active(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
-                                                      const uint32_t* __restrict__ act, const uint32_t* __restrict__ apos,
+                                                      const uint32_t* __restrict__ zoff, const uint32_t* __restrict__ act, const uint32_t* __restrict__ apos,
                                                       const uint32_t* __restrict__ head, const uint32_t* __restrict__ excl,
                                                       const uint32_t* __restrict__ perm, uint64_t n, uint32_t* __restrict__ pos_list,
                                                       uint64_t* __restrict__ key, uint32_t* __restrict__ aux, uint32_t* __restrict__ val) {
@@ -324,8 +385,9 @@ __global__ void __launch_bounds__(ST) k_compact_active(const uint8_t* __restrict
     uint32_t j = apos[p];
     uint32_t row = perm[p];
     pos_list[j] = (uint32_t)p;
-    uint32_t rem = width - off;
-    key[j] = load_be64(rows + (uint64_t)row * width + off, rem < 8 ? rem : 8);
+    const uint32_t z = zoff ? zoff[row] : 0u;
+    const uint32_t rem = z + off < width ? width - z - off : 0u;
+    key[j] = load_be64(rows + (uint64_t)row * width + z + off, rem < 8 ? rem : 8);
     aux[j] = excl[p] + head[p] - 1;
     val[j] = row;
 }
@@ -372,12 +434,18 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
     UQB_TRY(uqb_dalloc_t(ctx, &d_tot, 2));
 
     // ---- round 0 ----
+    uint32_t* zoff = nullptr;
+    if (width > SORT_ZOFF_MIN_WIDTH) {
+        UQB_TRY(uqb_dalloc_t(ctx, &zoff, n));
+        UQB_LAUNCH_B(n * 4, k_leading_zero_bytes, uqb_grid(ctx, n, ST / 32, 16), ST, 0, rows, n, width, zoff);
+    }
     {
         uqb_sortbuf sb;
-        UQB_TRY(uqb_sortbuf_alloc(ctx, &sb, n, false));
-        UQB_LAUNCH_B(n * ((width < 8 ? width : 8) + 12), k_chunk0_keys, nb, ST, 0, rows, n, width, sb.key[0], sb.val[0]);
-        UQB_TRY(uqb_radix_sort(ctx, &sb, n, false));
-        UQB_LAUNCH(k_mark_heads, nb, ST, 0, sb.key[sb.cur], n, head);
+        UQB_TRY(uqb_sortbuf_alloc(ctx, &sb, n, zoff != nullptr));
+        if (zoff) UQB_LAUNCH_B(n * 24, k_chunk0_keys_z, nb, ST, 0, rows, n, width, zoff, sb.key[0], sb.aux[0], sb.val[0]);
+        else UQB_LAUNCH_B(n * ((width < 8 ? width : 8) + 12), k_chunk0_keys, nb, ST, 0, rows, n, width, sb.key[0], sb.val[0]);
+        UQB_TRY(uqb_radix_sort(ctx, &sb, n, zoff != nullptr));
+        UQB_LAUNCH(k_mark_heads, nb, ST, 0, sb.key[sb.cur], zoff ? sb.aux[sb.cur] : (const uint32_t*)nullptr, n, head);
         UQB_CUDA(cudaMemcpyAsync(perm, sb.val[sb.cur], n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         UQB_TRY(uqb_sortbuf_free(ctx, &sb));
     }
@@ -402,7 +470,7 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
             UQB_CUDA(cudaMemsetAsync(d_large, 0, 8, ctx->stream));
             const uint32_t rem = width - off;
             const unsigned sg_grid = uqb_grid(ctx, n, ST, 16);
-            if (rem <= SG_STAGE_BYTES) {
+            if (rem <= SG_STAGE_BYTES && !zoff) {
                 const uint32_t pitch = (rem + 3) / 4;
                 const size_t smem = (size_t)(ST / 32) * (SG_MAX * pitch + 64) * 4;
                 static const char* la_env = getenv("UQB_SG_LOOKAHEAD");
@@ -423,14 +491,14 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
                     UQB_LAUNCH(k_small_groups_64, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, la, d_large);
                 }
             } else {
-                UQB_LAUNCH(k_small_groups_gmem, sg_grid, ST, 0, rows, width, off, perm, head, done, headpos, d_tot, d_large);
+                UQB_LAUNCH(k_small_groups_gmem, sg_grid, ST, 0, rows, width, off, zoff, perm, head, done, headpos, d_tot, d_large);
             }
             unsigned long long large = 0;
             UQB_TRY(uqb_readback(ctx, &large, d_large, 8));
             if (large == 0) break;                                 // no tie group of more than 32 rows is left
             // large tie groups: all-equal check, then one more 8-byte radix round over the still active rows
             UQB_CUDA(cudaMemsetAsync(gdiff, 0, n * 4, ctx->stream));
-            UQB_LAUNCH(k_group_diff, nb, ST, 0, rows, width, off, perm, head, excl, headpos, done, n, gdiff);
+            UQB_LAUNCH(k_group_diff, nb, ST, 0, rows, width, off, zoff, perm, head, excl, headpos, done, n, gdiff);
             UQB_LAUNCH(k_active_flags, nb, ST, 0, head, excl, gdiff, done, n, act);
             UQB_TRY(uqb_scan_u32(ctx, act, apos, n, d_tot + 1));
             uint32_t tot[2];
@@ -441,7 +509,7 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
             uint32_t* pos_list;
             UQB_TRY(uqb_sortbuf_alloc(ctx, &sb, m, true));
             UQB_TRY(uqb_dalloc_t(ctx, &pos_list, m));
-            UQB_LAUNCH_B(n * 8 + m * 32, k_compact_active, nb, ST, 0, rows, width, off, act, apos, head, excl, perm, n, pos_list, sb.key[0], sb.aux[0], sb.val[0]);
+            UQB_LAUNCH_B(n * 8 + m * 32, k_compact_active, nb, ST, 0, rows, width, off, zoff, act, apos, head, excl, perm, n, pos_list, sb.key[0], sb.aux[0], sb.val[0]);
             UQB_TRY(uqb_radix_sort(ctx, &sb, m, true));
             UQB_LAUNCH_B(m * 28, k_write_back, uqb_blocks(m, ST), ST, 0, sb.key[sb.cur], sb.aux[sb.cur], sb.val[sb.cur], pos_list, m, perm, head);
             UQB_TRY(uqb_dfree(ctx, pos_list, m * 4));
@@ -454,6 +522,7 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
         UQB_TRY(uqb_dfree(ctx, done, n));
         UQB_TRY(uqb_dfree(ctx, d_large, 8));
     }
+    if (zoff) UQB_TRY(uqb_dfree(ctx, zoff, n * 4));
     // ---- group ids in sorted order ----
     UQB_TRY(uqb_scan_u32(ctx, head, excl, n, d_tot));
     UQB_LAUNCH(k_gid_from_scan, nb, ST, 0, head, excl, n);
