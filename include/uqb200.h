@@ -200,6 +200,14 @@ int uqb_rows_lower_bound(uqb_ctx* ctx, const uqb_array* sorted_table, const uint
  * by destination (stable), counts_host[0..nsplit] = rows per destination */
 int uqb_partition_rows(uqb_ctx* ctx, const uqb_array* table, const uint64_t* split_keys_host, uint32_t nsplit,
                        uqb_array** order, uint64_t* counts_host);
+/* exchange buffers of the sample sort: the rows of segment d (order[first_d .. first_d + seg_counts[d])) gathered into a
+ * byte array in which every segment starts at a multiple of `align` bytes (NCCL moves 16 bytes per thread only between
+ * 16-byte aligned pointers); seg_offsets_host receives the byte offset of every segment */
+int uqb_gather_rows_segmented(uqb_ctx* ctx, const uqb_array* table, const uqb_array* order, uint32_t nseg,
+                              const uint64_t* seg_counts_host, uint32_t align, uqb_array** out, uint64_t* seg_offsets_host);
+/* the inverse on the receiving side: byte array with aligned segments -> dense table of `width`-byte rows */
+int uqb_compact_segments(uqb_ctx* ctx, const uqb_array* padded, uint32_t nseg, const uint64_t* seg_offsets_host,
+                         const uint64_t* seg_counts_host, uint32_t width, uqb_array** out);
 /* out[idx[j]] = src[j], uint32 arrays, idx a permutation (inverse of uqb_gather_rows) */
 int uqb_scatter_u32(uqb_ctx* ctx, const uqb_array* src, const uqb_array* idx, uqb_array** out);
 /* uint32 -> little-endian integer of itemsize bytes (key.astype(min_scalar_type(max)), uq.py:790) */

@@ -869,6 +869,51 @@ extern "C" int uqb_partition_rows(uqb_ctx* ctx, const uqb_array* table, const ui
     return 0;
 }
 
+// Row exchange buffers: NCCL's send/recv path only moves 16 bytes per thread when both user pointers are 16-byte
+// aligned, and the per-peer segments of a table of 113-byte rows start anywhere.  The rows of segment d
+// (order[first_d .. first_d + count_d)) are therefore gathered into a byte buffer in which every segment starts at a
+// multiple of `align` bytes; the receiver uses the same layout and closes the gaps afterwards (uqb_compact_segments).
+static inline uint64_t seg_round(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int uqb_gather_rows_segmented(uqb_ctx* ctx, const uqb_array* table, const uqb_array* order, uint32_t nseg,
+                                         const uint64_t* seg_counts_host, uint32_t align, uqb_array** out, uint64_t* seg_offsets_host) {
+    if (order->width != 4) return uqb_fail(ctx, "gather_rows_segmented: index array must be uint32");
+    if (align == 0 || (align & 3u)) return uqb_fail(ctx, "gather_rows_segmented: alignment must be a multiple of 4");
+    const uint32_t w = table->width;
+    uint64_t total = 0, rows = 0;
+    for (uint32_t d = 0; d < nseg; d++) {
+        seg_offsets_host[d] = total;
+        total = seg_round(total + seg_counts_host[d] * w, align);
+        rows += seg_counts_host[d];
+    }
+    if (rows != order->n) return uqb_fail(ctx, "gather_rows_segmented: the segments hold %llu rows, the index array %llu",
+                                          (unsigned long long)rows, (unsigned long long)order->n);
+    UQB_TRY(uqb_new_array(ctx, total, 1, out));
+    uint64_t first = 0;
+    for (uint32_t d = 0; d < nseg; d++) {
+        UQB_TRY(gather_rows_impl(ctx, table->d, w, (const uint32_t*)order->d + first, seg_counts_host[d], (uint8_t*)(*out)->d + seg_offsets_host[d]));
+        first += seg_counts_host[d];
+    }
+    return 0;
+}
+
+// byte buffer with aligned segments (seg_offsets, seg_counts rows of `width` bytes each) -> dense table
+extern "C" int uqb_compact_segments(uqb_ctx* ctx, const uqb_array* padded, uint32_t nseg, const uint64_t* seg_offsets_host,
+                                    const uint64_t* seg_counts_host, uint32_t width, uqb_array** out) {
+    uint64_t rows = 0;
+    for (uint32_t d = 0; d < nseg; d++) rows += seg_counts_host[d];
+    UQB_TRY(uqb_new_array(ctx, rows, width, out));
+    uint64_t first = 0;
+    for (uint32_t d = 0; d < nseg; d++) {
+        const uint64_t nb = seg_counts_host[d] * width;
+        if (seg_offsets_host[d] + nb > padded->nbytes()) return uqb_fail(ctx, "compact_segments: segment %u exceeds the buffer", d);
+        if (nb) UQB_CUDA(cudaMemcpyAsync((uint8_t*)(*out)->d + first * width, (const uint8_t*)padded->d + seg_offsets_host[d], nb,
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+        first += seg_counts_host[d];
+    }
+    return 0;
+}
+
 __global__ void __launch_bounds__(ST) k_scatter_u32(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t n,
                                                    uint32_t* __restrict__ out) {
     for (uint64_t j = (uint64_t)blockIdx.x * ST + threadIdx.x; j < n; j += (uint64_t)gridDim.x * ST) out[idx[j]] = src[j];

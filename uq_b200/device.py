@@ -123,6 +123,23 @@ class Context:
         self.check(self.lib.uqb_partition_rows(self.h, table.h, _ptr(keys), len(keys), C.byref(h), _ptr(counts)))
         return DeviceArray(self, h), [int(c) for c in counts]
 
+    def gather_rows_segmented(self, table, order, seg_counts, align=128):
+        """rows table[order[...]] gathered segment by segment into a byte array whose segments start at multiples of
+        `align` bytes -> (DeviceArray of bytes, byte offset of every segment)"""
+        counts = np.ascontiguousarray(seg_counts, dtype=np.uint64)
+        offs = np.zeros(len(counts), dtype=np.uint64)
+        h = C.c_void_p()
+        self.check(self.lib.uqb_gather_rows_segmented(self.h, table.h, order.h, len(counts), _ptr(counts), int(align), C.byref(h), _ptr(offs)))
+        return DeviceArray(self, h), [int(o) for o in offs]
+
+    def compact_segments(self, padded, seg_offsets, seg_counts, width):
+        """byte array with aligned segments -> dense table [sum(seg_counts)][width]"""
+        offs = np.ascontiguousarray(seg_offsets, dtype=np.uint64)
+        counts = np.ascontiguousarray(seg_counts, dtype=np.uint64)
+        h = C.c_void_p()
+        self.check(self.lib.uqb_compact_segments(self.h, padded.h, len(counts), _ptr(offs), _ptr(counts), int(width), C.byref(h)))
+        return DeviceArray(self, h)
+
     def scatter_u32(self, src, idx):
         """out[idx[j]] = src[j] (uint32 arrays, idx a permutation)"""
         h = C.c_void_p()
