@@ -148,19 +148,11 @@ __global__ void __launch_bounds__(ST) k_active_flags(const uint32_t* __restrict_
 // The first pass (pivot = first row of the group) is fused with the staging: the pivot's words stay in
 // registers and every row is compared with them the moment it arrives, so a group of identical rows is
 // finished without reading shared memory at all.
-__device__ __forceinline__ void sg_prefetch(const uint8_t* rows, uint32_t width, uint32_t off, uint32_t rem, const uint32_t* perm,
-                                            uint32_t st, uint32_t szz, unsigned lane) {
-    for (uint32_t t = lane & 3u; t < szz; t += 4) {
-        const uint64_t A = (uint64_t)(uintptr_t)rows + (uint64_t)perm[st + t] * width + off;
-        for (uint64_t q = A & ~31ull; q < A + rem; q += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-    }
-}
-
 template <int SUB, int TRIPS>      // TRIPS = ceil(pitch / SUB): 1, or 2 for SUB == 32 and 33..64 words
 __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
                                                     uint32_t* __restrict__ perm, uint32_t* __restrict__ head, uint8_t* __restrict__ done,
                                                     const uint32_t* __restrict__ headpos, const uint32_t* __restrict__ d_ngroups,
-                                                    uint32_t pitch, uint32_t lookahead, unsigned long long* __restrict__ large_rows) {
+                                                    uint32_t pitch, unsigned long long* __restrict__ large_rows) {
     extern __shared__ uint32_t sg_smem[];
     constexpr uint32_t NP = 32u / SUB;
     constexpr uint32_t SUBMASK = SUB == 32 ? 0xffffffffu : ((1u << (SUB & 31)) - 1u);
@@ -190,25 +182,9 @@ __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__
         const bool fin = size >= 2 && done[start];
         if (size > SG_MAX && !fin) my_large += size;
         unsigned need = __ballot_sync(0xffffffffu, size >= 2 && size <= SG_MAX && !fin);
-        // The rows of a group sit at random places of the table, and a warp works on one group at a time:
-        // optionally the rows of the NEXT eight groups are prefetched into L2 (four lanes per group) while the
-        // current eight are sorted.
-        const unsigned need_all = need;
-        unsigned fetched = 4u;
-        if (lookahead) {
-            const uint32_t st = __shfl_sync(0xffffffffu, start, lane >> 2), szz = __shfl_sync(0xffffffffu, size, lane >> 2);
-            if ((need_all >> (lane >> 2)) & 1u) sg_prefetch(rows, width, off, rem, perm, st, szz, lane);
-            fetched = 1u;
-        }
         while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
-            while (fetched < 4u && fetched <= ((unsigned)src >> 3) + 1u) {      // stay one sub-batch ahead
-                const unsigned gi = 8u * fetched + (lane >> 2);
-                const uint32_t st = __shfl_sync(0xffffffffu, start, gi), szz = __shfl_sync(0xffffffffu, size, gi);
-                if ((need_all >> gi) & 1u) sg_prefetch(rows, width, off, rem, perm, st, szz, lane);
-                fetched++;
-            }
             const uint32_t s = __shfl_sync(0xffffffffu, start, src), sz = __shfl_sync(0xffffffffu, size, src);
             const uint32_t r = lane < sz ? perm[s + lane] : 0u;
             // ---- stage, and compare with the first row ----
@@ -473,22 +449,20 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
             if (rem <= SG_STAGE_BYTES && !zoff) {
                 const uint32_t pitch = (rem + 3) / 4;
                 const size_t smem = (size_t)(ST / 32) * (SG_MAX * pitch + 64) * 4;
-                static const char* la_env = getenv("UQB_SG_LOOKAHEAD");
-                const uint32_t la = la_env ? (uint32_t)atoi(la_env) : 0u;
                 if (pitch <= 8) {
                     auto k_small_groups_8 = k_small_groups<8, 1>;
-                    UQB_LAUNCH(k_small_groups_8, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, la, d_large);
+                    UQB_LAUNCH(k_small_groups_8, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
                 } else if (pitch <= 16) {
                     auto k_small_groups_16 = k_small_groups<16, 1>;
-                    UQB_LAUNCH(k_small_groups_16, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, la, d_large);
+                    UQB_LAUNCH(k_small_groups_16, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
                 } else if (pitch <= 32) {
                     auto k_small_groups_32 = k_small_groups<32, 1>;
                     UQB_CUDA(cudaFuncSetAttribute(k_small_groups_32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    UQB_LAUNCH(k_small_groups_32, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, la, d_large);
+                    UQB_LAUNCH(k_small_groups_32, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
                 } else {
                     auto k_small_groups_64 = k_small_groups<32, 2>;
                     UQB_CUDA(cudaFuncSetAttribute(k_small_groups_64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    UQB_LAUNCH(k_small_groups_64, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, la, d_large);
+                    UQB_LAUNCH(k_small_groups_64, sg_grid, ST, smem, rows, width, off, perm, head, done, headpos, d_tot, pitch, d_large);
                 }
             } else {
                 UQB_LAUNCH(k_small_groups_gmem, sg_grid, ST, 0, rows, width, off, zoff, perm, head, done, headpos, d_tot, d_large);
@@ -748,6 +722,70 @@ __global__ void __launch_bounds__(ST) k_rows_to_cols(col_desc_out cd, uint64_t n
     }
 }
 
+// Rows of up to CR_MAXW bytes: one thread per ROW.  Column values are read / written with typed, coalesced
+// accesses, the rows of the CTA pass through shared memory, and the row table side is one contiguous range moved
+// as 32-bit words.
+#define CR_MAXW 64
+template <typename T>
+__device__ __forceinline__ unsigned long long cr_load(const uint8_t* p, uint64_t r) { return (unsigned long long)reinterpret_cast<const T*>(p)[r]; }
+
+__global__ void __launch_bounds__(ST) k_cols_to_rows_staged(col_desc cd, uint64_t n, uint8_t* __restrict__ rows) {
+    __shared__ __align__(16) uint8_t stage[ST * CR_MAXW];
+    const uint64_t nblk = (n + ST - 1) / ST;
+    for (uint64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const uint64_t r0 = blk * ST, r = r0 + threadIdx.x;
+        const uint32_t nr = (uint32_t)(n - r0 < ST ? n - r0 : ST);
+        __syncthreads();
+        if (r < n) {
+            uint8_t* dst = stage + threadIdx.x * cd.width;
+            for (uint32_t c = 0; c < cd.ncols; c++) {
+                const uint32_t sz = cd.size[c];
+                const unsigned long long v = sz == 1 ? cr_load<uint8_t>(cd.p[c], r) : sz == 2 ? cr_load<uint16_t>(cd.p[c], r)
+                                           : sz == 4 ? cr_load<uint32_t>(cd.p[c], r) : cr_load<uint64_t>(cd.p[c], r);
+                for (uint32_t b = 0; b < sz; b++) dst[cd.off[c] + b] = (uint8_t)(v >> (8 * (sz - 1 - b)));   // big-endian key bytes
+            }
+        }
+        __syncthreads();
+        const uint32_t total = nr * cd.width;
+        uint8_t* out = rows + r0 * cd.width;                                  // ST * width bytes per block: 4-byte aligned
+        for (uint32_t k = threadIdx.x; k < (total >> 2); k += ST) reinterpret_cast<uint32_t*>(out)[k] = reinterpret_cast<const uint32_t*>(stage)[k];
+        if (threadIdx.x < (total & 3u)) out[(total & ~3u) + threadIdx.x] = stage[(total & ~3u) + threadIdx.x];
+    }
+}
+
+__global__ void __launch_bounds__(ST) k_rows_to_cols_staged(col_desc_out cd, uint64_t n, const uint8_t* __restrict__ rows) {
+    __shared__ __align__(16) uint8_t stage[ST * CR_MAXW];
+    const uint64_t nblk = (n + ST - 1) / ST;
+    for (uint64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const uint64_t r0 = blk * ST, r = r0 + threadIdx.x;
+        const uint32_t nr = (uint32_t)(n - r0 < ST ? n - r0 : ST);
+        const uint32_t total = nr * cd.width;
+        const uint8_t* in = rows + r0 * cd.width;
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < (total >> 2); k += ST) reinterpret_cast<uint32_t*>(stage)[k] = reinterpret_cast<const uint32_t*>(in)[k];
+        if (threadIdx.x < (total & 3u)) stage[(total & ~3u) + threadIdx.x] = in[(total & ~3u) + threadIdx.x];
+        __syncthreads();
+        if (r < n) {
+            const uint8_t* src = stage + threadIdx.x * cd.width;
+            for (uint32_t c = 0; c < cd.ncols; c++) {
+                const uint32_t sz = cd.size[c];
+                unsigned long long v = 0;
+                for (uint32_t b = 0; b < sz; b++) v = (v << 8) | src[cd.off[c] + b];
+                if (sz == 1) reinterpret_cast<uint8_t*>(cd.p[c])[r] = (uint8_t)v;
+                else if (sz == 2) reinterpret_cast<uint16_t*>(cd.p[c])[r] = (uint16_t)v;
+                else if (sz == 4) reinterpret_cast<uint32_t*>(cd.p[c])[r] = (uint32_t)v;
+                else reinterpret_cast<uint64_t*>(cd.p[c])[r] = v;
+            }
+        }
+    }
+}
+
+static bool cr_staged_ok(const uint32_t* sizes, uint32_t ncols, uint32_t width, const void* rows) {
+    if (width > CR_MAXW || (reinterpret_cast<uintptr_t>(rows) & 3u)) return false;
+    for (uint32_t c = 0; c < ncols; c++) if (sizes[c] != 1 && sizes[c] != 2 && sizes[c] != 4 && sizes[c] != 8) return false;
+    return true;
+}
+
 extern "C" int uqb_columns_to_rows(uqb_ctx* ctx, uint32_t ncols, uqb_array* const* cols, uqb_array** rows) {
     if (ncols == 0 || ncols > UQB_MAX_COLS) return uqb_fail(ctx, "columns_to_rows: bad column count %u", ncols);
     col_desc cd;
@@ -760,7 +798,8 @@ extern "C" int uqb_columns_to_rows(uqb_ctx* ctx, uint32_t ncols, uqb_array* cons
     }
     cd.width = w;
     UQB_TRY(uqb_new_array(ctx, n, w, rows));
-    if (n) UQB_LAUNCH(k_cols_to_rows, uqb_grid(ctx, n * ncols, ST, 16), ST, 0, cd, n, (uint8_t*)(*rows)->d);
+    if (n && cr_staged_ok(cd.size, ncols, w, (*rows)->d)) UQB_LAUNCH_B(2 * n * w, k_cols_to_rows_staged, uqb_grid(ctx, n, ST, 16), ST, 0, cd, n, (uint8_t*)(*rows)->d);
+    else if (n) UQB_LAUNCH(k_cols_to_rows, uqb_grid(ctx, n * ncols, ST, 16), ST, 0, cd, n, (uint8_t*)(*rows)->d);
     return 0;
 }
 
@@ -775,7 +814,8 @@ extern "C" int uqb_rows_to_columns(uqb_ctx* ctx, const uqb_array* rows, uint32_t
     }
     cd.width = w;
     if (w != rows->width) return uqb_fail(ctx, "rows_to_columns: widths sum to %u, rows are %u wide", w, rows->width);
-    if (rows->n) UQB_LAUNCH(k_rows_to_cols, uqb_grid(ctx, rows->n * ncols, ST, 16), ST, 0, cd, rows->n, (const uint8_t*)rows->d);
+    if (rows->n && cr_staged_ok(cd.size, ncols, w, rows->d)) UQB_LAUNCH_B(2 * rows->n * w, k_rows_to_cols_staged, uqb_grid(ctx, rows->n, ST, 16), ST, 0, cd, rows->n, (const uint8_t*)rows->d);
+    else if (rows->n) UQB_LAUNCH(k_rows_to_cols, uqb_grid(ctx, rows->n * ncols, ST, 16), ST, 0, cd, rows->n, (const uint8_t*)rows->d);
     return 0;
 }
 
