@@ -660,6 +660,126 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_pair_hist_tiles(const uint8_t
     }
 }
 
+// Long reads (records that do not fit a tile): the same counters, fed straight from global memory.  One warp per
+// record; a lane takes aligned 16-byte units of the DNA line and, separately, of the QUAL line (the two lines have
+// different alignments, and counting does not need them paired).  Only a base that still carries the CHECK bit needs
+// its own quality: that single byte is fetched on the spot.  Same shared-memory layout as the tile kernel (the tile
+// area is simply unused), same flush rules: at most 15 units (240 increments of one 8-bit field) between flushes.
+__device__ __forceinline__ void pt_long_base(pt_smem* S, const uint8_t* __restrict__ d, uint64_t qbase, uint64_t pos0, unsigned b, unsigned k,
+                                             uint32_t lutb_a, uint32_t state_a, unsigned& cur, unsigned& pa, unsigned& pb) {
+    const uint2 e = lds_u64(lutb_a + (b << 3));
+    const unsigned dd = (e.y ^ cur) & PT_GMASK;
+    if (dd) {
+        unsigned q = 0;
+        if (e.y & PT_CHECK) q = __ldg(d + qbase + pos0 + k);                 // quality of this very position
+        if (dd != PT_CHECK || lds_u32(state_a + (b << 2)) != q) {
+            const uint3 r = pt_base_slow(S, b, q, e.y, cur, pa, pb);
+            cur = r.x; pa = r.y; pb = r.z;
+        }
+    }
+    pa += e.x;
+    pb += e.y;
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 1) k_pair_hist_long(const uint8_t* __restrict__ d, const uint64_t* __restrict__ line_off,
+                                                                 uint64_t r_begin, uint64_t n_reads, an_dev* __restrict__ s,
+                                                                 unsigned int* __restrict__ fallback) {
+    extern __shared__ __align__(128) uint8_t pt_raw[];
+    pt_smem* S = reinterpret_cast<pt_smem*>(pt_raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    for (unsigned i = tid; i < PT_WORDS * PT_THREADS; i += PT_THREADS) S->priv_q[i] = 0;
+    for (unsigned i = tid; i < PT_LO + 4 * PT_WORDS; i += PT_THREADS) S->hist_q[i] = 0;
+    for (unsigned i = tid; i < PT_GROUPS * 8; i += PT_THREADS) S->rev[i] = 0;
+    if (tid < 256) { S->hist_b[tid] = 0; S->state[tid] = -1; }
+    __syncthreads();
+    if (tid < 256) {
+        const unsigned v = tid;
+        unsigned grp, field;
+        pt_base_group(v, &grp, &field);
+        S->lutb[v] = make_uint2(field < 4 ? 1u << (8 * field) : 0u, ((grp << 24) | PT_CHECK) | (field >= 4 ? 1u << (8 * (field - 4)) : 0u));
+        S->rev[grp * 8 + field] = (uint8_t)v;
+        const unsigned idx = min(v - PT_LO, PT_OOR);
+        const unsigned word = idx < 96u ? idx % 24u : 24u, qf = idx < 96u ? idx / 24u : 0u;
+        S->lutq[v] = make_uint2(word * PT_ROW, 1u << (8 * qf));
+    }
+    __syncthreads();
+    const uint32_t pq_a = smem_u32(S->priv_q + tid);
+    const uint32_t lutb_a = smem_u32(S->lutb), lutq_a = smem_u32(S->lutq), state_a = smem_u32(S->state);
+    unsigned cur = PT_NONE, pa = 0, pb = 0, since_flush = 0;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (PT_THREADS / 32);
+    for (uint64_t r = r_begin + (uint64_t)blockIdx.x * (PT_THREADS / 32) + wid; r < n_reads; r += nwarps) {
+        const uint64_t o1 = line_off[4 * r + 1], o2 = line_off[4 * r + 2], o3 = line_off[4 * r + 3], o4 = line_off[4 * r + 4];
+        uint64_t len = o2 - o1 - 1;
+        const uint64_t qlen = o4 - o3 - 1;
+        if (qlen < len) len = qlen;                  // malformed records are reported by the record-stats kernel
+        // the two lines as ranges of aligned 16-byte units
+        for (int line = 0; line < 2; line++) {
+            const uint64_t b0 = line == 0 ? o1 : o3, b1 = b0 + len;
+            const uint64_t u0 = b0 >> 4, u1 = (b1 + 15) >> 4;
+            for (uint64_t ub = u0; ub < u1; ub += 32) {              // warp-uniform trip count
+                if (since_flush >= 15u) {
+                    pt_flush(S->priv_q, S->hist_q, tid);
+                    pt_base_flush_warp(S, cur, pa, pb, lane);
+                    since_flush = 0;
+                }
+                since_flush++;
+                const uint64_t u = ub + lane;
+                if (u < u1) {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(d) + u);
+                    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+                    const uint64_t p0 = u << 4;
+                    const bool inner = p0 >= b0 && p0 + 16 <= b1;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        if (inner || (p0 + k >= b0 && p0 + k < b1)) {
+                            const unsigned c = (w[k >> 2] >> (8 * (k & 3))) & 255u;
+                            if (line == 0) {
+                                pt_long_base(S, d, o3, p0 - o1, c, (unsigned)k, lutb_a, state_a, cur, pa, pb);
+                            } else {
+                                const uint2 e = lds_u64(lutq_a + (c << 3));
+                                const uint32_t wq = pq_a + e.x;
+                                sts_u32(wq, lds_u32(wq) + e.y);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    pt_flush(S->priv_q, S->hist_q, tid);
+    pt_base_flush(S, cur, pa, pb);
+    __syncthreads();
+    if (tid < 256) {
+        if (S->hist_b[tid]) atomicAdd(&s->base_count[tid], (unsigned long long)S->hist_b[tid]);
+        if (tid < 128 && S->hist_q[tid]) atomicAdd(&s->qual_count[tid], (unsigned long long)S->hist_q[tid]);
+        if (tid == 0 && S->hist_q[PT_LO + PT_OOR]) atomicOr(fallback, 1u);
+        const int f = S->state[tid];
+        if (f >= 0) {
+            if (f == 256) {
+                s->multi[tid] = 1;
+                atomicCAS(&s->first_q[tid], -1, 0);                 // mark the base as present
+            } else {
+                const int old = atomicCAS(&s->first_q[tid], -1, f);
+                if (old >= 0 && old != f) s->multi[tid] = 1;
+            }
+        }
+    }
+}
+
+// long reads: names-only record statistics + the direct histogram above
+static int stats_long_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsigned int* d_fb, uint32_t flen, uint64_t r0, uint64_t r1) {
+    if (r1 <= r0) return 0;
+    UQB_CUDA(cudaFuncSetAttribute(k_pair_hist_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pt_smem)));
+    UQB_LAUNCH_B((r1 - r0) * 128, k_record_stats_names, uqb_grid(ctx, r1 - r0, RD_THREADS, 8), RD_THREADS, sizeof(rd_smem), fq->d, fq->line_off, r0, r1,
+                 fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb);
+    const uint64_t ab = (uint64_t)((double)fq->n * (double)(r1 - r0) / (double)(fq->n_reads ? fq->n_reads : 1)) + 32 * (r1 - r0);
+    const uint64_t warps = (r1 - r0 + 0) ;
+    const unsigned g = (unsigned)((warps + PT_THREADS / 32 - 1) / (PT_THREADS / 32) < (uint64_t)ctx->sm_count ? (warps + PT_THREADS / 32 - 1) / (PT_THREADS / 32)
+                                                                                                           : (uint64_t)ctx->sm_count);
+    UQB_LAUNCH_B(ab, k_pair_hist_long, g, PT_THREADS, sizeof(pt_smem), fq->d, fq->line_off, r0, r1, s, d_fb);
+    return 0;
+}
+
 // launches the two tile kernels over records [r0, r1)
 static int stats_tiles_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsigned int* d_fb, uint32_t flen, uint64_t r0, uint64_t r1) {
     if (r1 <= r0) return 0;
@@ -771,6 +891,17 @@ extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
         UQB_CUDA(cudaMemsetAsync(d_fb, 0, 4, ctx->stream));
         UQB_LAUNCH(k_an_init, 1, 256, 0, s);
         UQB_TRY(stats_tiles_range(ctx, fq, s, d_fb, (uint32_t)flen, 0, N));
+        unsigned int fb = 0;
+        UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
+        UQB_TRY(uqb_dfree(ctx, d_fb, 4));
+        done_fast = fb == 0;
+    } else if ((((uintptr_t)fq->d) & 15) == 0) {
+        // long reads: the same counters straight from global memory
+        unsigned int* d_fb;
+        UQB_TRY(uqb_dalloc_t(ctx, &d_fb, 1));
+        UQB_CUDA(cudaMemsetAsync(d_fb, 0, 4, ctx->stream));
+        UQB_LAUNCH(k_an_init, 1, 256, 0, s);
+        UQB_TRY(stats_long_range(ctx, fq, s, d_fb, (uint32_t)flen, 0, N));
         unsigned int fb = 0;
         UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
         UQB_TRY(uqb_dfree(ctx, d_fb, 4));
