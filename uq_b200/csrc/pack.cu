@@ -55,7 +55,7 @@ __device__ __forceinline__ unsigned pack_byte(const uint8_t* __restrict__ sym_sr
 
 __global__ void __launch_bounds__(PK_THREADS) k_pack_rows(const uint8_t* __restrict__ d, const uint64_t* __restrict__ line_off,
                                                          uint64_t n_reads, pack_lut lut_in, uint32_t bb, uint32_t bq,
-                                                         uint32_t wd, uint32_t wq, uint32_t variable, uint32_t dna_max,
+                                                         uint32_t wd, uint32_t wq, uint32_t variable, uint32_t dna_max, uint32_t prefilled,
                                                          uint8_t* __restrict__ dna_out, uint8_t* __restrict__ qual_out,
                                                          unsigned long long* __restrict__ err_record) {
     __shared__ pack_lut lut;
@@ -79,10 +79,12 @@ __global__ void __launch_bounds__(PK_THREADS) k_pack_rows(const uint8_t* __restr
         const uint8_t* qual = d + o3;
         uint8_t* drow = dna_out + r * wd;
         uint8_t* qrow = qual_out + r * wq;
-        for (uint32_t j = lane; j < wd + wq; j += 32) {
-            if (j < wd) drow[j] = (uint8_t)pack_byte(dna, dna, false, &lut, bb, variable, len, wd, j);
-            else        qrow[j - wd] = (uint8_t)pack_byte(qual, dna, true, &lut, bq, variable, len, wq, j - wd);
-        }
+        // Variable-length rows are right aligned: everything before the marker's byte is zero.  The host has zeroed
+        // both tables with one memset, so only the significant bytes are produced here.
+        const uint32_t jd0 = prefilled ? (wd * 8u - (len + variable) * bb) >> 3 : 0u;
+        const uint32_t jq0 = prefilled ? (wq * 8u - (len + variable) * bq) >> 3 : 0u;
+        for (uint32_t j = jd0 + lane; j < wd; j += 32) drow[j] = (uint8_t)pack_byte(dna, dna, false, &lut, bb, variable, len, wd, j);
+        for (uint32_t j = jq0 + lane; j < wq; j += 32) qrow[j] = (uint8_t)pack_byte(qual, dna, true, &lut, bq, variable, len, wq, j);
     }
 }
 
@@ -308,8 +310,13 @@ extern "C" int uqb_pack(uqb_ctx* ctx, uqb_fastq* fq, const uqb_pack_params* p, u
     unsigned long long* d_err;
     UQB_TRY(uqb_dalloc_t(ctx, &d_err, 1));
     UQB_CUDA(cudaMemsetAsync(d_err, 0xFF, 8, ctx->stream));
+    const uint32_t prefilled = p->variable ? 1u : 0u;
+    if (prefilled) {                                   // right-aligned rows: zero both tables at memset speed first
+        UQB_CUDA(cudaMemsetAsync((*dna)->d, 0, N * (uint64_t)p->dna_bytes, ctx->stream));
+        UQB_CUDA(cudaMemsetAsync((*qual)->d, 0, N * (uint64_t)p->qual_bytes, ctx->stream));
+    }
     UQB_LAUNCH_B(abytes, k_pack_rows, uqb_grid(ctx, N, PK_THREADS / 32, 16), PK_THREADS, 0, fq->d, fq->line_off, N, lut,
-               p->bits_per_base, p->bits_per_quality, p->dna_bytes, p->qual_bytes, p->variable, p->dna_max,
+               p->bits_per_base, p->bits_per_quality, p->dna_bytes, p->qual_bytes, p->variable, p->dna_max, prefilled,
                (uint8_t*)(*dna)->d, (uint8_t*)(*qual)->d, d_err);
     unsigned long long err;
     UQB_TRY(uqb_readback(ctx, &err, d_err, 8));
