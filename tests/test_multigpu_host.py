@@ -128,3 +128,69 @@ def test_object_collectives_over_gloo():
     assert all(p.exitcode == 0 for p in procs)
     assert layout == ("@EAS139:136:FC706VJ:", "", "::: :::")
     assert recv == [0, 10]          # rank 0 receives send_counts[0] of rank 0 (=0) and of rank 1 (=10)
+
+
+# ---- partition-first sample sort: the host side of global_unique, emulated with numpy ---------------------------
+def _emu_partition(rows, split_keys):
+    """contract of uqb_partition_rows: dest = number of splitter keys <= big-endian first 8 bytes; stable grouping"""
+    key = mg.row_key64(rows)
+    dest = np.searchsorted(np.asarray(split_keys, dtype=np.uint64), key, side="right")
+    order = np.argsort(dest, kind="stable")
+    return order, np.bincount(dest, minlength=len(split_keys) + 1)
+
+
+def test_row_key64_is_the_big_endian_prefix():
+    rows = np.array([[1, 2, 3, 4, 5, 6, 7, 8, 9], [0, 0, 0, 0, 0, 0, 0, 1, 255], [255] * 9], dtype=np.uint8)
+    assert mg.row_key64(rows).tolist() == [0x0102030405060708, 1, 0xFFFFFFFFFFFFFFFF]
+    narrow = np.array([[1, 2, 3], [0, 0, 9]], dtype=np.uint8)                 # shorter than 8 bytes: zero padded on the right
+    assert mg.row_key64(narrow).tolist() == [0x0102030000000000, 0x0000090000000000]
+    assert mg.row_key64(np.zeros((0, 5), np.uint8)).shape == (0,)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("width", [3, 9, 38])
+def test_partition_first_sample_sort_gives_the_global_sort(world, width):
+    """rows scattered over `world` ranks, partitioned by the splitter keys and sorted per destination: the
+    concatenation over the destinations is the stable global sort, identical rows meet on one rank, and the ids
+    scattered back through the partition order are numpy.unique's inverse."""
+    rng = np.random.default_rng(world * 100 + width)
+    n = 4000
+    table = rng.integers(0, 3, size=(n, width), dtype=np.uint8)              # few byte values: many ties on 8-byte prefixes
+    table[rng.integers(0, n, 300)] = table[rng.integers(0, n, 300)]          # and exact duplicates
+    cuts = np.sort(rng.integers(1, n - 1, world - 1))
+    shards = np.split(np.arange(n), cuts)
+    samples = [table[s][np.unique(np.linspace(0, len(s) - 1, num=min(len(s), 64)).astype(np.int64))] for s in shards]
+    splitters = mg.pick_splitters(np.concatenate(samples), world)
+    skeys = np.sort(mg.row_key64(splitters))
+    received = [[] for _ in range(world)]                                     # (global record index, row) per destination
+    routes = []
+    for s in shards:
+        order, counts = _emu_partition(table[s], skeys)
+        routes.append((s, order, counts))
+        b = np.concatenate([[0], np.cumsum(counts)])
+        for d in range(world):
+            for j in order[b[d]:b[d + 1]]:
+                received[d].append((int(s[j]), table[s[j]]))
+    void = lambda a: np.ascontiguousarray(a).view("V%d" % width).reshape(-1)
+    want_perm = np.argsort(void(table), kind="stable")
+    got_perm, uniq_parts, ids = [], [], np.zeros(n, dtype=np.int64)
+    offset = 0
+    for d in range(world):
+        if not received[d]:
+            continue
+        idx = np.array([g for g, _ in received[d]])
+        rows = np.stack([r for _, r in received[d]])
+        p = np.argsort(void(rows), kind="stable")
+        got_perm.extend(idx[p].tolist())
+        u, inv = np.unique(void(rows), return_inverse=True)
+        uniq_parts.append(u)
+        ids[idx] = inv.reshape(-1) + offset
+        offset += len(u)
+    assert got_perm == want_perm.tolist()                                     # rank-major concatenation = stable global sort
+    wu, winv = np.unique(void(table), return_inverse=True)
+    assert np.array_equal(np.concatenate(uniq_parts), wu)                     # unique tables concatenate
+    assert np.array_equal(ids, winv.reshape(-1))                              # ids back in record order
+
+
+def test_skew_guard_constants():
+    assert mg.SKEW_LIMIT >= 1.5 and mg.SAMPLES_PER_RANK >= 256
