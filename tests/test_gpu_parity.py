@@ -282,6 +282,25 @@ def test_roundtrip_variable_length_sort_qual(ctx):
     dev.free()
 
 
+@pytest.mark.parametrize("sort", ["None", "QUAL"])
+def test_long_variable_reads_equal_the_literal_oracle(ctx, sort):
+    """Reads of 64 .. 3 000 bases (too long for record tiles: direct histogram, one-CTA-per-read packer, leading-zero
+    aware sort) against the pinned literal oracle, member by member."""
+    from oracle import synth, uq_literal as lit
+    from uq_b200 import host
+    tab = synth.ont_length_table(64, 3000)
+    dev = ctx.synth("ont", 120, (64, 3000), 77, len_table=tab)
+    fastq = dev.download().tobytes()
+    dev.free()
+    kw = dict(sort=sort) if sort != "None" else dict(sort="None", raw=["DNA", "QUAL", "QNAME"])
+    want, want_cfg = lit.encode(fastq, **kw)
+    got, got_cfg = host.encode(fastq, ctx=ctx, **kw)
+    assert want_cfg["variable_read_lengths"] is True
+    assert_members_equal(got, want)
+    assert_config_equal(got_cfg, want_cfg)
+    assert host.decode(got, got_cfg, ctx=ctx).tobytes() == lit.decode(want, want_cfg)
+
+
 def test_streamed_load_and_async_download_match_the_serial_path(ctx):
     """uqb_fastq_load_streamed (chunked H2D overlapped with split + Pass-1 statistics) and the asynchronous
     member downloads must give exactly the arrays of the serial path."""

@@ -156,6 +156,75 @@ __device__ __forceinline__ void place_chunk16_any(uint32_t bits, const uint32_t 
     }
 }
 
+// Long / variable-length reads: one CTA per read.  The significant part of both packed rows (from the marker's byte
+// to the end of the row - everything before it is zero and was set by the host's memset) is assembled in shared
+// memory with the same 16-symbol work items as the tile kernel, reading the symbols straight from global memory,
+// and then written out.  Slot 0 of a variable-length row is the marker (code 1, uq.py:242-243).
+__global__ void __launch_bounds__(PKT_THREADS) k_pack_long(const uint8_t* __restrict__ d, const uint64_t* __restrict__ line_off,
+                                                          uint64_t n_reads, pack_lut lut_in, uint32_t bb, uint32_t bq, uint32_t wd, uint32_t wq,
+                                                          uint32_t variable, uint32_t dna_max, uint8_t* __restrict__ dna_out,
+                                                          uint8_t* __restrict__ qual_out, unsigned long long* __restrict__ err_record) {
+    extern __shared__ __align__(16) uint8_t pkl_raw[];
+    pkt_lut* lut = reinterpret_cast<pkt_lut*>(pkl_raw);
+    uint32_t* stage_d = reinterpret_cast<uint32_t*>(pkl_raw + sizeof(pkt_lut));
+    uint32_t* stage_q = stage_d + (wd + 3) / 4 + 8;
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid; i < 256; i += PKT_THREADS) {
+        const int t = lut_in.trick_qual[i];
+        lut->base[i] = (uint16_t)(lut_in.base_code[i] | ((t >= 0 ? (unsigned)t : 0xFFu) << 8));
+        lut->qual[i] = lut_in.qual_code[i];
+    }
+    for (uint64_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const uint64_t o1 = line_off[4 * r + 1], o2 = line_off[4 * r + 2], o3 = line_off[4 * r + 3];
+        uint64_t len64 = o2 - o1 - 1;
+        uint32_t len = (uint32_t)len64;
+        if (len64 > dna_max) {                              // cannot happen after uqb_analyze; never write out of row
+            if (tid == 0) atomicMin(err_record, (unsigned long long)r);
+            len = dna_max;
+        }
+        const uint8_t* dna = d + o1;
+        const uint8_t* qual = d + o3;
+        const uint32_t nsym = len + variable;
+        const uint32_t pad_d = wd * 8u - nsym * bb, pad_q = wq * 8u - nsym * bq;       // bit position of slot 0 in its row
+        const uint32_t jd0 = pad_d >> 3, jq0 = pad_q >> 3;                             // first significant byte
+        const uint32_t wjd = jd0 & ~3u, wjq = jq0 & ~3u;                               // staging word 0 = row bytes wj .. wj + 3
+        const uint32_t nwd = (wd - wjd + 3) / 4 + 8, nwq = (wq - wjq + 3) / 4 + 8;
+        __syncthreads();                                     // the previous read has left the staging areas (and the LUT is set)
+        for (uint32_t i = tid; i < nwd; i += PKT_THREADS) stage_d[i] = 0;
+        for (uint32_t i = tid; i < nwq; i += PKT_THREADS) stage_q[i] = 0;
+        __syncthreads();
+        const uint32_t chunks = (nsym + 15) / 16;
+        for (uint32_t item = tid; item < chunks; item += PKT_THREADS) {
+            const uint32_t s0 = item * 16;
+            uint32_t cdv[16], cqv[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint32_t slot = s0 + k;
+                uint32_t cd = 0, cq = 0;
+                if (slot < nsym) {
+                    if (variable && slot == 0) {
+                        cd = 1; cq = 1;
+                    } else {
+                        const uint32_t i = slot - variable;
+                        const uint32_t be = lut->base[__ldg(dna + i)];
+                        const uint32_t tq = be >> 8;
+                        cd = be & 0xFFu;
+                        cq = tq != 0xFFu ? tq : lut->qual[__ldg(qual + i)];
+                    }
+                }
+                cdv[k] = cd; cqv[k] = cq;
+            }
+            place_chunk16_any(bb, cdv, stage_d, pad_d - 8u * wjd + s0 * bb);
+            place_chunk16_any(bq, cqv, stage_q, pad_q - 8u * wjq + s0 * bq);
+        }
+        __syncthreads();
+        uint8_t* drow = dna_out + r * wd;
+        uint8_t* qrow = qual_out + r * wq;
+        for (uint32_t j = jd0 + tid; j < wd; j += PKT_THREADS) drow[j] = (uint8_t)(stage_d[(j - wjd) >> 2] >> (24u - 8u * ((j - wjd) & 3u)));
+        for (uint32_t j = jq0 + tid; j < wq; j += PKT_THREADS) qrow[j] = (uint8_t)(stage_q[(j - wjq) >> 2] >> (24u - 8u * ((j - wjq) & 3u)));
+    }
+}
+
 __global__ void __launch_bounds__(PKT_THREADS) k_pack_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
                                                            const uint64_t* __restrict__ line_off, uint64_t n_reads, pack_lut lut_in,
                                                            uint32_t bb, uint32_t bq, uint32_t wd, uint32_t wq, uint32_t L,
@@ -315,9 +384,20 @@ extern "C" int uqb_pack(uqb_ctx* ctx, uqb_fastq* fq, const uqb_pack_params* p, u
         UQB_CUDA(cudaMemsetAsync((*dna)->d, 0, N * (uint64_t)p->dna_bytes, ctx->stream));
         UQB_CUDA(cudaMemsetAsync((*qual)->d, 0, N * (uint64_t)p->qual_bytes, ctx->stream));
     }
-    UQB_LAUNCH_B(abytes, k_pack_rows, uqb_grid(ctx, N, PK_THREADS / 32, 16), PK_THREADS, 0, fq->d, fq->line_off, N, lut,
-               p->bits_per_base, p->bits_per_quality, p->dna_bytes, p->qual_bytes, p->variable, p->dna_max, prefilled,
-               (uint8_t*)(*dna)->d, (uint8_t*)(*qual)->d, d_err);
+    const size_t long_smem = sizeof(pkt_lut) + (((size_t)p->dna_bytes + 3) / 4 + 8 + ((size_t)p->qual_bytes + 3) / 4 + 8) * 4;
+    if (trick_ok && long_smem <= 160 * 1024 && p->dna_max >= 64) {
+        // rows assembled in shared memory, one CTA per read
+        UQB_CUDA(cudaFuncSetAttribute(k_pack_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem));
+        const unsigned per_sm = (unsigned)(200 * 1024 / (long_smem + 1024)) > 8u ? 8u : ((unsigned)(200 * 1024 / (long_smem + 1024)) ? (unsigned)(200 * 1024 / (long_smem + 1024)) : 1u);
+        const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
+        UQB_LAUNCH_B(abytes, k_pack_long, (unsigned)(N < cap ? N : cap), PKT_THREADS, long_smem, fq->d, fq->line_off, N, lut,
+                     p->bits_per_base, p->bits_per_quality, p->dna_bytes, p->qual_bytes, p->variable, p->dna_max,
+                     (uint8_t*)(*dna)->d, (uint8_t*)(*qual)->d, d_err);
+    } else {
+        UQB_LAUNCH_B(abytes, k_pack_rows, uqb_grid(ctx, N, PK_THREADS / 32, 16), PK_THREADS, 0, fq->d, fq->line_off, N, lut,
+                   p->bits_per_base, p->bits_per_quality, p->dna_bytes, p->qual_bytes, p->variable, p->dna_max, prefilled,
+                   (uint8_t*)(*dna)->d, (uint8_t*)(*qual)->d, d_err);
+    }
     unsigned long long err;
     UQB_TRY(uqb_readback(ctx, &err, d_err, 8));
     UQB_TRY(uqb_dfree(ctx, d_err, 8));
