@@ -85,6 +85,70 @@ __global__ void __launch_bounds__(LT) k_layout_transpose(const uint8_t* __restri
     }
 }
 
+// Column-major forms, tall tiles: a CTA takes LR_ROWS consecutive rows of ALL columns.  On the table side that is one
+// contiguous, 16-byte aligned range (vector loads / stores through shared memory); on the stream side it is one run
+// of LR_ROWS bytes per column, moved as 32-bit words.  The 64 x 64 tiles above write 64-byte runs scattered over
+// `width` streams, which DRAM does not like; here a run is 512 bytes.
+#define LR_ROWS 512
+#define LR_SMEM_MAX (96 * 1024)
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(LT) k_layout_transpose_tall(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n,
+                                                             uint32_t width, int rev_r, int rev_b) {
+    extern __shared__ __align__(16) uint8_t lr_tile[];                 // [rows][width] as in the table
+    const uint64_t nblk = (n + LR_ROWS - 1) / LR_ROWS;
+    for (uint64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const uint64_t r0 = blk * LR_ROWS;
+        const uint32_t nr = (uint32_t)(n - r0 < LR_ROWS ? n - r0 : LR_ROWS);
+        const uint32_t total = nr * width, q = (nr + 3) / 4;
+        const uint64_t lo = rev_r ? n - r0 - nr : r0;                  // first stream index (within a column) of this tile
+        const uint8_t* table_c = INVERSE ? nullptr : src + r0 * width;
+        uint8_t* table_m = INVERSE ? dst + r0 * width : nullptr;
+        __syncthreads();
+        if (!INVERSE) {
+            for (uint32_t v = threadIdx.x; v < (total + 15) / 16; v += LT)   // the table has 64 bytes of slack behind its last row
+                reinterpret_cast<uint4*>(lr_tile)[v] = __ldg(reinterpret_cast<const uint4*>(table_c) + v);
+            __syncthreads();
+        }
+        // stream side: work item = 4 consecutive bytes of one column's run
+        for (uint32_t t = threadIdx.x; t < width * q; t += LT) {
+            const uint32_t b = t / q, i4 = (t - b * q) * 4;
+            const uint32_t bp = rev_b ? width - 1 - b : b;
+            const uint64_t a = (uint64_t)bp * n + lo + i4;             // stream address of the first of the 4 bytes
+            const uint32_t cnt = nr - i4 < 4 ? nr - i4 : 4;
+            if (!INVERSE) {
+                uint32_t w = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++) {
+                    if (k < cnt) {
+                        const uint32_t i = rev_r ? nr - 1 - (i4 + k) : i4 + k;       // tile row of stream byte i4 + k
+                        w |= (uint32_t)lr_tile[i * width + b] << (8 * k);
+                    }
+                }
+                if (cnt == 4 && (a & 3) == 0) *reinterpret_cast<uint32_t*>(dst + a) = w;
+                else for (uint32_t k = 0; k < cnt; k++) dst[a + k] = (uint8_t)(w >> (8 * k));
+            } else {
+                uint32_t w = 0;
+                if (cnt == 4 && (a & 3) == 0) w = __ldg(reinterpret_cast<const uint32_t*>(src + a));
+                else for (uint32_t k = 0; k < cnt; k++) w |= (uint32_t)__ldg(src + a + k) << (8 * k);
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++) {
+                    if (k < cnt) {
+                        const uint32_t i = rev_r ? nr - 1 - (i4 + k) : i4 + k;
+                        lr_tile[i * width + b] = (uint8_t)(w >> (8 * k));
+                    }
+                }
+            }
+        }
+        if (INVERSE) {
+            __syncthreads();
+            for (uint32_t v = threadIdx.x; v < total / 16; v += LT)
+                reinterpret_cast<uint4*>(table_m)[v] = reinterpret_cast<const uint4*>(lr_tile)[v];
+            for (uint32_t x = (total & ~15u) + threadIdx.x; x < total; x += LT) table_m[x] = lr_tile[x];
+        }
+    }
+}
+
 static int layout_impl(uqb_ctx* ctx, const uint8_t* src, uint8_t* dst, uint64_t n, uint32_t width, int pattern, bool inverse) {
     layout_desc ld;
     if (pattern_desc(pattern, &ld)) return uqb_fail(ctx, "layout: pattern id %d out of range", pattern);
@@ -93,6 +157,16 @@ static int layout_impl(uqb_ctx* ctx, const uint8_t* src, uint8_t* dst, uint64_t 
         unsigned g = uqb_grid(ctx, n, LT / 32, 16);
         if (inverse) UQB_LAUNCH_B(2 * n * width, k_layout_rows<true>, g, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
         else         UQB_LAUNCH_B(2 * n * width, k_layout_rows<false>, g, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
+    } else if ((size_t)LR_ROWS * width + 16 <= LR_SMEM_MAX && ((reinterpret_cast<uintptr_t>(inverse ? dst : src)) & 15) == 0) {
+        const size_t smem = (size_t)LR_ROWS * width + 16;
+        const unsigned g = uqb_grid(ctx, n, LR_ROWS, 16);
+        if (inverse) {
+            UQB_CUDA(cudaFuncSetAttribute(k_layout_transpose_tall<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            UQB_LAUNCH_B(2 * n * width, k_layout_transpose_tall<true>, g, LT, smem, src, dst, n, width, ld.rev_r, ld.rev_b);
+        } else {
+            UQB_CUDA(cudaFuncSetAttribute(k_layout_transpose_tall<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            UQB_LAUNCH_B(2 * n * width, k_layout_transpose_tall<false>, g, LT, smem, src, dst, n, width, ld.rev_r, ld.rev_b);
+        }
     } else {
         uint64_t gx = (n + TILE - 1) / TILE;
         if (gx > 0x7fffffffull) return uqb_fail(ctx, "layout: too many rows");
