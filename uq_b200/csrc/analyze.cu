@@ -1,12 +1,16 @@
 // Stage 1: the Pass-1 statistics of the reference (uq.py:342-425) as device reductions.
 //
-//  k_record_stats  one thread per record: FASTQ shape checks, read-length min/max, and the QNAME
-//                  statistics against line 1 from which the host reproduces the order-dependent
-//                  prefix / suffix / separator logic of uq.py:395-413 exactly (see host.py).
-//  k_pair_hist     base and quality byte histograms plus "does this base always carry one single
-//                  quality" (static_qualities, uq.py:369-375, 420-425, read at uq.py:480-494).
-//                  Counters are private per thread (packed 8-bit fields in shared memory, flushed
-//                  before they can overflow) so the hot loop has no atomics.
+// Per-record statistics (FASTQ shape checks, read-length min/max, and the QNAME statistics against line 1 from which
+// the host reproduces the order-dependent prefix / suffix / separator logic of uq.py:395-413 exactly, see host.py):
+//   k_record_stats_names   the product kernel: thread per record, reads offsets + name + '+' only
+//   k_record_stats         generic fallback (names longer than 255 bytes, more than 64 distinct bytes in line 1)
+// Base and quality byte histograms plus "does this base always carry one single quality" (static_qualities,
+// uq.py:369-375, 420-425, read at uq.py:480-494):
+//   k_pair_hist_tiles      records that fit shared-memory tiles (double-buffered TMA tiles, tile.cuh)
+//   k_pair_hist_long       long reads, straight from global memory
+//   k_pair_hist            generic fallback (bytes outside 32..127)
+// Counters are private per thread (packed 8-bit fields in shared memory or registers, flushed before they can
+// overflow), so the hot loops have no atomics.
 #include "common.cuh"
 #include "tile.cuh"
 
@@ -212,10 +216,9 @@ __global__ void __launch_bounds__(PH_THREADS) k_pair_hist(const uint8_t* __restr
 }
 
 // ================================================================================================
-// v2: the same statistics from shared-memory record tiles (tile.cuh).  Used whenever the records are
-// short enough for TL_R of them to fit a tile; the direct-from-global kernels above remain the path
-// for long reads and for QNAME lines that defeat the packed counters (more than 64 distinct bytes in
-// line 1 or a QNAME longer than 255 bytes) - the kernel reports that through `fallback`.
+// The product kernels.  The generic kernels above remain the path for QNAME lines that defeat the packed
+// counters (more than 64 distinct bytes in line 1 or a QNAME longer than 255 bytes) and for bytes outside
+// 32..127 - the kernels report that through `fallback` and the host runs the generic pair.
 // ================================================================================================
 #define RS_SLOTS 64
 

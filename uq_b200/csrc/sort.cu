@@ -3,8 +3,11 @@
 // encode_dna_qual (uq.py:765-805) and encode_qname (uq.py:808-851).
 //
 // Algorithm: MSD refinement in 8-byte chunks on top of the stable LSD radix sort of prims.cu.
-//   round 0   sort (be64(row[0:8]), row index) over all rows; mark group heads.
-//   round c   only rows that are still tied with a neighbour AND whose tie group is not made of
+//   round 0   sort (be64(row[0:8]), row index) over all rows; mark group heads.  Rows wider than 256 bytes are
+//             taken from their first non-zero byte: the key is (significant length, first 8 significant bytes).
+//   finisher  tie groups of 2..32 rows are completed by one warp each (k_small_groups: three-way quicksort on rows
+//             staged in shared memory); for typical data nothing is left after it.
+//   round c   (groups of more than 32 rows) only rows that are still tied with a neighbour AND whose tie group is not made of
 //             identical rows ("all-equal finisher": one compare of the remaining bytes against the
 //             group's first row) stay active; they are compacted, keyed by (group id, be64(row[8c:8c+8]))
 //             and sorted again; results are written back in place.  Groups are contiguous, so a
