@@ -149,11 +149,51 @@ __global__ void __launch_bounds__(LT) k_layout_transpose_tall(const uint8_t* __r
     }
 }
 
+// Row-major forms with reversed rows and / or bytes, tall tiles: LR_ROWS consecutive rows are one contiguous range on
+// both sides (the rows of the block just appear in reverse order), so the block is read with 16-byte loads into shared
+// memory and written as 32-bit words.  Reversing is its own inverse: the same kernel serves layout and unlayout.
+__global__ void __launch_bounds__(LT) k_layout_rows_tall(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n, uint32_t width,
+                                                        int rev_r, int rev_b) {
+    extern __shared__ __align__(16) uint8_t lr_tile[];
+    const uint64_t nblk = (n + LR_ROWS - 1) / LR_ROWS;
+    for (uint64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const uint64_t r0 = blk * LR_ROWS;
+        const uint32_t nr = (uint32_t)(n - r0 < LR_ROWS ? n - r0 : LR_ROWS);
+        const uint32_t total = nr * width;
+        __syncthreads();
+        for (uint32_t v = threadIdx.x; v < (total + 15) / 16; v += LT)        // the source has 64 bytes of slack behind its last row
+            reinterpret_cast<uint4*>(lr_tile)[v] = __ldg(reinterpret_cast<const uint4*>(src + r0 * width) + v);
+        __syncthreads();
+        uint8_t* out = dst + (rev_r ? n - r0 - nr : r0) * width;              // the block's place on the other side
+        const uint32_t head = (uint32_t)((4u - ((uintptr_t)out & 3u)) & 3u);   // bytes before the first aligned word
+        const uint32_t nwords = total > head ? (total - head) / 4 : 0;
+        for (uint32_t x = threadIdx.x; x < nwords + 8; x += LT) {
+            // items 0 .. nwords-1: aligned words; the last 8 items: the (at most 3 + 3) edge bytes
+            uint32_t first, cnt;
+            if (x < nwords) { first = head + 4 * x; cnt = 4; }
+            else { const uint32_t e = x - nwords; first = e < 4 ? e : head + 4 * nwords + (e - 4); cnt = (e < 4 ? (e < head && e < total) : (first < total && first >= head)) ? 1u : 0u; }
+            uint32_t w = 0;
+            uint32_t io = first / width, bo = first - io * width;             // output row / byte of the first byte
+            for (uint32_t k = 0; k < cnt; k++) {
+                const uint32_t i = rev_r ? nr - 1 - io : io, b = rev_b ? width - 1 - bo : bo;
+                w |= (uint32_t)lr_tile[i * width + b] << (8 * k);
+                if (++bo == width) { bo = 0; io++; }
+            }
+            if (cnt == 4) *reinterpret_cast<uint32_t*>(out + first) = w;
+            else if (cnt == 1) out[first] = (uint8_t)w;
+        }
+    }
+}
+
 static int layout_impl(uqb_ctx* ctx, const uint8_t* src, uint8_t* dst, uint64_t n, uint32_t width, int pattern, bool inverse) {
     layout_desc ld;
     if (pattern_desc(pattern, &ld)) return uqb_fail(ctx, "layout: pattern id %d out of range", pattern);
     if (n == 0 || width == 0) return 0;
-    if (!ld.transposed) {
+    if (!ld.transposed && (size_t)LR_ROWS * width + 16 <= LR_SMEM_MAX && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const size_t smem = (size_t)LR_ROWS * width + 16;
+        UQB_CUDA(cudaFuncSetAttribute(k_layout_rows_tall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        UQB_LAUNCH_B(2 * n * width, k_layout_rows_tall, uqb_grid(ctx, n, LR_ROWS, 16), LT, smem, src, dst, n, width, ld.rev_r, ld.rev_b);
+    } else if (!ld.transposed) {
         unsigned g = uqb_grid(ctx, n, LT / 32, 16);
         if (inverse) UQB_LAUNCH_B(2 * n * width, k_layout_rows<true>, g, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
         else         UQB_LAUNCH_B(2 * n * width, k_layout_rows<false>, g, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
