@@ -18,8 +18,12 @@ layout, ending with every output array resident in HBM in its final layout.
   cpu_baseline  the oracle's literal restatement of uq.py (1 core, the reference is single threaded)
          on a bounded sample of the same FASTQ.
 
-Multi-GPU (torchrun, one process per GPU): every rank encodes its own contiguous range of reads into
-its own container shard (weak scaling, no data-path collective in round 1 - see DESIGN.md (e)).
+Multi-GPU (torchrun, one process per GPU): rank r holds the contiguous read range [r n, (r+1) n) of ONE file and the
+ranks produce ONE global container (merged statistics, partition-first sample sort with an all-to-all of the packed
+rows over NVLink, global --sort order).  Weak scaling: n = 100 M reads per GPU.  Before the timed
+loop every N>1 run encodes a small file both ways (sharded over the ranks and whole on rank 0), compares every member
+and the config, decodes the container over the ranks, and reports the outcome as `parity_check`; a mismatch ends the
+run with a non-zero exit code.  `--multi shards` (independent container shards, no collective) is kept as a diagnostic.
 """
 import argparse
 import json
@@ -147,6 +151,16 @@ def run_ours(args):
     if global_mode:
         from uq_b200 import multigpu
         comm = multigpu.Comm(dist, "cuda:%d" % local_rank)
+
+    parity = None
+    if global_mode and not args.no_parity:
+        parity = parity_check(ctx, comm, rank, world, host, multigpu, opts)
+        if not parity["ok"]:
+            if rank == 0:
+                emit({"metric": "fastq_to_uq_encode_reads_per_s", "value": None, "n_gpus": world, "parity_check": parity,
+                      "error": "sharded encode differs from the single-GPU encode"})
+            dist.destroy_process_group()
+            sys.exit(3)
 
     def one_step():
         fq = ctx.adopt_fastq(dev)
@@ -364,9 +378,50 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "pipeline_roofline": pipeline, "kernels": top5, "decode": decode, "cpu_baseline": cpu,
         }
+        if parity is not None:
+            line["parity_check"] = parity
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def parity_check(ctx, comm, rank, world, host, multigpu, opts, n_each=200_000):
+    """The sharded path against the single-GPU path on a file small enough for rank 0 to encode alone: every member
+    (dtype, shape, bytes) and the config of the global container must equal the single-GPU container, and the sharded
+    decode of it must reproduce the single-GPU decode.  Runs with the bench's own options (--sort DNA, keyed)."""
+    import numpy as np
+    kw = dict(genome=n_each * world // 10, pool=max(1, n_each * world // 5))
+    dev = ctx.synth("genome", n_each, READ_LEN, SEED + 1, first=rank * n_each, **kw)
+    fq = ctx.adopt_fastq(dev)
+    res, cfg = multigpu.encode_sharded(ctx, comm, fq, **opts)
+    members = multigpu.assemble(comm, res)
+    res.free(); fq.free(); dev.free()
+    bad, k = [], 0
+    if rank == 0:
+        whole = ctx.synth("genome", n_each * world, READ_LEN, SEED + 1, first=0, **kw)
+        wfq = ctx.adopt_fastq(whole)
+        wm, wcfg = host.encode_device(ctx, wfq, **opts)
+        want = wm.download()
+        if sorted(want) != sorted(members):
+            bad.append("member names")
+        else:
+            for name in want:
+                a, b = members[name], np.asarray(want[name])
+                k += 1
+                if a.dtype != b.dtype or a.shape != b.shape or not np.array_equal(a, b):
+                    bad.append(name)
+        if json.loads(json.dumps(cfg, default=str)) != json.loads(json.dumps(wcfg, default=str)):
+            bad.append("config.json")
+        single_text = host.decode(want, wcfg, ctx=ctx).tobytes()
+        wm.free(); wfq.free(); whole.free()
+    members = comm.all_gather_object(members)[0]
+    text, a, b = multigpu.decode_sharded(ctx, comm, members, cfg)
+    texts = comm.all_gather_object(bytes(text))
+    if rank == 0 and b"".join(texts) != single_text:
+        bad.append("sharded decode")
+    bad = comm.all_gather_object(bad)[0]
+    return {"ranks": world, "reads": n_each * world, "members": k if rank == 0 else None, "decode": "sharded decode == single-GPU decode",
+            "ok": not bad, "mismatches": bad}
 
 
 def _ref_worker(job):
@@ -428,6 +483,7 @@ def main():
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e without copy/compute overlap (diagnostics)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the sharded-vs-single parity check before the timed loop")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

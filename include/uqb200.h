@@ -72,6 +72,11 @@ int uqb_ctx_copy_sync(uqb_ctx* ctx);
 int uqb_array_first_difference(uqb_ctx* ctx, const uqb_array* a, const uqb_array* b, int64_t* first);
 int uqb_array_free(uqb_ctx* ctx, uqb_array* a);
 void* uqb_array_device_ptr(const uqb_array* a);   /* for benches/tests that adopt device memory */
+/* non-owning view of device memory (a peer GPU's window, another context's array): uqb_array_free releases the view only */
+int uqb_array_wrap(uqb_ctx* ctx, void* dev, uint64_t n, uint32_t width, uqb_array** out);
+/* device -> device copy of nbytes from src_dev (any device pointer this process can address, peer memory included)
+ * into dst at byte offset dst_offset, on the context's stream */
+int uqb_array_copy_in(uqb_ctx* ctx, uqb_array* dst, uint64_t dst_offset, const void* src_dev, uint64_t nbytes);
 
 /* ---- stage 1: load + record splitting  (replaces open()/next(f) uq.py:339-342, 378-385 and the
  *      `wc -l` record count uq.py:85-87) -------------------------------------------------------- */
@@ -210,6 +215,9 @@ int uqb_compact_segments(uqb_ctx* ctx, const uqb_array* padded, uint32_t nseg, c
                          const uint64_t* seg_counts_host, uint32_t width, uqb_array** out);
 /* out[idx[j]] = src[j], uint32 arrays, idx a permutation (inverse of uqb_gather_rows) */
 int uqb_scatter_u32(uqb_ctx* ctx, const uqb_array* src, const uqb_array* idx, uqb_array** out);
+/* the inverse on the decode side: an index member read from a container (itemsize 1/2/4/8, uq.py:953, 957, 973) widened to
+ * uint32 and checked: first_bad = first position whose value is >= bound (rows of the table it indexes), -1 if none */
+int uqb_index_u32(uqb_ctx* ctx, const uqb_array* a, uint64_t bound, uqb_array** out, int64_t* first_bad);
 /* uint32 -> little-endian integer of itemsize bytes (key.astype(min_scalar_type(max)), uq.py:790) */
 int uqb_narrow_u32(uqb_ctx* ctx, const uqb_array* a, uint32_t itemsize, uqb_array** out);
 /* QNAME columns <-> rows in sort-key form: columns concatenated big-endian at their own widths,

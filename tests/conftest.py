@@ -81,3 +81,19 @@ def assert_config_equal(got, want, context=""):
     assert sorted(map(str, g.pop("raw"))) == sorted(map(str, w.pop("raw"))), context + " raw"
     for k in sorted(set(g) | set(w)):
         assert g.get(k) == w.get(k), "%s config[%s]: %r vs %r" % (context, k, g.get(k), w.get(k))
+
+
+def hiseq_like_fastq(n=3000, length=36, seed=4):
+    """N always carries '#', and '#' also sits on other (low quality) bases: the N-trick's "new quality" branch
+    (uq.py:489-494)."""
+    import random
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        dna = [rng.choice("ACGT") for _ in range(length)]
+        qual = [rng.choice("IH5A#") if rng.random() < 0.9 else "#" for _ in range(length)]
+        for p in range(length):
+            if rng.random() < 0.03:
+                dna[p] = "N"; qual[p] = "#"
+        out.append("@HS:%d:%d\n%s\n+\n%s\n" % (1 + i % 4, 1000 + i, "".join(dna), "".join(qual)))
+    return "".join(out).encode()

@@ -341,3 +341,29 @@ def test_streamed_load_and_async_download_match_the_serial_path(ctx):
     for f in STAT_FIELDS:
         assert list(getattr(st, f)) == list(getattr(ref, f)), f
     h.free(); pin2.free(); pin.free()
+
+
+def test_ntrick_new_quality_branch_encodes_like_the_reference_and_decodes(ctx):
+    """Q3: the reference encodes such a file (N gets quality code len(qualities)+1) but cannot decode it and stores
+    the original quality nowhere.  The arrays and the reference's config keys must stay bit-exact; the extra
+    N_qual_symbol key makes the container decodable here - byte for byte."""
+    from oracle import uq_literal as lit
+    from uq_b200 import host
+    from conftest import hiseq_like_fastq
+    fq = hiseq_like_fastq()
+    for kw in (dict(sort="None", raw=["DNA", "QUAL", "QNAME"]), dict(sort="QUAL")):
+        want, want_cfg = lit.encode(fq, **kw)
+        got, got_cfg = host.encode(fq, ctx=ctx, **kw)
+        assert want_cfg["N_qual"] == {"N": len(want_cfg["qualities"]) + 1}         # the branch fired
+        assert_members_equal(got, want)
+        extra = dict(got_cfg)
+        assert extra.pop("N_qual_symbol") == {"N": "#"}
+        assert_config_equal(extra, want_cfg)
+        text = host.decode(got, got_cfg, ctx=ctx).tobytes()
+        if kw["sort"] == "None":
+            assert text == fq
+        else:
+            assert records_multiset(text) == records_multiset(fq)
+        stripped = {k: v for k, v in got_cfg.items() if k != "N_qual_symbol"}      # a reference-written container
+        with pytest.raises(host.UQError, match="no quality symbol"):
+            host.decode(got, stripped, ctx=ctx)

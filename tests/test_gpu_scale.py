@@ -213,6 +213,108 @@ def _assert_idempotent(ctx, dev, **opts):
     return m1, cfg1, m2, text
 
 
+def rows_strictly_ascending(t, chunk=4_000_000):
+    """memcmp order of the rows of a uint8 table, strictly increasing (numpy has no ordering for void dtypes: the rows
+    are compared as big-endian 64-bit words, most significant first)"""
+    n, w = t.shape
+    pad = (-w) % 8
+    for s0 in range(0, n, chunk):
+        blk = t[max(s0 - 1, 0):s0 + chunk]
+        a = np.zeros((len(blk), w + pad), dtype=np.uint8)
+        a[:, :w] = blk
+        k = a.view(">u8")
+        lt = np.zeros(len(blk) - 1, dtype=bool)
+        eq = np.ones(len(blk) - 1, dtype=bool)
+        for j in range(k.shape[1]):
+            lt |= eq & (k[:-1, j] < k[1:, j])
+            eq &= k[:-1, j] == k[1:, j]
+        if not bool(lt.all()):
+            return False
+    return True
+
+
+def row_hashes(t, chunk=8_000_000):
+    """order-independent fingerprint material: one 64-bit hash per row"""
+    n, w = t.shape
+    pad = (-w) % 8
+    mult = np.array([0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0x27D4EB2F165667C5] * 8, dtype=np.uint64)
+    out = np.empty(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for s0 in range(0, n, chunk):
+            blk = t[s0:s0 + chunk]
+            a = np.zeros((len(blk), w + pad), dtype=np.uint8)
+            a[:, :w] = blk
+            k = a.view("<u8")
+            h = np.zeros(len(blk), dtype=np.uint64)
+            for j in range(k.shape[1]):
+                h = (h ^ k[:, j]) * mult[j % len(mult)]
+                h ^= h >> np.uint64(29)
+            out[s0:s0 + len(blk)] = h
+    return out
+
+
+def test_config1_full_size_sort_dna_keyed(ctx):
+    """BASELINE configs[1] - the benched workload - at its full size: 100 M reads x 150 bp, --sort DNA, keyed tables.
+      * the packed DNA / QUAL rows of the first 5 M reads equal the vectorised oracle (closed form, bit exact);
+      * both unique tables are strictly ascending in memcmp order, DNA.key is non-decreasing, every key < table size;
+      * unique[key] (the sorted rows) is a permutation of the packed table (multiset of 64-bit row hashes);
+      * encode -> decode -> encode reproduces every member (compared on the device)."""
+    from oracle import uq_vec as vec
+    from uq_b200 import host
+    n = 100_000_000
+    used, free, total = ctx.mem_info()
+    if total - used < 150 << 30:
+        pytest.skip("needs ~150 GB of free HBM")
+    dev = ctx.synth("genome", n, 150, 1002, genome=10_000_000, pool=n // 5)
+    # ---- pack parity on the head of the file ----
+    fq = ctx.adopt_fastq(dev)
+    st = {}
+    m0, cfg0 = host.encode_device(ctx, fq, sort="DNA", stages=st)
+    head_reads = 5_000_000
+    offs = fq.line_offsets(4 * head_reads, 1)
+    head = fq.download(0, int(offs[0])).tobytes()
+    dna_rows = st["dna"].download()                      # 3.8 GB, record order
+    qual_head = ctx.gather_rows(st["qual"], ctx.upload(np.arange(head_reads, dtype=np.uint32))).download()
+    lines_per, start = 4 * 1_000_000, 0
+    for s0 in range(0, head_reads, 1_000_000):           # 1 M reads at a time (the bit expansion of the oracle is 48x)
+        end = _nth_newline(head, start, lines_per)
+        _, dna, qual = vec.parse_fixed(head[start:end], 150)
+        d, q = vec.pack_tables(dna, qual, st["dec"])
+        assert np.array_equal(dna_rows[s0:s0 + 1_000_000], d), "DNA rows %d.." % s0
+        assert np.array_equal(qual_head[s0:s0 + 1_000_000], q), "QUAL rows %d.." % s0
+        start = end
+    del head, qual_head
+    # ---- sort / unique properties ----
+    out = {k: m0.items[k][0].download(dtype=np.dtype(m0.items[k][2]) if m0.items[k][1] == "vector" else np.uint8)
+           for k in ("DNA", "QUAL", "DNA.key", "QUAL.key")}
+    assert rows_strictly_ascending(out["DNA"]) and rows_strictly_ascending(out["QUAL"])
+    key = out["DNA.key"]
+    assert key.dtype == np.uint32 and len(key) == n
+    assert bool(np.all(key[1:] >= key[:-1])) and int(key[-1]) == len(out["DNA"]) - 1 and int(key[0]) == 0
+    assert int(out["QUAL.key"].max()) == len(out["QUAL"]) - 1
+    assert np.array_equal(np.unique(key), np.arange(len(out["DNA"]), dtype=np.uint32))      # every unique row is used
+    hs = np.sort(row_hashes(out["DNA"])[key])
+    hp = np.sort(row_hashes(dna_rows))
+    assert np.array_equal(hs, hp), "DNA[DNA.key] is not a permutation of the packed table"
+    del dna_rows, out, hs, hp
+    keep = {id(a) for a, _, _ in m0.items.values()}
+    for a in [st["dna"], st["qual"]] + st["cols"]:
+        if id(a) not in keep:
+            a.free()
+    m0.free(); fq.free()
+    # ---- idempotence ----
+    m1, cfg, m2, text = _assert_idempotent(ctx, dev, sort="DNA")
+    assert cfg["reads"] == n and cfg["bits_per_base"] == 2 and cfg["bits_per_quality"] == 6
+    m1.free(); m2.free(); text.free(); dev.free()
+
+
+def _nth_newline(buf, start, count):
+    """offset just behind the count-th newline at or after `start`"""
+    a = np.frombuffer(buf, dtype=np.uint8, offset=start)
+    nl = np.flatnonzero(a[:count * 200] == 10)           # 4 lines of a 150 bp record: about 85 bytes per line
+    return start + int(nl[count - 1]) + 1
+
+
 def test_config3_full_size_sort_qname(ctx):
     """50 M CASAVA-1.8 reads, --sort QNAME: column typing, sorted unique QNAME table, monotone key, idempotence."""
     n = 50_000_000

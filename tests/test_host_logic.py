@@ -91,3 +91,23 @@ def test_error_messages():
     assert host.normalise_options(sort="none") == ((None,), (None,), ["0.1", "0.1"])
     assert host.key_itemsize(1) == 1 and host.key_itemsize(256) == 1 and host.key_itemsize(257) == 2
     assert host.key_itemsize(65537) == 4
+
+
+def test_ntrick_new_quality_branch_records_the_symbol():
+    """Q3 (uq.py:489-494): N always has '#', '#' also occurs on other bases -> code len(qualities)+1, and the host
+    records which character that code stands for so that the container can be decoded."""
+    from conftest import hiseq_like_fastq
+    fq = hiseq_like_fastq(n=400)
+    st, n = emu_stats(fq)
+    dec = host.decide_alphabets(st)
+    stages = {}
+    lit.encode(fq, stages=stages)
+    assert dec["N_qual"] == stages["dec"]["N_qual"] == {"N": len(dec["qualities"]) + 1}
+    assert dec["N_qual_symbol"] == {"N": "#"}
+    assert dec["bases"] == "ACGT"
+    cfg = host.config_of(dec, n, "@HS:", "", ":", [], (None,), (None,), ["0.1", "0.1"])
+    assert cfg["N_qual_symbol"] == {"N": "#"}
+    fq2, _, _ = golden_case("c1_raw_p01_31")               # the usual branch: N owns its quality -> no extra key
+    plain = host.decide_alphabets(emu_stats(fq2)[0])
+    assert plain["N_qual"] and plain["N_qual_symbol"] == {}
+    assert "N_qual_symbol" not in host.config_of(plain, 2, "@a:", "", ":", [], (None,), (None,), ["0.1", "0.1"])

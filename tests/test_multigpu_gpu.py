@@ -15,6 +15,8 @@ CASES = [
     ("casava", 26000, 50, dict(sort="QNAME")),
     ("casava", 8000, 50, dict(sort="DNA", raw=["QNAME", "QUAL"])),
     ("illumina", 7000, 30, dict()),
+    ("genome", 9000, 40, dict(sort="DNA", pattern=["2.2", "1.1"])),
+    ("genome", 9000, 40, dict(sort="None", raw=["DNA", "QUAL"], pattern=["3.1", "1.2"])),
 ]
 
 
@@ -47,7 +49,7 @@ def _worker(rank, world, port, q):
         shard = synth.make_fastq(kind=kind, n=cnt, length=length, seed=21, first=first, **kwg)
         fq = ctx.load_fastq(shard)
         res, cfg = mg.encode_sharded(ctx, comm, fq, **kw)
-        members = mg.assemble(comm, res.download())
+        members = mg.assemble(comm, res)
         res.free(); fq.free()
         if rank == 0:
             whole = synth.make_fastq(kind=kind, n=n, length=length, seed=21, first=0, **kwg)
@@ -65,6 +67,13 @@ def _worker(rank, world, port, q):
             if json.loads(json.dumps(cfg, default=str)) != json.loads(json.dumps(want_cfg, default=str)):
                 bad.append("config differs")
             results.append((kind + (" merge" if merge == "1" else ""), kw, bad))
+        # sharded decode of the container just written: the ranks' texts concatenate to the single-GPU decode
+        members = comm.all_gather_object(members)[0]
+        text, a, b = mg.decode_sharded(ctx, comm, members, cfg)
+        texts = comm.all_gather_object(bytes(text))
+        if rank == 0:
+            single = host.decode(members, cfg, ctx=ctx).tobytes()
+            results.append((kind + " decode", kw, [] if b"".join(texts) == single else ["sharded decode differs"]))
     os.environ["UQB_MG_MERGE"] = "0"
     # a larger case generated on the device, loaded through the streamed path with the reference line, async downloads
     n_each = 700_000
@@ -85,7 +94,7 @@ def _worker(rank, world, port, q):
         bufs[name] = ctx.pinned_empty(nbytes)
         return bufs[name].array
     res, cfg = mg.encode_sharded(ctx, comm, fq, sort="DNA", sink=sink)
-    members = mg.assemble(comm, {k: np.array(v) for k, v in res.download().items()})
+    members = mg.assemble(comm, res)
     res.free(); fq.free()
     if rank == 0:
         whole = ctx.synth("genome", 2 * n_each, 150, 1002, first=0, genome=200_000, pool=300_000)

@@ -94,6 +94,9 @@ SIGNATURES = {
     "uqb_array_first_difference": (C.c_int, [P, P, P, C.POINTER(C.c_int64)]),
     "uqb_array_free": (C.c_int, [P, P]),
     "uqb_array_device_ptr": (C.c_void_p, [P]),
+    "uqb_array_wrap": (C.c_int, [P, P, C.c_uint64, C.c_uint32, PP]),
+    "uqb_array_copy_in": (C.c_int, [P, P, C.c_uint64, P, C.c_uint64]),
+    "uqb_index_u32": (C.c_int, [P, P, C.c_uint64, PP, C.POINTER(C.c_int64)]),
     "uqb_fastq_load": (C.c_int, [P, P, C.c_uint64, PP]),
     "uqb_fastq_adopt": (C.c_int, [P, P, C.c_uint64, PP]),
     "uqb_fastq_load_streamed": (C.c_int, [P, P, C.c_uint64, C.c_uint64, PP]),

@@ -391,6 +391,23 @@ extern "C" int uqb_array_alloc(uqb_ctx* ctx, uint64_t n, uint32_t width, uqb_arr
     return uqb_new_array(ctx, n, width, out);
 }
 
+// view of device memory the caller owns (a peer's window, another context's array on the same device): never freed here
+extern "C" int uqb_array_wrap(uqb_ctx* ctx, void* dev, uint64_t n, uint32_t width, uqb_array** out) {
+    uqb_array* a = new (std::nothrow) uqb_array();
+    if (!a) return uqb_fail(ctx, "out of host memory");
+    a->d = dev; a->n = n; a->width = width; a->owned = false;
+    *out = a;
+    return 0;
+}
+
+// device -> device copy on the context's stream; `src_dev` may live in a peer GPU's memory (unified addressing)
+extern "C" int uqb_array_copy_in(uqb_ctx* ctx, uqb_array* dst, uint64_t dst_offset, const void* src_dev, uint64_t nbytes) {
+    if (dst_offset + nbytes > dst->nbytes()) return uqb_fail(ctx, "copy_in: %llu bytes at offset %llu exceed an array of %llu",
+                                                                (unsigned long long)nbytes, (unsigned long long)dst_offset, (unsigned long long)dst->nbytes());
+    if (nbytes) UQB_CUDA(cudaMemcpyAsync((uint8_t*)dst->d + dst_offset, src_dev, nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
 extern "C" int uqb_array_upload(uqb_ctx* ctx, const void* host, uint64_t n, uint32_t width, uqb_array** out) {
     uqb_array* a;
     UQB_TRY(uqb_new_array(ctx, n, width, &a));

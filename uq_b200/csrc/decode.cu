@@ -58,16 +58,21 @@ __device__ __forceinline__ void dec_write(uint8_t* w, unsigned long long a, uint
     while (i) { w[--i] = (uint8_t)('0' + x % 10u); x /= 10u; }
 }
 
-// read length of a variable-length row: the first set bit is the marker's
-__device__ __forceinline__ uint32_t row_read_len(const uint8_t* row, uint32_t w, uint32_t bits, uint32_t dna_max, uint32_t variable) {
+// read length of a variable-length row: the first set bit is the marker's.  A row of a malformed
+// container may carry bits in front of the widest legal marker position: the length is clamped to dna_max (so that
+// no symbol index can leave the row) and *bad is set; uqb_decode then fails instead of emitting garbage.
+__device__ __forceinline__ uint32_t row_read_len(const uint8_t* row, uint32_t w, uint32_t bits, uint32_t dna_max, uint32_t variable, bool* bad) {
     if (!variable) return dna_max;
     for (uint32_t j = 0; j < w; j++) {
         unsigned b = row[j];
         if (b) {
             uint32_t p = 8 * j + (__clz(b) - 24);
-            return (8 * w - 1 - p) / bits;
+            uint32_t len = (8 * w - 1 - p) / bits;
+            if (len > dna_max) { *bad = true; len = dna_max; }
+            return len;
         }
     }
+    *bad = true;                 // no marker at all
     return 0;
 }
 
@@ -84,11 +89,13 @@ __device__ __forceinline__ uint32_t qname_text_len(const dec_params& P, uint64_t
 }
 
 __global__ void __launch_bounds__(DC) k_decode_len(const dec_params* __restrict__ Pp, const uint8_t* __restrict__ dna, uint64_t n,
-                                                  uint32_t* __restrict__ rec_len) {
+                                                  uint32_t* __restrict__ rec_len, unsigned long long* __restrict__ bad_row) {
     const uint64_t r = (uint64_t)blockIdx.x * DC + threadIdx.x;
     if (r >= n) return;
     const dec_params& P = *Pp;
-    const uint32_t len = row_read_len(dna + r * P.wd, P.wd, P.bb, P.dna_max, P.variable);
+    bool bad = false;
+    const uint32_t len = row_read_len(dna + r * P.wd, P.wd, P.bb, P.dna_max, P.variable, &bad);
+    if (bad) atomicMin(bad_row, (unsigned long long)r);
     rec_len[r] = qname_text_len(P, r) + 1 + len + 1 + 2 + len + 1;
 }
 
@@ -164,7 +171,8 @@ __global__ void __launch_bounds__(DC) k_decode_write(const dec_params* __restric
         if (lane == 0) o[run + P.suffix_len] = '\n';
         const uint32_t hl = run + P.suffix_len + 1;
         uint32_t len = 0;
-        if (lane == 0) len = row_read_len(drow, P.wd, P.bb, P.dna_max, P.variable);
+        bool bad_unused = false;
+        if (lane == 0) len = row_read_len(drow, P.wd, P.bb, P.dna_max, P.variable, &bad_unused);
         len = __shfl_sync(0xffffffffu, len, 0);
         uint8_t* od = o + hl;                  // DNA line
         uint8_t* oq = od + len + 3;            // after "\n+\n"
@@ -415,9 +423,23 @@ extern "C" int uqb_decode(uqb_ctx* ctx, const uqb_array* dna, const uqb_array* q
     UQB_TRY(uqb_dalloc_t(ctx, &rec_len, n));
     UQB_TRY(uqb_dalloc_t(ctx, &rec_off, n));
     UQB_TRY(uqb_dalloc_t(ctx, &d_total, 1));
-    if (n) UQB_LAUNCH(k_decode_len, uqb_blocks(n, DC), DC, 0, dp, (const uint8_t*)dna->d, n, rec_len);
+    unsigned long long* d_bad;
+    UQB_TRY(uqb_dalloc_t(ctx, &d_bad, 1));
+    UQB_CUDA(cudaMemsetAsync(d_bad, 0xFF, 8, ctx->stream));
+    if (n) UQB_LAUNCH(k_decode_len, uqb_blocks(n, DC), DC, 0, dp, (const uint8_t*)dna->d, n, rec_len, d_bad);
     UQB_TRY(uqb_scan_u32_to_u64(ctx, rec_len, rec_off, n, d_total));
     UQB_TRY(uqb_readback(ctx, &total, d_total, 8));
+    unsigned long long bad_row = ~0ull;
+    UQB_TRY(uqb_readback(ctx, &bad_row, d_bad, 8));
+    UQB_TRY(uqb_dfree(ctx, d_bad, 8));
+    if (bad_row != ~0ull) {
+        UQB_TRY(uqb_dfree(ctx, rec_len, n * 4));
+        UQB_TRY(uqb_dfree(ctx, rec_off, n * 8));
+        UQB_TRY(uqb_dfree(ctx, d_total, 8));
+        UQB_TRY(uqb_dfree(ctx, dp, sizeof(dec_params)));
+        for (size_t i = 0; i < temps.size(); i++) UQB_TRY(uqb_dfree(ctx, temps[i], temp_sizes[i]));
+        return uqb_fail(ctx, "decode: DNA row %llu has no valid length marker (malformed variable-length table)", bad_row);
+    }
     UQB_TRY(uqb_new_array(ctx, total, 1, fastq));
     bool done = false;
     const uint32_t in_words = ((DT_R * dna->width + 3) / 4 + 4 + 3) / 4 * 4 + (DT_R * qual->width + 3) / 4 + 8;

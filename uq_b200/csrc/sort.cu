@@ -699,6 +699,44 @@ extern "C" int uqb_narrow_u32(uqb_ctx* ctx, const uqb_array* a, uint32_t itemsiz
     return 0;
 }
 
+// Index arrays read from a container (DNA.key / QUAL.key / QNAME.key, uq.py:953, 957, 973) are widened to uint32 and
+// checked against the size of the table they index: a malformed file must not turn into an out-of-bounds gather.
+template <typename T>
+__global__ void __launch_bounds__(ST) k_index_u32(const T* __restrict__ in, uint64_t n, uint64_t bound, uint32_t* __restrict__ out,
+                                                 unsigned long long* __restrict__ first_bad) {
+    unsigned long long bad = ~0ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * ST + threadIdx.x; i < n; i += (uint64_t)gridDim.x * ST) {
+        const unsigned long long v = (unsigned long long)in[i];
+        if (v >= bound) { if (i < bad) bad = i; out[i] = 0u; }
+        else out[i] = (uint32_t)v;
+    }
+    if (bad != ~0ull) atomicMin(first_bad, bad);
+}
+
+extern "C" int uqb_index_u32(uqb_ctx* ctx, const uqb_array* a, uint64_t bound, uqb_array** out, int64_t* first_bad) {
+    if (bound > (1ull << 32)) return uqb_fail(ctx, "index_u32: tables of more than 2^32 rows are not supported");
+    UQB_TRY(uqb_new_array(ctx, a->n, 4, out));
+    *first_bad = -1;
+    if (a->n == 0) return 0;
+    unsigned long long* d_bad;
+    UQB_TRY(uqb_dalloc_t(ctx, &d_bad, 1));
+    UQB_CUDA(cudaMemsetAsync(d_bad, 0xFF, 8, ctx->stream));
+    const unsigned g = uqb_grid(ctx, a->n, ST, 16);
+    uint32_t* o = (uint32_t*)(*out)->d;
+    switch (a->width) {
+        case 1: UQB_LAUNCH_B(a->n * 5, k_index_u32<uint8_t>, g, ST, 0, (const uint8_t*)a->d, a->n, bound, o, d_bad); break;
+        case 2: UQB_LAUNCH_B(a->n * 6, k_index_u32<uint16_t>, g, ST, 0, (const uint16_t*)a->d, a->n, bound, o, d_bad); break;
+        case 4: UQB_LAUNCH_B(a->n * 8, k_index_u32<uint32_t>, g, ST, 0, (const uint32_t*)a->d, a->n, bound, o, d_bad); break;
+        case 8: UQB_LAUNCH_B(a->n * 12, k_index_u32<uint64_t>, g, ST, 0, (const uint64_t*)a->d, a->n, bound, o, d_bad); break;
+        default: UQB_TRY(uqb_dfree(ctx, d_bad, 8)); return uqb_fail(ctx, "index_u32: itemsize %u", a->width);
+    }
+    unsigned long long h = 0;
+    UQB_TRY(uqb_readback(ctx, &h, d_bad, 8));
+    UQB_TRY(uqb_dfree(ctx, d_bad, 8));
+    if (h != ~0ull) *first_bad = (int64_t)h;
+    return 0;
+}
+
 // ---- QNAME columns <-> big-endian key rows -------------------------------------------------------
 struct col_desc { const uint8_t* p[UQB_MAX_COLS]; uint32_t size[UQB_MAX_COLS]; uint32_t off[UQB_MAX_COLS]; uint32_t ncols; uint32_t width; };
 struct col_desc_out { uint8_t* p[UQB_MAX_COLS]; uint32_t size[UQB_MAX_COLS]; uint32_t off[UQB_MAX_COLS]; uint32_t ncols; uint32_t width; };

@@ -111,6 +111,22 @@ class Context:
         self.check(self.lib.uqb_array_alloc(self.h, int(n), int(width), C.byref(h)))
         return DeviceArray(self, h)
 
+    def wrap(self, dev_ptr, n, width):
+        """non-owning DeviceArray over device memory somebody else owns (a peer's window, another context's array)"""
+        h = C.c_void_p()
+        self.check(self.lib.uqb_array_wrap(self.h, C.c_void_p(int(dev_ptr)), int(n), int(width), C.byref(h)))
+        return DeviceArray(self, h)
+
+    def copy_in(self, dst, dst_offset, src_ptr, nbytes):
+        """device -> device copy from a raw device pointer (peer memory included) on this context's stream"""
+        self.check(self.lib.uqb_array_copy_in(self.h, dst.h, int(dst_offset), C.c_void_p(int(src_ptr)), int(nbytes)))
+
+    def index_u32(self, arr, bound):
+        """index member of a container (uint8/16/32/64) -> (uint32 DeviceArray, first position with value >= bound or -1)"""
+        h, bad = C.c_void_p(), C.c_int64()
+        self.check(self.lib.uqb_index_u32(self.h, arr.h, int(bound), C.byref(h), C.byref(bad)))
+        return DeviceArray(self, h), int(bad.value)
+
     def add_scalar_u32(self, arr, value):
         self.check(self.lib.uqb_add_scalar_u32(self.h, arr.h, int(value)))
 

@@ -22,6 +22,10 @@ from . import _lib as L
 from .device import Context, DeviceArray, PATTERN_ID
 
 PATTERNS = ['0.1', '1.1', '2.1', '3.1', '0.2', '1.2', '2.2', '3.2']
+# pattern id -> (transposed, rows reversed, bytes reversed) of the byte stream numpy.save emits for the logical table
+# m[N][B] (uq.py:263-270): row-major stream[r' * B + b'] or column-major stream[b' * N + r']
+PATTERN_DESC = {'0.1': (0, 0, 0), '1.2': (0, 0, 1), '3.2': (0, 1, 0), '2.1': (0, 1, 1),
+                '0.2': (1, 0, 0), '1.1': (1, 0, 1), '3.1': (1, 1, 0), '2.2': (1, 1, 1)}
 _DT = [(255, 'uint8', 1), (65535, 'uint16', 2), (4294967295, 'uint32', 4), (18446744073709551615, 'uint64', 8)]
 
 
@@ -166,6 +170,7 @@ def decide_alphabets(st, notricks=False, pad=False):
     bases = sorted(base_graph)                     # uq.py:456-457
     quals = sorted(qual_graph)
     n_qual = {}
+    n_qual_symbol = {}
     total_quals = len(quals)
     if not notricks:                               # uq.py:479-494
         for base in sorted(base_graph):            # py2 dict order in the reference; only matters for >=2 tricked bases (Q10)
@@ -179,12 +184,13 @@ def decide_alphabets(st, notricks=False, pad=False):
                     n_qual[base] = quals.index(q)
                 else:
                     total_quals += 1
-                    n_qual[base] = total_quals     # Q3
+                    n_qual[base] = total_quals     # Q3: a code with no entry in `qualities`
+                    n_qual_symbol[base] = q        # the quality character that code stands for (see config_of)
     bpb = bits_for(len(bases), pad)
     dna_max = int(st.dna_max)
     variable = int(st.dna_min) != dna_max
     bpq = bits_for(total_quals, pad)
-    return dict(bases=''.join(bases), qualities=''.join(quals), N_qual=n_qual, bits_per_base=bpb,
+    return dict(bases=''.join(bases), qualities=''.join(quals), N_qual=n_qual, N_qual_symbol=n_qual_symbol, bits_per_base=bpb,
                 bits_per_quality=bpq, variable_read_lengths=variable, dna_max=dna_max,
                 dna_bytes=-(-(bpb * (dna_max + variable)) // 8), qual_bytes=-(-(bpq * (dna_max + variable)) // 8),
                 base_distribution=base_graph, qual_distribution=qual_graph)
@@ -315,8 +321,7 @@ class DeviceMembers:
                 out[name] = flat.view(meta).reshape(-1)
             else:
                 n, width, pattern = meta
-                shape = (n, width) if pattern[0] in '02' else (width, n)
-                out[name] = np.ndarray(shape, dtype=np.uint8, buffer=flat, order='C' if pattern[2] == '1' else 'F')
+                out[name] = table_ndarray(flat, n, width, pattern)
         return out
 
     def free(self):
@@ -325,6 +330,36 @@ class DeviceMembers:
         for a, _, _ in self.items.values():
             a.free()
         self.items = {}
+
+
+def table_ndarray(flat, n, width, pattern):
+    """stream bytes of a laid-out table -> the ndarray object the reference hands to numpy.save (shape and memory
+    order of uq.py:263-270): (N, B) for patterns 0.x / 2.x, (B, N) for 1.x / 3.x; C order for x.1, Fortran for x.2"""
+    shape = (n, width) if pattern[0] in '02' else (width, n)
+    return np.ndarray(shape, dtype=np.uint8, buffer=flat, order='C' if pattern[2] == '1' else 'F')
+
+
+def stream_of(arr):
+    """ndarray as numpy.load returns a DNA / QUAL member -> its byte stream (memory order), no copy"""
+    if arr.flags.c_contiguous:
+        return arr.reshape(-1)
+    if arr.flags.f_contiguous:
+        return arr.T.reshape(-1)
+    return np.ascontiguousarray(arr).reshape(-1)
+
+
+def stream_rows(arr, pattern, a, b):
+    """The part of a laid-out member that holds the logical rows [a, b): contiguous uint8 bytes which are exactly the
+    stream of those rows alone under the same pattern (so uqb_unlayout on them yields rows a..b-1 in order).  Row-major
+    streams: one byte range (from the other end when the pattern reverses the rows); column-major streams: one run per
+    byte column.  This is how a rank of the sharded decode picks its share of a member."""
+    n, width = arr.shape if pattern[0] in '02' else arr.shape[::-1]
+    transposed, rev_r, _ = PATTERN_DESC[pattern]
+    flat = stream_of(arr)
+    first = n - b if rev_r else a
+    if not transposed:
+        return np.ascontiguousarray(flat[first * width:(first + b - a) * width])
+    return np.ascontiguousarray(flat.reshape(width, n)[:, first:first + b - a]).reshape(-1)
 
 
 def _layout(ctx, table, pattern):
@@ -451,6 +486,26 @@ def run_mix(ctx, dna, qual, cols, columns, sorted_on, raw_tables, pattern, sink=
 # ------------------------------------------------------------------------------------------------
 # encode
 # ------------------------------------------------------------------------------------------------
+def config_of(dec, n, prefix, suffix, separators, columns, sort, raw, pattern):
+    """config.json (uq.py:681-696, 898-903).
+
+    One key is added when - and only when - the N-trick took its "new quality" branch (uq.py:489-494): the
+    reference then stores a quality code that has no entry in `qualities`, its own decoder raises IndexError on such
+    a file and the original quality character is written nowhere.  `N_qual_symbol` = {base: that character} makes
+    the container decodable (decode_device reads it); every array and every other key stay exactly the reference's."""
+    config = {
+        'base_distribution': dec['base_distribution'], 'qual_distribution': dec['qual_distribution'],
+        'reads': n, 'bases': dec['bases'], 'qualities': dec['qualities'],
+        'variable_read_lengths': dec['variable_read_lengths'], 'bits_per_base': dec['bits_per_base'],
+        'bits_per_quality': dec['bits_per_quality'], 'N_qual': dec['N_qual'], 'dna_max': dec['dna_max'],
+        'QNAME_prefix': prefix, 'QNAME_suffix': suffix, 'QNAME_separators': separators,
+        'QNAME_columns': columns, 'sort': sort, 'raw': list(raw), 'pattern': pattern,
+    }
+    if dec.get('N_qual_symbol'):
+        config['N_qual_symbol'] = dict(dec['N_qual_symbol'])
+    return config
+
+
 def encode_device(ctx, fq, sort=None, raw=None, pattern=None, pad=False, notricks=False, stages=None, sink=None):
     """FASTQ already in HBM (device.Fastq) -> (DeviceMembers, config).  All O(N) work is on the GPU."""
     sort, raw, pattern = normalise_options(sort, raw, pattern)
@@ -487,15 +542,7 @@ def encode_device(ctx, fq, sort=None, raw=None, pattern=None, pad=False, notrick
         for a in [dna, qual] + cols:
             if id(a) not in keep:
                 a.free()
-    config = {
-        'base_distribution': dec['base_distribution'], 'qual_distribution': dec['qual_distribution'],
-        'reads': n, 'bases': dec['bases'], 'qualities': dec['qualities'],
-        'variable_read_lengths': dec['variable_read_lengths'], 'bits_per_base': dec['bits_per_base'],
-        'bits_per_quality': dec['bits_per_quality'], 'N_qual': dec['N_qual'], 'dna_max': dec['dna_max'],
-        'QNAME_prefix': prefix, 'QNAME_suffix': suffix, 'QNAME_separators': separators,
-        'QNAME_columns': columns, 'sort': sort, 'raw': list(raw), 'pattern': pattern,
-    }
-    return members, config
+    return members, config_of(dec, n, prefix, suffix, separators, columns, sort, raw, pattern)
 
 
 def encode(fastq, sort=None, raw=None, pattern=None, pad=False, notricks=False, ctx=None, stages=None):
@@ -534,11 +581,30 @@ def _upload_table(ctx, members, name, pattern):
         return logical(members[name + '.raw'])
     if name in members and name + '.key' in members:
         uniq = logical(members[name])
-        key = ctx.upload(np.ascontiguousarray(members[name + '.key'], dtype=np.uint32))
+        key = _upload_key(ctx, members[name + '.key'], uniq.n, name + '.key')
         tab = ctx.gather_rows(uniq, key)                                           # uq.py:953, 957
         uniq.free(); key.free()
         return tab
     raise UQError('ERROR: No %s data was found in this uQ file?!' % name)
+
+
+def _upload_key(ctx, key, n_rows, name):
+    """index member in its own dtype -> uint32 DeviceArray; every value must index the table it belongs to (a malformed
+    container must fail here, not fault in the gather: the reference raises IndexError at uq.py:953/957/973)."""
+    key = np.ascontiguousarray(key)
+    if key.dtype.kind not in 'ui' or key.ndim != 1:
+        raise UQError('ERROR: %s is not a one-dimensional integer array' % name)
+    if key.dtype.kind == 'i':
+        if key.size and int(key.min()) < 0:
+            raise UQError('ERROR: %s holds a negative index' % name)
+        key = key.view(np.dtype('uint%d' % (8 * key.dtype.itemsize)))
+    raw = ctx.upload(key)
+    k32, bad = ctx.index_u32(raw, n_rows)
+    raw.free()
+    if bad >= 0:
+        k32.free()
+        raise UQError('ERROR: %s[%d] points outside its table of %d rows (malformed uQ file)' % (name, bad, n_rows))
+    return k32
 
 
 def decode_device(ctx, dna, qual, dcols, config):
@@ -555,8 +621,14 @@ def decode_device(ctx, dna, qual, dcols, config):
     for i in range(256):
         p.qual_to_base[i] = -1
     for base, code in config['N_qual'].items():                                    # qual_N, uq.py:999
+        if not 0 <= code <= 255:
+            raise UQError('ERROR: N_qual code %r is out of range' % (code,))
         if code >= len(config['qualities']):
-            raise UQError('ERROR: N_qual code %d has no quality symbol; the reference decoder raises IndexError here (Q3)' % code)
+            # "new quality" branch of the N-trick (Q3): the code has no entry in `qualities`
+            sym = config.get('N_qual_symbol', {}).get(base)
+            if sym is None:
+                raise UQError('ERROR: N_qual code %d has no quality symbol; the reference decoder raises IndexError here (Q3)' % code)
+            p.qual_char[code] = ord(sym)
         p.qual_to_base[code] = ord(base)
     p.bits_per_base, p.bits_per_quality = config['bits_per_base'], config['bits_per_quality']
     p.variable, p.dna_max = int(config['variable_read_lengths']), config['dna_max']
@@ -606,12 +678,14 @@ def decode(members, config, ctx=None, out=None):
     cols_meta = config['QNAME_columns']
     keyed = 'QNAME.key' in members
     dcols = []
-    key = ctx.upload(np.ascontiguousarray(members['QNAME.key'], dtype=np.uint32)) if keyed else None
+    key = None
     for i, meta in enumerate(cols_meta):
         nm = 'QNAME_%d' % (i + 1) + ('' if keyed else '.raw')
         if nm not in members:
             raise UQError('ERROR: No QNAME data exists in this uQ file?')
         c = ctx.upload(np.ascontiguousarray(members[nm], dtype=meta['dtype']))
+        if keyed and key is None:
+            key = _upload_key(ctx, members['QNAME.key'], c.n, 'QNAME.key')
         if keyed:
             c2 = ctx.gather_rows(c, key)                                           # uq.py:973
             c.free()

@@ -229,6 +229,12 @@ class Comm:
         ctx.sync()                                       # the rows are produced on the context's stream
         if _TRACE["on"]:
             self._a2a_t0, self._a2a_bytes = _time.perf_counter(), sum(send_counts) * w
+        if isinstance(send, _Repeated):                  # the same rows to every peer (all-gather with uneven sizes)
+            st, rt = self._tensor(send.arr), self._tensor(recv)
+            roffs = [sum(recv_counts[:d]) * w for d in range(self.world)]
+            outs = [rt[roffs[d]:roffs[d] + recv_counts[d] * w] for d in range(self.world)]
+            work = self.dist.all_to_all(outs, [st] * self.world, async_op=True)
+            return recv, work
         work = self.dist.all_to_all_single(self._tensor(recv), self._tensor(send), [c * w for c in recv_counts],
                                            [c * w for c in send_counts], async_op=True)
         return recv, work
@@ -275,6 +281,147 @@ class Comm:
         out = ctx.compact_segments(ex["recv"], ex["roffs"], ex["recv_counts"], ex["width"])
         ex["recv"].free()                                # stream ordered: the copy above is queued before any reuse
         return out
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier(group=self.obj_group)
+
+    def all_gather_rows(self, ctx, local, counts):
+        """every rank contributes `local` (counts[rank] rows) -> DeviceArray with the rows of rank 0, 1, ... in that
+        order on every rank (the unique tables of the sharded decode).  One all-to-all in which every rank sends its
+        rows to everybody: per-peer sizes may differ, which NCCL's all-gather does not allow."""
+        if not self.dist:
+            return local
+        return self.all_to_all_rows(ctx, _Repeated(local, self.world), [local.n] * self.world, list(counts))
+
+
+class _Repeated:
+    """send buffer of an all-to-all in which every peer receives the same rows"""
+
+    def __init__(self, arr, times):
+        self.arr, self.times, self.width = arr, times, arr.width
+
+
+# ------------------------------------------------------------------------------------------------
+# W ranks on ONE device (SURVEY section 4d): every rank is a host thread with its own context (stream, arena); the
+# collectives are barriers over shared Python slots and device->device copies out of the peers' buffers.  Everything
+# else - uqb_partition_rows, uqb_gather_rows_segmented, uqb_compact_segments, uqb_scatter_u32, the merges, global_order
+# - is the code the NCCL ranks run, so the single-GPU test box exercises the whole sharded path.
+# ------------------------------------------------------------------------------------------------
+class LocalGroup:
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+
+class LocalComm:
+    dist = None
+
+    def __init__(self, group, rank):
+        self.group, self.rank, self.world = group, rank, group.world
+
+    def barrier(self):
+        self.group.barrier.wait(timeout=600)
+
+    def all_gather_object(self, obj):
+        g = self.group
+        g.slots[self.rank] = obj
+        self.barrier()
+        out = list(g.slots)
+        self.barrier()
+        return out
+
+    def exchange_counts(self, send_counts):
+        table = self.all_gather_object(list(map(int, send_counts)))
+        return [table[src][self.rank] for src in range(self.world)]
+
+    def _pull(self, ctx, recv, roffs, my_ptr, my_soffs, my_sbytes):
+        """recv[roffs[src] ...] <- the bytes rank `src` holds for this rank, for every src"""
+        ctx.sync()                                       # my own send buffer is final
+        infos = self.all_gather_object((int(my_ptr or 0), list(my_soffs), list(my_sbytes)))
+        for src in range(self.world):
+            ptr, soffs, sbytes = infos[src]
+            if sbytes[self.rank]:
+                ctx.copy_in(recv, roffs[src], ptr + soffs[self.rank], sbytes[self.rank])
+        ctx.sync()
+        self.barrier()                                   # nobody releases its send buffer before every peer has copied
+
+    def all_to_all_rows_start(self, ctx, send, send_counts, recv_counts):
+        w = send.width
+        recv = ctx.alloc(sum(recv_counts), w)
+        if isinstance(send, _Repeated):
+            ptr, soffs = send.arr.device_ptr.value, [0] * self.world
+        else:
+            ptr, soffs = send.device_ptr.value, [sum(send_counts[:d]) * w for d in range(self.world)]
+        roffs = [sum(recv_counts[:d]) * w for d in range(self.world)]
+        self._pull(ctx, recv, roffs, ptr, soffs, [c * w for c in send_counts])
+        return recv, None
+
+    def all_to_all_rows_wait(self, work):
+        pass
+
+    def all_to_all_rows(self, ctx, send, send_counts, recv_counts):
+        return self.all_to_all_rows_start(ctx, send, send_counts, recv_counts)[0]
+
+    def exchange_rows_start(self, ctx, table, order, send_counts, recv_counts):
+        w = table.width
+        send_pad, soffs = ctx.gather_rows_segmented(table, order, send_counts, 128)
+        roffs, total = [], 0
+        for c in recv_counts:
+            roffs.append(total)
+            total = (total + c * w + 127) // 128 * 128
+        recv_pad = ctx.alloc(total, 1)
+        self._pull(ctx, recv_pad, roffs, send_pad.device_ptr.value, soffs, [c * w for c in send_counts])
+        return dict(work=None, send=send_pad, recv=recv_pad, roffs=roffs, recv_counts=list(recv_counts), width=w)
+
+    def exchange_rows_wait(self, ctx, ex):
+        ex["send"].free()
+        out = ctx.compact_segments(ex["recv"], ex["roffs"], ex["recv_counts"], ex["width"])
+        ex["recv"].free()
+        return out
+
+    def all_gather_rows(self, ctx, local, counts):
+        return self.all_to_all_rows(ctx, _Repeated(local, self.world), [local.n] * self.world, list(counts))
+
+
+def run_local(world, fn, device=0):
+    """Run fn(ctx, comm) on `world` emulated ranks of one device (one host thread and one context per rank).
+    -> [fn's result per rank]; the first exception of any rank is re-raised after all threads have stopped."""
+    import threading
+    from .device import Context
+    group = LocalGroup(world)
+    results, errors = [None] * world, [None] * world
+    create = threading.Lock()
+
+    def body(rank):
+        ctx = None
+        try:
+            with create:                                 # library start-up (driver entry points) is not re-entrant
+                ctx = Context(device)
+            results[rank] = fn(ctx, LocalComm(group, rank))
+        except BaseException as e:                       # noqa: a failed rank must release the others
+            errors[rank] = e
+            group.barrier.abort()
+        finally:
+            if ctx is not None:
+                try:
+                    ctx.sync()
+                    ctx.close()
+                except Exception:
+                    pass
+
+    threads = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(world)]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    import threading as _t
+    real = [e for e in errors if e is not None and not isinstance(e, _t.BrokenBarrierError)]
+    if real:
+        raise real[0]
+    if any(errors):
+        raise [e for e in errors if e is not None][0]
+    return results
 
 
 # ------------------------------------------------------------------------------------------------
@@ -457,12 +604,19 @@ def global_order(ctx, comm, route, payloads):
 # the encode
 # ------------------------------------------------------------------------------------------------
 class ShardResult:
-    """This rank's part of every member.  `slices[name]` = (DeviceArray, kind, dtype or width); members
-    concatenate over the ranks in rank order (axis 0)."""
+    """This rank's part of every member.  `slices[name]` = (DeviceArray, kind, meta):
+      kind 'vector'  meta = dtype; the members concatenate over the ranks in rank order
+      kind 'table'   meta = dict(width, pattern, rows): the DeviceArray holds the byte stream of this rank's `rows`
+                     logical rows under `pattern` (uqb_layout of the local rows).  Where those bytes sit in the
+                     member's global stream follows from the pattern (place()): row-major streams are one byte range
+                     (counted from the other end when the pattern reverses the rows), column-major streams one run of
+                     `rows` bytes per byte column at col * N + first row ("layout").
+    place(comm) adds the global geometry (first row of this rank, total rows) with one small object collective."""
 
     def __init__(self, ctx=None, sink=None):
         self.slices = {}
         self.ctx, self.sink, self.host = ctx, sink, {}
+        self.geometry = {}          # name -> (first logical row / element of this rank, total over the ranks)
 
     def add(self, name, arr, kind, meta):
         """with a sink ((name, nbytes) -> pinned uint8 ndarray) the device->host copy starts right away"""
@@ -472,20 +626,34 @@ class ShardResult:
             arr.download_async(buf)
             self.host[name] = buf
 
+    def rows_of(self, name):
+        arr, kind, meta = self.slices[name]
+        return meta['rows'] if kind == 'table' else arr.n
+
+    def place(self, comm):
+        mine = {name: self.rows_of(name) for name in self.slices}
+        allr = comm.all_gather_object(mine)
+        for name in self.slices:
+            per = [a[name] for a in allr]
+            self.geometry[name] = (sum(per[:comm.rank]), sum(per))
+
     def nbytes(self):
         return sum(a.nbytes for a, _, _ in self.slices.values())
 
     def download(self):
+        """-> {name: flat uint8 ndarray (tables: the local stream) or typed 1-D ndarray (vectors)}"""
         out = {}
         if self.sink is not None:
             self.ctx.copy_sync()
         for name, (arr, kind, meta) in self.slices.items():
             flat = self.host[name][:arr.nbytes] if self.sink is not None else arr.download(dtype=np.uint8).reshape(-1)
-            if kind == "vector":
-                out[name] = flat.view(np.dtype(meta)).reshape(-1)
-            else:
-                out[name] = flat.reshape(arr.n, arr.width)
+            out[name] = flat.view(np.dtype(meta)).reshape(-1) if kind == "vector" else flat
         return out
+
+    def describe(self):
+        """picklable description of this rank's slices: name -> (kind, meta, first, total)"""
+        return {name: (kind, str(np.dtype(meta)) if kind == 'vector' else dict(meta)) + self.geometry[name]
+                for name, (_, kind, meta) in self.slices.items()}
 
     def free(self):
         if self.sink is not None and self.ctx is not None:
@@ -494,13 +662,33 @@ class ShardResult:
             arr.free()
         self.slices = {}
 
+    def __del__(self):
+        try:
+            if self.slices and self.ctx is not None and self.ctx.h:
+                self.free()             # queued device->host copies must finish before the arrays are recycled
+        except Exception:
+            pass
+
+
+def place_slice(dst_flat, kind, meta, first, total, data):
+    """Put one rank's slice `data` (flat bytes / typed vector) into the member's global buffer `dst_flat`."""
+    if kind == 'vector':
+        dst_flat[first:first + len(data)] = data
+        return
+    width, pattern, rows = meta['width'], meta['pattern'], meta['rows']
+    transposed, rev_r, _ = host.PATTERN_DESC[pattern]
+    at = total - first - rows if rev_r else first
+    if not transposed:
+        dst_flat[at * width:(at + rows) * width] = data
+    else:
+        dst_flat.reshape(width, total)[:, at:at + rows] = data.reshape(width, rows)
+
 
 def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, notricks=False, sink=None):
     """fq: this rank's contiguous range of the reads (device.Fastq).  -> (ShardResult, config); config is identical on
     every rank and equal to the single-GPU config of the whole file."""
     sort, raw, pattern = host.normalise_options(sort, raw, pattern)
-    if pattern != ['0.1', '0.1']:
-        raise host.UQError('ERROR: the multi-GPU path writes pattern 0.1 only (other layouts interleave the ranks\' rows)')
+    pat_of = {'DNA': pattern[0], 'QUAL': pattern[1]}
     _mark(ctx, comm, None)
     info = fq.split()
     n_local = int(info.n_reads)
@@ -582,6 +770,17 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
     _mark(ctx, comm, "pack+cols")
     # ---- run_mix over the ranks ----
     res = ShardResult(ctx, sink)
+
+    def add_table(name, rows_arr, t):
+        """this rank's rows of a DNA / QUAL member -> their stream under the table's --pattern (uq.py:257-270)"""
+        pat = pat_of[t]
+        if pat == '0.1':
+            stream = rows_arr
+        else:
+            stream = ctx.layout(rows_arr, pat)
+            rows_arr.free()
+        res.add(name, stream, 'table', dict(width=rows_arr.width, pattern=pat, rows=rows_arr.n))
+
     sorted_on = sort if sort in ('DNA', 'QUAL', 'QNAME') else None
     tables = {'DNA': dna, 'QUAL': qual, 'QNAME': ctx.columns_to_rows(cols)}
     keyed = {t: (t not in raw) for t in tables}
@@ -610,7 +809,7 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
                     res.add(meta['name'], c, 'vector', meta['dtype'])
                 g['uniq'].free()
             else:
-                res.add(t, g['uniq'], 'table', g['uniq'].width)
+                add_table(t, g['uniq'], t)
         else:
             g['uniq'].free()
             if not (t == sorted_on and route[0] == 'merge'):      # the merge route still needs the key
@@ -647,22 +846,104 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
             for meta in columns:
                 res.add(meta['name'] + '.raw', payload[meta['name'] + '.raw'], 'vector', meta['dtype'])
         else:
-            res.add(t + '.raw', payload[t + '.raw'], 'table', tables[t].width)
-    config = {
-        'base_distribution': dec['base_distribution'], 'qual_distribution': dec['qual_distribution'],
-        'reads': n_total, 'bases': dec['bases'], 'qualities': dec['qualities'],
-        'variable_read_lengths': dec['variable_read_lengths'], 'bits_per_base': dec['bits_per_base'],
-        'bits_per_quality': dec['bits_per_quality'], 'N_qual': dec['N_qual'], 'dna_max': dec['dna_max'],
-        'QNAME_prefix': prefix, 'QNAME_suffix': suffix, 'QNAME_separators': separators,
-        'QNAME_columns': columns, 'sort': sort, 'raw': list(raw), 'pattern': pattern,
-    }
-    return res, config
+            add_table(t + '.raw', payload[t + '.raw'], t)
+    if tables['QNAME'] is not None:
+        tables['QNAME'].free()
+    res.place(comm)
+    return res, host.config_of(dec, n_total, prefix, suffix, separators, columns, sort, raw, pattern)
 
 
-def assemble(comm, shard_members):
-    """Gather every rank's host slices on rank 0 and concatenate them (axis 0) -> members dict on rank 0, None
-    elsewhere.  (A production writer would let every rank write its slice at its byte offset of the tar.)"""
-    parts = comm.all_gather_object(shard_members)
+def assemble(comm, res):
+    """Gather every rank's host slices on rank 0 and put them at their place in the global members -> members dict
+    (name -> ndarray as numpy.save would receive it) on rank 0, None elsewhere.  Test / small-file helper: the container
+    writer (container.ShardedWriter) lets every rank write its slices at their byte offsets of the tar instead."""
+    parts = comm.all_gather_object((res.describe(), res.download()))
     if comm.rank != 0:
         return None
-    return {name: np.concatenate([p[name] for p in parts], axis=0) for name in parts[0]}
+    out = {}
+    for name, (kind, meta, _, total) in parts[0][0].items():
+        if kind == 'vector':
+            flat = np.empty(total, dtype=np.dtype(meta))
+        else:
+            flat = np.empty(total * meta['width'], dtype=np.uint8)
+        for desc, data in parts:
+            k, m, first, tot = desc[name]
+            place_slice(flat, k, m, first, tot, data[name])
+        out[name] = flat if kind == 'vector' else host.table_ndarray(flat, total, meta['width'], meta['pattern'])
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the decode (uq.py:926-1060) over the ranks: every rank produces the text of a contiguous range of records
+# ------------------------------------------------------------------------------------------------
+def split_evenly(n_total, rank, world):
+    base, rem = divmod(n_total, world)
+    first = rank * base + min(rank, rem)
+    return first, first + base + (1 if rank < rem else 0)
+
+
+def decode_sharded(ctx, comm, members, config):
+    """members / config as container.read_container returns them (every rank can read the container) -> (text, first,
+    last): uint8 ndarray with the FASTQ text of records [first, last) of the file; the texts concatenate in rank order.
+
+    Raw tables: a rank uploads only the part of the member's stream that holds its rows (host.stream_rows) and undoes
+    the layout on the device.  Keyed tables: every rank uploads 1/W of the unique table, the shares are all-gathered
+    over NVLink (all_gather_rows; they are the small side of a keyed container), and the rank's slice of the key
+    selects its rows ("decode")."""
+    n = int(config['reads'])
+    a, b = split_evenly(n, comm.rank, comm.world)
+    pat = config['pattern']
+
+    def upload_rows(arr, pattern, r0, r1):
+        width = arr.shape[1] if pattern[0] in '02' else arr.shape[0]
+        stream = ctx.upload(host.stream_rows(arr, pattern, r0, r1), width=1)
+        tab = ctx.unlayout(stream, r1 - r0, width, pattern)
+        stream.free()
+        return tab
+
+    def table(name, pattern):
+        if name + '.raw' in members:
+            arr = members[name + '.raw']
+            if (arr.shape[0] if pattern[0] in '02' else arr.shape[1]) != n:
+                raise host.UQError('ERROR: %s.raw does not hold %d rows' % (name, n))
+            return upload_rows(arr, pattern, a, b)
+        if name in members and name + '.key' in members:
+            arr = members[name]
+            u = arr.shape[0] if pattern[0] in '02' else arr.shape[1]
+            shares = [split_evenly(u, r, comm.world) for r in range(comm.world)]
+            mine = upload_rows(arr, pattern, *shares[comm.rank])
+            uniq = comm.all_gather_rows(ctx, mine, [e - s0 for s0, e in shares])
+            if uniq is not mine:
+                mine.free()
+            key = host._upload_key(ctx, members[name + '.key'][a:b], u, name + '.key')
+            tab = ctx.gather_rows(uniq, key)
+            uniq.free(); key.free()
+            return tab
+        raise host.UQError('ERROR: No %s data was found in this uQ file?!' % name)
+
+    dna = table('DNA', pat[0])
+    qual = table('QUAL', pat[1])
+    cols_meta = config['QNAME_columns']
+    keyed = 'QNAME.key' in members
+    dcols, key = [], None
+    for i, meta in enumerate(cols_meta):
+        nm = 'QNAME_%d' % (i + 1) + ('' if keyed else '.raw')
+        if nm not in members:
+            raise host.UQError('ERROR: No QNAME data exists in this uQ file?')
+        col = np.ascontiguousarray(members[nm], dtype=meta['dtype'])
+        if keyed:
+            if key is None:
+                key = host._upload_key(ctx, members['QNAME.key'][a:b], len(col), 'QNAME.key')
+            c = ctx.upload(col)                       # unique QNAME columns: small, every rank takes them whole
+            c2 = ctx.gather_rows(c, key)
+            c.free()
+            dcols.append(c2)
+        else:
+            dcols.append(ctx.upload(col[a:b]))
+    if key is not None:
+        key.free()
+    text = host.decode_device(ctx, dna, qual, dcols, config)
+    data = text.download().reshape(-1)
+    for arr in [dna, qual, text] + dcols:
+        arr.free()
+    return data, a, b
