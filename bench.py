@@ -235,33 +235,12 @@ def run_ours(args):
     top5 = [{"kernel": k, "launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / ms, 4),
              "GBps": round(v[2] / 1e9 / (v[1] / 1e3), 1) if v[1] > 0 and v[2] else None} for k, v in kern[:8]]
 
-    # ---- decode: logical tables resident in HBM -> FASTQ text resident in HBM, N = 1 only ----
+    # ---- decode, N = 1 only: three measurements, everything resident in HBM, text compared on the device ----
     decode = None
     if world == 1 and not args.no_decode:
         used, free, total = ctx.mem_info()
         if total - used > 2.8 * fbytes:             # the arena keeps what it mapped: room = total - bytes in use
-            fq = ctx.adopt_fastq(dev)
-            st = {}
-            dmembers, dcfg = host.encode_device(ctx, fq, sort="None", raw=["DNA", "QUAL", "QNAME"], stages=st)
-            text = host.decode_device(ctx, st["dna"], st["qual"], st["cols"], dcfg)       # warm-up
-            same = text.first_difference(dev) == -1
-            text.free()
-            ctx.sync()
-            ctx.span_begin()
-            for _ in range(args.steps):
-                text = host.decode_device(ctx, st["dna"], st["qual"], st["cols"], dcfg)
-                text.free()
-            dms = ctx.span_end() / args.steps
-            tab_bytes = st["dna"].nbytes + st["qual"].nbytes + sum(c.nbytes for c in st["cols"])
-            decode = {"value": n / (dms / 1e3), "unit": "reads/s", "ms_per_step": round(dms, 3),
-                      "gb_per_s_fastq": round(fbytes / 1e9 / (dms / 1e3), 2),
-                      "algorithmic_GBps": round((tab_bytes + fbytes) / 1e9 / (dms / 1e3), 1),
-                      "frac_of_peak": round((tab_bytes + fbytes) / 1e9 / (dms / 1e3) / peak, 4),
-                      "byte_exact": bool(same),
-                      "workload": "uQ -> FASTQ of the same %d reads: packed DNA / QUAL tables and QNAME columns resident in HBM -> "
-                                  "FASTQ text resident in HBM, compared byte for byte with the input on the device" % n}
-            dmembers.free()
-            fq.free()
+            decode = decode_block(ctx, host, dev, n, fbytes, peak, args.steps)
         else:
             decode = {"value": None, "note": "skipped: needs %.0f GB of free HBM" % (2.6 * fbytes / 1e9)}
 
@@ -383,6 +362,81 @@ def run_ours(args):
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def decode_block(ctx, host, dev, n, fbytes, peak, steps):
+    """uQ -> FASTQ on the device.
+      value / tables     packed DNA / QUAL tables and QNAME columns of the benched file (record order) -> text, compared
+                         byte for byte with the input (the round-1 measurement)
+      from_members       the members of a keyed container in layout 2.2 (--sort DNA --pattern 2.2 2.2): layouts undone,
+                         keys widened and checked, unique rows gathered, text produced (uq.py:943-973 + 1002-1058)
+      variable_length    configs[4]: 1 M reads of 1-20 kb, packed tables -> text, compared byte for byte with the input"""
+    def timed(fn):
+        fn().free()                                            # warm-up
+        ctx.sync()
+        ctx.span_begin()
+        for _ in range(steps):
+            fn().free()
+        return ctx.span_end() / steps
+
+    out = {}
+    # ---- tables in record order ----
+    fq = ctx.adopt_fastq(dev)
+    st = {}
+    dmembers, dcfg = host.encode_device(ctx, fq, sort="None", raw=["DNA", "QUAL", "QNAME"], stages=st)
+    text = host.decode_device(ctx, st["dna"], st["qual"], st["cols"], dcfg)
+    same = text.first_difference(dev) == -1
+    text.free()
+    dms = timed(lambda: host.decode_device(ctx, st["dna"], st["qual"], st["cols"], dcfg))
+    tab_bytes = st["dna"].nbytes + st["qual"].nbytes + sum(c.nbytes for c in st["cols"])
+    out.update({"value": n / (dms / 1e3), "unit": "reads/s", "ms_per_step": round(dms, 3),
+                "gb_per_s_fastq": round(fbytes / 1e9 / (dms / 1e3), 2),
+                "algorithmic_GBps": round((tab_bytes + fbytes) / 1e9 / (dms / 1e3), 1),
+                "frac_of_peak": round((tab_bytes + fbytes) / 1e9 / (dms / 1e3) / peak, 4), "byte_exact": bool(same),
+                "workload": "uQ -> FASTQ of the same %d reads: packed DNA / QUAL tables and QNAME columns resident in HBM -> "
+                            "FASTQ text resident in HBM, compared byte for byte with the input on the device" % n})
+    dmembers.free()
+    fq.free()
+    # ---- from the members of a keyed, transposed container ----
+    fq = ctx.adopt_fastq(dev)
+    km, kcfg = host.encode_device(ctx, fq, sort="DNA", pattern=["2.2", "2.2"])
+    fq.free()
+    text = host.decode_members_device(ctx, km, kcfg)
+    size_ok = text.nbytes == fbytes
+    text.free()
+    kms = timed(lambda: host.decode_members_device(ctx, km, kcfg))
+    mbytes = km.nbytes()
+    out["from_members"] = {"ms_per_step": round(kms, 3), "value": n / (kms / 1e3), "unit": "reads/s",
+                           "algorithmic_GBps": round((mbytes + fbytes) / 1e9 / (kms / 1e3), 1),
+                           "frac_of_peak": round((mbytes + fbytes) / 1e9 / (kms / 1e3) / peak, 4), "text_bytes_ok": bool(size_ok),
+                           "workload": "members of the keyed container of the same file (--sort DNA --pattern 2.2 2.2, %.1f GB): "
+                                       "unlayout + key check + unique-row gather + text; record order = DNA order "
+                                       "(round trip checked by tests/test_gpu_scale.py)" % (mbytes / 1e9)}
+    km.free()
+    # ---- configs[4]: variable-length long reads ----
+    import numpy as np
+    # the generator's table of 4096 log-spaced read lengths (same formula as the host generator of the tests)
+    tab = np.clip(np.floor(1000 * np.power(20000.0 / 1000.0, np.arange(4096, dtype=np.float64) / 4096.0)).astype(np.int64), 1000, 20000)
+    vn = 1_000_000
+    vdev = ctx.synth("ont", vn, (1000, 20000), 1005, len_table=tab)
+    fq = ctx.adopt_fastq(vdev)
+    vst = {}
+    vm, vcfg = host.encode_device(ctx, fq, sort="None", raw=["DNA", "QUAL", "QNAME"], stages=vst)
+    text = host.decode_device(ctx, vst["dna"], vst["qual"], vst["cols"], vcfg)
+    vsame = text.first_difference(vdev) == -1
+    text.free()
+    vms = timed(lambda: host.decode_device(ctx, vst["dna"], vst["qual"], vst["cols"], vcfg))
+    # algorithmic bytes: the SIGNIFICANT part of the right-aligned rows (2 + 7 bits per base) + columns + text
+    sig = (vcfg["bits_per_base"] + vcfg["bits_per_quality"]) / 8.0 * (vdev.nbytes / 2.0)
+    vab = sig + sum(c.nbytes for c in vst["cols"]) + vdev.nbytes
+    out["variable_length"] = {"ms_per_step": round(vms, 3), "value": vn / (vms / 1e3), "unit": "reads/s",
+                              "gb_per_s_fastq": round(vdev.nbytes / 1e9 / (vms / 1e3), 2),
+                              "algorithmic_GBps": round(vab / 1e9 / (vms / 1e3), 1), "frac_of_peak": round(vab / 1e9 / (vms / 1e3) / peak, 4),
+                              "byte_exact": bool(vsame),
+                              "workload": "configs[4]: %d reads of 1-20 kb (%.1f GB of FASTQ), tables %d + %d bytes per row "
+                                          "(right aligned, significant bytes counted) -> text" % (vn, vdev.nbytes / 1e9, vst["dna"].width, vst["qual"].width)}
+    vm.free(); fq.free(); vdev.free()
+    return out
 
 
 def parity_check(ctx, comm, rank, world, host, multigpu, opts, n_each=200_000):

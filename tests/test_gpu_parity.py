@@ -367,3 +367,86 @@ def test_ntrick_new_quality_branch_encodes_like_the_reference_and_decodes(ctx):
         stripped = {k: v for k, v in got_cfg.items() if k != "N_qual_symbol"}      # a reference-written container
         with pytest.raises(host.UQError, match="no quality symbol"):
             host.decode(got, stripped, ctx=ctx)
+
+
+@pytest.mark.parametrize("name", ["c2_keyed_sortDNA", "c3_casava_sortQNAME", "c5_variable_sortQUAL"])
+def test_mix_feed_serves_every_mix_like_a_fresh_encode(ctx, name):
+    """the --test feed loads and packs once, sorts each table at most once and serves every member of
+    every (sort, raw, pattern) mix as a gather / layout of resident arrays - the members must be those of a fresh
+    encode with the same options, bit for bit (dtype, shape, memory order)."""
+    from uq_b200 import host
+    fq, _, kw = golden_case(name)
+    dfq = ctx.load_fastq(fq)
+    feed = host.MixFeed(ctx, dfq, pad=kw["pad"], notricks=kw["notricks"])
+    launches_before = ctx.launches
+    pats = ['0.1', '1.1', '2.1', '3.1', '0.2', '1.2', '2.2', '3.2']
+    raws = [('DNA', 'QUAL', 'QNAME'), ('DNA', 'QUAL'), ('QUAL', 'QNAME'), ('DNA', 'QNAME'), ('DNA',), ('QUAL',), ('QNAME',), (None,)]
+    n = 0
+    for i, raw in enumerate(raws):
+        for j, sort in enumerate(['DNA', 'QUAL', 'QNAME', None]):
+            pat = [pats[(i + j) % 8], pats[(3 * i + j + 5) % 8]]
+            opts = dict(sort=sort if sort else 'None', raw=[r if r else 'none' for r in raw], pattern=pat)
+            got = feed.members(**opts)
+            want, want_cfg = host.encode(fq, ctx=ctx, pad=kw["pad"], notricks=kw["notricks"], **opts)
+            assert_members_equal(got, want, "%s %r" % (name, opts))
+            assert_config_equal(feed.config(**opts), want_cfg)
+            n += 1
+    assert n == 32
+    # the whole sweep cost three sorts: asking again launches nothing
+    before = ctx.launches
+    feed.members(sort='QUAL', raw=['DNA'], pattern=['2.2', '1.1'])
+    feed.members(sort='QUAL', raw=['DNA'], pattern=['2.2', '1.1'])
+    assert ctx.launches - before <= 40
+    feed.free()
+    dfq.free()
+
+
+@pytest.mark.parametrize("name", ["c1_raw_p01_31", "c2_keyed_sortDNA", "c3_casava_sortQNAME", "c4_twoNquals", "c6_checkpoints", "c7_offset_suffix_keyed"])
+def test_fused_scan_path_matches_reference_container(ctx, name, monkeypatch):
+    """UQB_FUSED_SCAN=1: one sweep (k_scan_hist) does the newline scan with decoupled look-back, line offsets, record
+    checks, histograms and the compact QNAME array; name statistics and the tokeniser then read the side array.  Same
+    containers as the default path, member for member."""
+    from uq_b200 import host
+    monkeypatch.setenv("UQB_FUSED_SCAN", "1")
+    from oracle import uq_literal as lit
+    fq, uq, kw = golden_case(name)
+    want, want_cfg = lit.read_container(uq)
+    got, got_cfg = host.encode(fq, ctx=ctx, **kw)
+    assert_members_equal(got, want, name)
+    assert_config_equal(got_cfg, want_cfg, name)
+    text = host.decode(got, got_cfg, ctx=ctx).tobytes()
+    assert records_multiset(text) == records_multiset(fq)
+
+
+def test_fused_scan_path_large_and_malformed(ctx, monkeypatch):
+    """the fused sweep over many tiles (look-back across tiles, records straddling tile ends) against the default path,
+    plus its error reporting (third line without '+', length mismatch) and its fallbacks (long records)."""
+    from uq_b200 import host
+    dev = ctx.synth("genome", 700_000, 150, 77, genome=70_000, pool=100_000)
+    data = dev.download().copy()
+    dev.free()
+    want, want_cfg = host.encode(data, ctx=ctx, sort="QUAL")
+    monkeypatch.setenv("UQB_FUSED_SCAN", "1")
+    l0 = ctx.launches
+    got, got_cfg = host.encode(data, ctx=ctx, sort="QUAL")
+    assert_members_equal(got, want, "fused scan, 700 k reads")
+    assert_config_equal(got_cfg, want_cfg)
+    bad = bytearray(data[:400_000].tobytes())
+    lines = bytes(bad).split(b"\n")
+    lines[4 * 700 + 2] = b"-"                               # record 700: third line does not start with '+'
+    lines[4 * 900 + 3] = lines[4 * 900 + 3][:-3]            # record 900: quality line three symbols short
+    broken = b"\n".join(lines[:4 * 1000]) + b"\n"
+    with pytest.raises(host.UQError, match="entry 700 the third line"):
+        host.encode(broken, ctx=ctx)
+    lines[4 * 700 + 2] = b"+"
+    broken = b"\n".join(lines[:4 * 1000]) + b"\n"
+    with pytest.raises(host.UQError, match="for entry 901"):
+        host.encode(broken, ctx=ctx)
+    # records longer than a tile's look-ahead: the sweep reports it and the line-offset kernels take over
+    from oracle import synth
+    long_fq = synth.make_fastq(kind="ont", n=40, length=(2000, 6000), seed=3)
+    monkeypatch.setenv("UQB_FUSED_SCAN", "0")
+    w2, c2 = host.encode(long_fq, ctx=ctx, sort="None", raw=["DNA", "QUAL", "QNAME"])
+    monkeypatch.setenv("UQB_FUSED_SCAN", "1")
+    g2, gc2 = host.encode(long_fq, ctx=ctx, sort="None", raw=["DNA", "QUAL", "QNAME"])
+    assert_members_equal(g2, w2, "long reads fall back")

@@ -49,7 +49,7 @@ ti = sum(a[0] for a in agg.values()) or 1
 ts = sum(a[1] for a in agg.values()) or 1
 src = {}
 print("line      inst%  stall%  notissued%  sass  source")
-for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:(100000 if os.environ.get("NCU_LINES_ALL") else 45)]:
     text = ""
     if ln:
         fn = os.path.join(root, "uq_b200", "csrc", ln[0])

@@ -46,6 +46,15 @@ __global__ void k_an_init(an_dev* s) {
     }
 }
 
+// the QNAME part of the accumulators alone (a new reference line restarts the name statistics, not the histograms)
+__global__ void k_an_init_names(an_dev* s) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s->last_count_mismatch[i] = -1;
+    for (int i = threadIdx.x; i <= UQB_HDR_MAX; i += blockDim.x) {
+        s->first_lcp_eq[i] = LLONG_MAX; s->first_lcs_eq[i] = LLONG_MAX;
+        s->first_short_prefix[i] = LLONG_MAX; s->first_short_suffix[i] = LLONG_MAX;
+    }
+}
+
 __global__ void __launch_bounds__(AN_THREADS) k_record_stats(const uint8_t* __restrict__ d, const uint64_t* __restrict__ line_off,
                                                            uint64_t n_reads, const uint8_t* __restrict__ ref, uint64_t rbase,
                                                            uint32_t first_len, an_dev* __restrict__ s) {
@@ -249,7 +258,10 @@ struct rd_smem {
 __global__ void __launch_bounds__(RD_THREADS) k_record_stats_names(const uint8_t* __restrict__ d, const uint64_t* __restrict__ line_off,
                                                                   uint64_t r_begin, uint64_t n_reads, const uint8_t* __restrict__ ref,
                                                                   uint64_t rbase, uint32_t first_len, an_dev* __restrict__ s,
-                                                                  unsigned int* __restrict__ fallback) {
+                                                                  unsigned int* __restrict__ fallback,
+                                                                  const uint8_t* __restrict__ names, uint32_t name_pitch) {
+    // names != nullptr: the QNAME lines come from the compact side array of sweep A (row r: length byte + text); the
+    // per-record FASTQ checks and read lengths were done there, only the name statistics are produced here
     extern __shared__ __align__(16) uint8_t rd_raw[];
     rd_smem* S = reinterpret_cast<rd_smem*>(rd_raw);
     const unsigned tid = threadIdx.x, lane = tid & 31u;
@@ -293,21 +305,29 @@ __global__ void __launch_bounds__(RD_THREADS) k_record_stats_names(const uint8_t
         const bool active = r < n_reads;
         unsigned lcp = 0, lcs = 0, name_len = 0;
         if (active) {
-            const ulonglong2 oa = __ldg(reinterpret_cast<const ulonglong2*>(line_off + 4 * r));
-            const ulonglong2 ob = __ldg(reinterpret_cast<const ulonglong2*>(line_off + 4 * r + 2));
-            const uint64_t o0 = oa.x, o1 = oa.y, o2 = ob.x, o3 = ob.y, o4 = __ldg(line_off + 4 * r + 4);
-            const uint64_t dlen = o2 - o1 - 1, qlen = o4 - o3 - 1;
-            const unsigned plus = o3 - o2 < 2 ? 0u : (unsigned)__ldg(d + o2);           // used after the name loop
-            if (dlen != qlen) bad_len = bad_len < (long long)r ? bad_len : (long long)r;
-            mn = dlen < mn ? dlen : mn; mx = dlen > mx ? dlen : mx;
-            const uint64_t nl64 = o1 - o0 - 1;
-            name_len = nl64 > 0xFFFFu ? 0xFFFFu : (unsigned)nl64;
+            unsigned plus = '+';
+            const uint8_t* name;
+            if (names) {
+                name = names + r * name_pitch + 1;
+                name_len = __ldg(name - 1);
+            } else {
+                const ulonglong2 oa = __ldg(reinterpret_cast<const ulonglong2*>(line_off + 4 * r));
+                const ulonglong2 ob = __ldg(reinterpret_cast<const ulonglong2*>(line_off + 4 * r + 2));
+                const uint64_t o0 = oa.x, o1 = oa.y, o2 = ob.x, o3 = ob.y, o4 = __ldg(line_off + 4 * r + 4);
+                const uint64_t dlen = o2 - o1 - 1, qlen = o4 - o3 - 1;
+                plus = o3 - o2 < 2 ? 0u : (unsigned)__ldg(d + o2);           // used after the name loop
+                if (dlen != qlen) bad_len = bad_len < (long long)r ? bad_len : (long long)r;
+                mn = dlen < mn ? dlen : mn; mx = dlen > mx ? dlen : mx;
+                const uint64_t nl64 = o1 - o0 - 1;
+                name_len = nl64 > 0xFFFFu ? 0xFFFFu : (unsigned)nl64;
+                name = d + o0;
+            }
             nm = name_len > nm ? name_len : nm;
             if (name_len > 255) {
                 atomicOr(fallback, 1u);                      // 8-bit packed counters could wrap
             } else {
                 const unsigned lim = name_len < first_len ? name_len : first_len;
-                const uint64_t addr = (uint64_t)(uintptr_t)d + o0;
+                const uint64_t addr = (uint64_t)(uintptr_t)name;
                 const uint64_t* q = reinterpret_cast<const uint64_t*>(addr & ~7ull);
                 const unsigned ph = (unsigned)(addr & 7ull);
                 // the first 64 bytes of the aligned window are fetched at once (independent loads), then consumed
@@ -347,7 +367,6 @@ __global__ void __launch_bounds__(RD_THREADS) k_record_stats_names(const uint8_t
                         sts_u32(wa, lds_u32(wa) + __byte_perm(1u, 0u, e));
                     }
                 }
-                const uint8_t* name = d + o0;
                 while (lcs < lim && __ldg(name + name_len - 1 - lcs) == S->first[first_len - 1 - lcs]) lcs++;
             }
             if (plus != '+') bad_plus = bad_plus < (long long)r ? bad_plus : (long long)r;
@@ -387,7 +406,7 @@ __global__ void __launch_bounds__(RD_THREADS) k_record_stats_names(const uint8_t
         bad_plus = e < bad_plus ? e : bad_plus; bad_len = f < bad_len ? f : bad_len;
     }
     if (lane == 0) {
-        atomicMin(&s->dna_min, mn);
+        if (mn != ~0ull) atomicMin(&s->dna_min, mn);
         atomicMax(&s->dna_max, mx);
         atomicMax(&s->max_name_len, nm);
         if (bad_plus != LLONG_MAX) atomicMin(&s->bad_plus, bad_plus);
@@ -571,6 +590,8 @@ __device__ __forceinline__ void pt_chunks(pt_smem* S, uint32_t dna_a, uint32_t q
         pb += eb[k].y;                               // the top byte collects group ids and is never read
     }
 }
+
+#include "scan_kernel.cuh"
 
 __global__ void __launch_bounds__(PT_THREADS, 1) k_pair_hist_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
                                                                const uint64_t* __restrict__ line_off, uint64_t r_begin, uint64_t n_reads,
@@ -774,7 +795,7 @@ static int stats_long_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsign
     if (r1 <= r0) return 0;
     UQB_CUDA(cudaFuncSetAttribute(k_pair_hist_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pt_smem)));
     UQB_LAUNCH_B((r1 - r0) * 128, k_record_stats_names, uqb_grid(ctx, r1 - r0, RD_THREADS, 8), RD_THREADS, sizeof(rd_smem), fq->d, fq->line_off, r0, r1,
-                 fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb);
+                 fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb, (const uint8_t*)nullptr, 0u);
     const uint64_t ab = (uint64_t)((double)fq->n * (double)(r1 - r0) / (double)(fq->n_reads ? fq->n_reads : 1)) + 32 * (r1 - r0);
     const uint64_t warps = (r1 - r0 + 0) ;
     const unsigned g = (unsigned)((warps + PT_THREADS / 32 - 1) / (PT_THREADS / 32) < (uint64_t)ctx->sm_count ? (warps + PT_THREADS / 32 - 1) / (PT_THREADS / 32)
@@ -793,7 +814,7 @@ static int stats_tiles_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsig
     const uint64_t ab = (uint64_t)((double)fq->n * (double)(r1 - r0) / (double)(fq->n_reads ? fq->n_reads : 1)) + 32 * (r1 - r0);
     // names only: 32 B of offsets, the name's sectors and the '+' sector per record
     UQB_LAUNCH_B((r1 - r0) * 128, k_record_stats_names, uqb_grid(ctx, r1 - r0, RD_THREADS, 8), RD_THREADS, sizeof(rd_smem), fq->d, fq->line_off, r0, r1,
-                 fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb);
+                 fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb, (const uint8_t*)nullptr, 0u);
     UQB_LAUNCH_B(ab, k_pair_hist_tiles, g2, PT_THREADS, sizeof(pt_smem), fq->d, fq->n, fq->line_off, r0, r1, s, d_fb);
     return 0;
 }
@@ -860,6 +881,137 @@ static int stats_finish(uqb_ctx* ctx, uqb_fastq* fq, an_dev* s, uqb_stats* out, 
     return 0;
 }
 
+// ================================================================================================
+// Sweep A over a resident file: k_scan_hist (scan_kernel.cuh) in two launches - a short one over the first tiles, whose
+// line count sizes the line-offset and QNAME arrays for the rest - then nothing else touches the FASTQ until the packer.
+// ================================================================================================
+__global__ void k_scan_set_ticket(unsigned int* ticket, unsigned int v) { *ticket = v; }
+
+int uqb_scan_release(uqb_ctx* ctx, uqb_fastq* fq) {
+    if (fq->names) { UQB_TRY(uqb_dfree(ctx, fq->names, 0)); fq->names = nullptr; }
+    if (fq->scan_acc) { UQB_TRY(uqb_dfree(ctx, fq->scan_acc, 0)); fq->scan_acc = nullptr; }
+    fq->name_pitch = 0; fq->names_cap = 0; fq->line_cap = 0;
+    return 0;
+}
+
+// Opt-in (UQB_FUSED_SCAN=1).  Measured on a B200 at 100 M reads x 150 bp (profiles/README.md, round 2): the fused sweep
+// reads the FASTQ once (DRAM reads of the step: 2.0 x F instead of 5.6 x F) but takes 51 ms + 6 ms of name statistics
+// against 48 ms for the four line-offset based kernels - it is instruction-issue bound (1.0 warp instructions per byte:
+// newline ranking 23 %, histogram loop 40 %, deferred line-offset / QNAME writes 10 %), not bandwidth bound, so fewer
+// bytes did not buy time.  The default path therefore stays with the separate kernels.
+static bool scan_enabled() {
+    const char* e = getenv("UQB_FUSED_SCAN");
+    return e && e[0] == '1';
+}
+
+int uqb_scan_file(uqb_ctx* ctx, uqb_fastq* fq, bool* done) {
+    *done = false;
+    if (!scan_enabled() || fq->n < 64 || (((uintptr_t)fq->d) & 15) != 0) return 0;
+    const uint64_t n = fq->n;
+    if ((n + SC_T - 1) / SC_T >= (1ull << 31)) return 0;
+    // ---- a look at the head of the file: length of the first QNAME line (row pitch of the side array), line density ----
+    uint8_t head[4096];
+    const size_t hn = n < sizeof(head) ? (size_t)n : sizeof(head);
+    UQB_TRY(uqb_readback(ctx, head, fq->d, hn));
+    size_t first_len = 0, head_lines = 0;
+    while (first_len < hn && head[first_len] != '\n') first_len++;
+    if (first_len == hn || first_len > 200) return 0;                 // no newline in sight / long names: line-offset kernels
+    for (size_t i = 0; i < hn; i++) head_lines += head[i] == '\n';
+    uint32_t pitch = (uint32_t)((first_len + 1 + 24 + 15) / 16 * 16);
+    if (pitch < 32) pitch = 32;
+    if (pitch > 256) pitch = 256;
+    const uint32_t ntiles = (uint32_t)((n + SC_T - 1) / SC_T);
+    const uint32_t t_first = ntiles < 192 ? ntiles : 128;              // the first launch: up to 128 tiles (2.7 MB)
+
+    uint64_t* status = nullptr;
+    unsigned int *ticket = nullptr, *d_fb = nullptr;
+    unsigned long long* d_total = nullptr;
+    an_dev* acc = nullptr;
+    UQB_TRY(uqb_dalloc_t(ctx, &status, ntiles));
+    UQB_TRY(uqb_dalloc_t(ctx, &ticket, 1));
+    UQB_TRY(uqb_dalloc_t(ctx, &d_fb, 1));
+    UQB_TRY(uqb_dalloc_t(ctx, &d_total, 1));
+    UQB_TRY(uqb_dalloc_t(ctx, &acc, 1));
+    UQB_CUDA(cudaMemsetAsync(status, 0, (size_t)ntiles * 8, ctx->stream));
+    UQB_CUDA(cudaMemsetAsync(d_fb, 0, 4, ctx->stream));
+    UQB_CUDA(cudaMemsetAsync(d_total, 0, 8, ctx->stream));
+    UQB_LAUNCH(k_an_init, 1, 256, 0, acc);
+    UQB_CUDA(cudaFuncSetAttribute(k_scan_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sc_smem)));
+    UQB_CUDA(cudaFuncSetAttribute(k_scan_hist, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+
+    auto release = [&]() {
+        uqb_dfree(ctx, status, 0); uqb_dfree(ctx, ticket, 0); uqb_dfree(ctx, d_fb, 0); uqb_dfree(ctx, d_total, 0);
+    };
+    uint64_t* line_off = nullptr;
+    uint8_t* names = nullptr;
+    uint64_t cap_lines = 0, cap_records = 0;
+    bool ok = true;
+    for (int pass = 0; pass < 2 && ok; pass++) {
+        const uint32_t t0 = pass == 0 ? 0u : t_first, t1 = pass == 0 ? t_first : ntiles;
+        if (t1 <= t0) break;
+        // capacity: pass 0 from the density of the head (x2), pass 1 from the density of the first tiles (+6 %)
+        uint64_t want_lines;
+        if (pass == 0) {
+            const double dens = (double)(head_lines + 1) / (double)hn;
+            want_lines = (uint64_t)(dens * 2.0 * (double)((uint64_t)t1 * SC_T + SC_LOAD)) + 4096;
+        } else {
+            uint64_t st = 0;
+            UQB_TRY(uqb_readback(ctx, &st, status + (t_first - 1), 8));
+            unsigned int fb = 0;
+            UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
+            if (fb || (st >> 62) != 2ull) { ok = false; break; }
+            const uint64_t lines_head = st & ((1ull << 62) - 1);
+            const double dens = (double)(lines_head + 1) / (double)((uint64_t)t_first * SC_T);
+            want_lines = (uint64_t)(dens * 1.06 * (double)n) + (1u << 16);
+        }
+        if (want_lines > n + 1) want_lines = n + 1;
+        const uint64_t want_records = want_lines / 4 + 2;
+        uint64_t* lo2;
+        uint8_t* nm2;
+        UQB_TRY(uqb_dalloc_t(ctx, &lo2, want_lines + 2));
+        UQB_TRY(uqb_dalloc(ctx, (void**)&nm2, want_records * pitch + 64));
+        if (line_off) {                                               // keep what the first launch produced
+            UQB_CUDA(cudaMemcpyAsync(lo2, line_off, (cap_lines + 1 < want_lines + 1 ? cap_lines + 1 : want_lines + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            UQB_CUDA(cudaMemcpyAsync(nm2, names, (cap_records < want_records ? cap_records : want_records) * pitch, cudaMemcpyDeviceToDevice, ctx->stream));
+            UQB_TRY(uqb_dfree(ctx, line_off, 0));
+            UQB_TRY(uqb_dfree(ctx, names, 0));
+        } else {
+            UQB_TRY(uqb_split_set_first(ctx, lo2));
+        }
+        line_off = lo2; names = nm2; cap_lines = want_lines; cap_records = want_records;
+        sc_params P;
+        P.d = fq->d; P.n = n; P.n_avail = n; P.tile_end = t1; P.status = status; P.ticket = ticket;
+        P.line_off = line_off; P.cap_lines = cap_lines; P.names = names; P.name_pitch = pitch; P.cap_records = cap_records;
+        P.s = acc; P.fallback = d_fb; P.lines_total = d_total;
+        UQB_LAUNCH(k_scan_set_ticket, 1, 1, 0, ticket, t0);
+        const unsigned gmax = (unsigned)SC_CTAS_PER_SM * (unsigned)ctx->sm_count;
+        const unsigned grid = (t1 - t0) < gmax ? (t1 - t0) : gmax;
+        const uint64_t span = (uint64_t)(t1 - t0) * SC_T;
+        UQB_LAUNCH_B(span < n ? span : n, k_scan_hist, grid, SC_THREADS, sizeof(sc_smem), P);
+    }
+    unsigned int fb = 0;
+    unsigned long long total = 0;
+    if (ok) {
+        UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
+        UQB_TRY(uqb_readback(ctx, &total, d_total, 8));
+        if (fb) ok = false;
+        uqb_timer_add_bytes(ctx, 8 * total + total / 4 * pitch);       // line offsets and QNAME rows written
+    }
+    release();
+    if (!ok) {
+        if (line_off) UQB_TRY(uqb_dfree(ctx, line_off, 0));
+        if (names) UQB_TRY(uqb_dfree(ctx, names, 0));
+        UQB_TRY(uqb_dfree(ctx, acc, 0));
+        return 0;                                                     // the caller runs the line-offset based kernels
+    }
+    fq->line_off = line_off; fq->line_cap = cap_lines + 2;
+    fq->n_lines = total; fq->n_reads = total / 4;
+    fq->names = names; fq->name_pitch = pitch; fq->names_cap = cap_records;
+    fq->scan_acc = acc;
+    *done = true;
+    return 0;
+}
+
 // Multi-GPU: this handle holds records [rbase, rbase + n) of a larger file whose first QNAME line is `name`.
 // uqb_analyze then reports prefix/suffix/separator statistics against that line (record indices stay local).
 extern "C" int uqb_fastq_set_reference(uqb_ctx* ctx, uqb_fastq* fq, const uint8_t* name, uint32_t len, uint64_t rbase) {
@@ -884,6 +1036,27 @@ extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
     uint64_t flen = 0;
     UQB_TRY(stats_names(ctx, fq, out, &flen));
     if (fq->ref_name) flen = fq->ref_len;        // multi-GPU shard: everything is measured against the global line 1
+    if (fq->scan_acc && fq->names) {
+        // sweep A has produced the histograms, the record checks and the compact QNAME array: only the name statistics
+        // (against the current reference line) are left, and they never touch the FASTQ bytes
+        an_dev* acc = (an_dev*)fq->scan_acc;
+        unsigned int* d_fb;
+        UQB_TRY(uqb_dalloc_t(ctx, &d_fb, 1));
+        UQB_CUDA(cudaMemsetAsync(d_fb, 0, 4, ctx->stream));
+        UQB_LAUNCH(k_an_init_names, 1, 256, 0, acc);
+        UQB_LAUNCH_B(N * fq->name_pitch, k_record_stats_names, uqb_grid(ctx, N, RD_THREADS, 8), RD_THREADS, sizeof(rd_smem), fq->d, fq->line_off,
+                     0ull, N, fq->ref_name ? fq->ref_name : fq->d, fq->rbase, (uint32_t)flen, acc, d_fb, (const uint8_t*)fq->names, fq->name_pitch);
+        unsigned int fb = 0;
+        UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
+        UQB_TRY(uqb_dfree(ctx, d_fb, 4));
+        if (fb) {                                 // line 1 defeats the packed counters: generic name statistics
+            UQB_LAUNCH(k_an_init_names, 1, 256, 0, acc);
+            UQB_LAUNCH(k_record_stats, uqb_blocks(N, AN_THREADS), AN_THREADS, 0, fq->d, fq->line_off, N,
+                       fq->ref_name ? fq->ref_name : fq->d, fq->rbase, (uint32_t)flen, acc);
+        }
+        UQB_TRY(stats_finish(ctx, fq, acc, out, flen));
+        return 0;
+    }
     an_dev* s;
     UQB_TRY(uqb_dalloc_t(ctx, &s, 1));
     bool done_fast = false;

@@ -33,12 +33,21 @@ struct qn_params {
 struct qn_flags { long long bad_record; unsigned int has_nul; unsigned int pad; };
 
 __global__ void __launch_bounds__(QN) k_qname_tokens(const uint8_t* __restrict__ d, const uint64_t* __restrict__ line_off, uint64_t n_reads,
-                                                    qn_params P, qn_flags* __restrict__ flags) {
+                                                    qn_params P, qn_flags* __restrict__ flags,
+                                                    const uint8_t* __restrict__ names, uint32_t name_pitch) {
     const uint64_t r = (uint64_t)blockIdx.x * QN + threadIdx.x;
     if (r >= n_reads) return;
-    const uint64_t o0 = line_off[4 * r];
-    const uint64_t n = line_off[4 * r + 1] - o0 - 1;
-    const uint8_t* name = d + o0;
+    // names != nullptr: QNAME lines from the compact side array of sweep A (row r: length byte + text)
+    uint64_t n;
+    const uint8_t* name;
+    if (names) {
+        name = names + r * name_pitch + 1;
+        n = name[-1];
+    } else {
+        const uint64_t o0 = line_off[4 * r];
+        n = line_off[4 * r + 1] - o0 - 1;
+        name = d + o0;
+    }
     uint64_t mid_start = P.prefix_len;
     uint64_t mid_end = n > P.suffix_len ? n - P.suffix_len : 0;
     if (mid_end < mid_start) mid_end = mid_start;
@@ -139,12 +148,12 @@ __global__ void __launch_bounds__(QN) k_col_reduce(const int64_t* __restrict__ v
 // zero-padded token bytes of records [0, n) as rows of `w` bytes
 __global__ void __launch_bounds__(QN) k_token_rows(const uint8_t* __restrict__ d, const uint64_t* __restrict__ line_off,
                                                   const uint32_t* __restrict__ span, uint32_t prefix_len, uint32_t w, uint64_t n,
-                                                  uint8_t* __restrict__ rows) {
+                                                  uint8_t* __restrict__ rows, const uint8_t* __restrict__ names, uint32_t name_pitch) {
     const uint64_t r = (uint64_t)blockIdx.x * QN + threadIdx.x;
     if (r >= n) return;
     const uint32_t sp = span[r];
     const uint32_t len = sp & SPAN_MAXLEN, rel = (sp >> SPAN_LEN_BITS) & SPAN_MAXLEN;
-    const uint8_t* src = d + line_off[4 * r] + prefix_len + rel;
+    const uint8_t* src = (names ? names + r * name_pitch + 1 : d + line_off[4 * r]) + prefix_len + rel;
     uint8_t* dst = rows + r * w;
     for (uint32_t i = 0; i < w; i++) dst[i] = i < len ? __ldg(src + i) : (uint8_t)0;
 }
@@ -190,7 +199,7 @@ int uqb_fastq_free_qcols(uqb_ctx* ctx, uqb_fastq* fq);
 static int distinct_of_prefix(uqb_ctx* ctx, uqb_fastq* fq, const uqb_qcol& qc, uint32_t w, uint64_t n, uint64_t* distinct) {
     uint8_t* rows;
     UQB_TRY(uqb_dalloc(ctx, (void**)&rows, n * w + 64));
-    if (w) UQB_LAUNCH(k_token_rows, uqb_blocks(n, QN), QN, 0, fq->d, fq->line_off, qc.span, fq->prefix_len, w, n, rows);
+    if (w) UQB_LAUNCH(k_token_rows, uqb_blocks(n, QN), QN, 0, fq->d, fq->line_off, qc.span, fq->prefix_len, w, n, rows, (const uint8_t*)fq->names, fq->name_pitch);
     uint32_t *perm, *gid;
     UQB_TRY(uqb_sort_rows_impl(ctx, rows, n, w, &perm, &gid, distinct));
     UQB_TRY(uqb_dfree(ctx, perm, n * 4));
@@ -228,7 +237,8 @@ extern "C" int uqb_qname_scan_ex(uqb_ctx* ctx, uqb_fastq* fq, uint32_t prefix_le
     qn_flags* dflags;
     UQB_TRY(uqb_dalloc_t(ctx, &dflags, 1));
     UQB_CUDA(cudaMemcpyAsync(dflags, &hf, sizeof(hf), cudaMemcpyHostToDevice, ctx->stream));
-    UQB_LAUNCH(k_qname_tokens, uqb_blocks(N, QN), QN, 0, fq->d, fq->line_off, N, P, dflags);
+    UQB_LAUNCH_B(fq->names ? N * fq->name_pitch + 12 * N * ncols : 0, k_qname_tokens, uqb_blocks(N, QN), QN, 0, fq->d, fq->line_off, N, P, dflags,
+                 (const uint8_t*)fq->names, fq->name_pitch);
     col_red* dred;
     UQB_TRY(uqb_dalloc_t(ctx, &dred, ncols));
     UQB_LAUNCH(k_col_red_init, 1, UQB_MAX_COLS, 0, dred, (int)ncols);
@@ -279,7 +289,7 @@ extern "C" int uqb_qname_scan_ex(uqb_ctx* ctx, uqb_fastq* fq, uint32_t prefix_le
         // full dictionary: ranks, first occurrences, distinct counts at every checkpoint
         uint8_t* rows;
         UQB_TRY(uqb_dalloc(ctx, (void**)&rows, N * w + 64));
-        if (w) UQB_LAUNCH(k_token_rows, uqb_blocks(N, QN), QN, 0, fq->d, fq->line_off, qc.span, prefix_len, w, N, rows);
+        if (w) UQB_LAUNCH(k_token_rows, uqb_blocks(N, QN), QN, 0, fq->d, fq->line_off, qc.span, prefix_len, w, N, rows, (const uint8_t*)fq->names, fq->name_pitch);
         uint32_t *perm, *gid;
         uint64_t u = 0;
         UQB_TRY(uqb_sort_rows_impl(ctx, rows, N, w, &perm, &gid, &u));

@@ -160,6 +160,7 @@ int uqb_fastq_free_qcols(uqb_ctx* ctx, uqb_fastq* fq) { return free_qcols(ctx, f
 extern "C" int uqb_fastq_free(uqb_ctx* ctx, uqb_fastq* fq) {
     if (!fq) return 0;
     UQB_TRY(free_qcols(ctx, fq));
+    UQB_TRY(uqb_scan_release(ctx, fq));
     if (fq->line_off) UQB_TRY(uqb_dfree(ctx, fq->line_off, (fq->n_lines + 1) * 8));
     delete fq->cached_stats;
     if (fq->ref_name) UQB_TRY(uqb_dfree(ctx, fq->ref_name, 0));
@@ -199,6 +200,17 @@ extern "C" int uqb_split(uqb_ctx* ctx, uqb_fastq* fq, uqb_split_info* info) {
     }
     info->n_bytes = fq->n;
     if (fq->line_off) { UQB_TRY(uqb_dfree(ctx, fq->line_off, (fq->n_lines + 1) * 8)); fq->line_off = nullptr; }
+    UQB_TRY(uqb_scan_release(ctx, fq));
+    {   // sweep A: newline scan, line offsets, record checks, histograms and the compact QNAME array in ONE pass
+        bool done = false;
+        UQB_TRY(uqb_scan_file(ctx, fq, &done));
+        if (done) {
+            info->n_lines = fq->n_lines;
+            info->n_reads = fq->n_reads;
+            info->status = (fq->n_lines % 4 == 0) ? 0 : 1;
+            return 0;
+        }
+    }
     uint64_t ntiles = (fq->n + SP_TILE - 1) / SP_TILE;
     uint64_t total = 0;
     uint32_t* counts = nullptr;

@@ -506,9 +506,10 @@ def config_of(dec, n, prefix, suffix, separators, columns, sort, raw, pattern):
     return config
 
 
-def encode_device(ctx, fq, sort=None, raw=None, pattern=None, pad=False, notricks=False, stages=None, sink=None):
-    """FASTQ already in HBM (device.Fastq) -> (DeviceMembers, config).  All O(N) work is on the GPU."""
-    sort, raw, pattern = normalise_options(sort, raw, pattern)
+def prepare(ctx, fq, pad=False, notricks=False):
+    """Pass 1 - Pass 4 of the reference (uq.py:338-735) on a FASTQ that is resident in HBM: statistics, decisions,
+    packed DNA / QUAL tables and encoded QNAME columns.  -> dict(stats, dec, columns, prefix, suffix, separators,
+    total, dna, qual, cols); everything a mix (run_mix) or the --test feed (MixFeed) needs."""
     info = _timed(ctx, 'split', fq.split)
     if info.status == 1:                                                           # uq.py:86-87
         raise UQError('ERROR: The FASTQ file provided contains' + str(info.n_lines) + 'rows, which is not divisible by 4!')
@@ -533,16 +534,148 @@ def encode_device(ctx, fq, sort=None, raw=None, pattern=None, pad=False, notrick
     columns = decide_columns(colstats, n, fq.qname_dict)
     dna, qual = _timed(ctx, 'pack', fq.pack, pack_params(dec))
     cols = _timed(ctx, 'qname_encode', fq.qname_encode, column_specs(columns))
+    return dict(stats=st, dec=dec, columns=columns, dna=dna, qual=qual, cols=cols, prefix=prefix, suffix=suffix,
+                separators=separators, total=n)
+
+
+def encode_device(ctx, fq, sort=None, raw=None, pattern=None, pad=False, notricks=False, stages=None, sink=None):
+    """FASTQ already in HBM (device.Fastq) -> (DeviceMembers, config).  All O(N) work is on the GPU."""
+    sort, raw, pattern = normalise_options(sort, raw, pattern)
+    p = prepare(ctx, fq, pad=pad, notricks=notricks)
+    dna, qual, cols, columns = p['dna'], p['qual'], p['cols'], p['columns']
     if stages is not None:
-        stages.update(stats=st, dec=dec, columns=columns, dna=dna, qual=qual, cols=cols, prefix=prefix, suffix=suffix,
-                      separators=separators, total=n)
+        stages.update(p)
     members = run_mix(ctx, dna, qual, cols, columns, sort, raw, pattern, sink=sink)
     if stages is None:
         keep = {id(a) for a, _, _ in members.items.values()}
         for a in [dna, qual] + cols:
             if id(a) not in keep:
                 a.free()
-    return members, config_of(dec, n, prefix, suffix, separators, columns, sort, raw, pattern)
+    return members, config_of(p['dec'], p['total'], p['prefix'], p['suffix'], p['separators'], columns, sort, raw, pattern)
+
+
+class MixFeed:
+    """Device-resident feed of the --test search (test_patterns uq.py:290-334, loop uq.py:855-889).
+
+    The reference re-sorts, re-uniques and rot90s its tables for every candidate mix.  Here the FASTQ is loaded and
+    Pass 1-4 run ONCE; the packed tables stay in HBM, each of DNA / QUAL / QNAME is sorted at most once (one
+    uqb_sort_rows gives its stable argsort, its unique table and its key both in record and in sorted order), and a
+    member of any (sort, raw, pattern) mix is then only a gather (uqb_gather_rows) and / or a layout (uqb_layout) of
+    cached arrays.  members(sort, raw, pattern) returns host ndarrays exactly like encode() - same bytes, same dtypes,
+    same memory order - so the compressor / argmin side of --test stays the reference's."""
+
+    def __init__(self, ctx, fq, pad=False, notricks=False):
+        self.ctx = ctx
+        self.p = prepare(ctx, fq, pad=pad, notricks=notricks)
+        self.tables = {'DNA': self.p['dna'], 'QUAL': self.p['qual'], 'QNAME': None}
+        self.sorted = {}            # table -> dict(perm, key, key_sorted, uniq, nu)
+        self.cache = {}             # derived device arrays: ('rows', T, S) / ('key', T, S) / ('stream', ...) ...
+        self.kernel_launches_after_prepare = ctx.launches
+
+    def config(self, sort, raw, pattern):
+        sort, raw, pattern = normalise_options(sort, raw, pattern)
+        p = self.p
+        return config_of(p['dec'], p['total'], p['prefix'], p['suffix'], p['separators'], p['columns'], sort, raw, pattern)
+
+    def _table(self, t):
+        if self.tables[t] is None:                       # QNAME sort rows: the columns concatenated big-endian (uq.py:814-816)
+            self.tables[t] = self.ctx.columns_to_rows(self.p['cols'])
+        return self.tables[t]
+
+    def _sorted(self, t):
+        if t not in self.sorted:
+            perm, key, uniq, nu, key_sorted = self.ctx.sort_rows(self._table(t), want_perm=True, want_key=True, want_uniq=True,
+                                                                 want_key_sorted=True)
+            self.sorted[t] = dict(perm=perm, key=key, uniq=uniq, nu=nu, key_sorted=key_sorted)
+        return self.sorted[t]
+
+    def _cached(self, tag, make):
+        if tag not in self.cache:
+            self.cache[tag] = make()
+        return self.cache[tag]
+
+    def _host_table(self, tag, rows, pattern):
+        """laid-out table -> ndarray as handed to numpy.save; the stream is produced on the device once per (table, pattern)"""
+        def make():
+            if pattern == '0.1':
+                return rows.download(dtype=np.uint8).reshape(-1)
+            stream = self.ctx.layout(rows, pattern)
+            flat = stream.download(dtype=np.uint8).reshape(-1)
+            stream.free()
+            return flat
+        flat = self._cached(('stream',) + tag + (pattern,), make)
+        return table_ndarray(flat, rows.n, rows.width, pattern)
+
+    def members(self, sort=None, raw=None, pattern=None):
+        ctx = self.ctx
+        sort, raw, pattern = normalise_options(sort, raw, pattern)
+        s_on = sort if sort in ('DNA', 'QUAL', 'QNAME') else None
+        order = self._sorted(s_on)['perm'] if s_on else None                         # uq.py:775, 796, 816, 833
+        out = {}
+        for t, pat in (('DNA', pattern[0]), ('QUAL', pattern[1])):
+            if t in raw:                                                             # uq.py:767-781
+                rows = self.tables[t] if order is None else self._cached(('rows', t, s_on), lambda: ctx.gather_rows(self.tables[t], order))
+                out[t + '.raw'] = self._host_table(('raw', t, s_on), rows, pat)
+            else:                                                                    # uq.py:783-802
+                srt = self._sorted(t)
+                out[t + '.key'] = self._key(t, s_on, order)
+                out[t] = self._host_table(('uniq', t), srt['uniq'], pat)
+        columns = self.p['columns']
+        if 'QNAME' in raw:                                                           # uq.py:812-826
+            for c, meta in zip(self.p['cols'], columns):
+                def make(c=c):
+                    if order is None:
+                        return c.download(dtype=np.dtype(meta['dtype'])).reshape(-1)
+                    g = ctx.gather_rows(c, order)
+                    h = g.download(dtype=np.dtype(meta['dtype'])).reshape(-1)
+                    g.free()
+                    return h
+                out[meta['name'] + '.raw'] = self._cached(('qcol', meta['name'], s_on), make)
+        else:                                                                        # uq.py:827-847
+            srt = self._sorted('QNAME')
+            out['QNAME.key'] = self._key('QNAME', s_on, order)
+
+            def make_cols():
+                ucols = ctx.rows_to_columns(srt['uniq'], [np.dtype(m['dtype']).itemsize for m in columns])
+                host = [u.download(dtype=np.dtype(m['dtype'])).reshape(-1) for u, m in zip(ucols, columns)]
+                for u in ucols:
+                    u.free()
+                return host
+            for h, meta in zip(self._cached(('qucols',), make_cols), columns):
+                out[meta['name']] = h
+        return out
+
+    def _key(self, t, s_on, order):
+        """key of table t in the order of the mix, narrowed like key.astype(min_scalar_type(max(key))) (uq.py:790, 832)"""
+        def make():
+            srt = self._sorted(t)
+            size = key_itemsize(srt['nu'])
+            if t == s_on:
+                k32, tmp = srt['key_sorted'], None                                   # key[argsort(key)]
+            elif order is None:
+                k32, tmp = srt['key'], None
+            else:
+                k32 = tmp = self.ctx.gather_rows(srt['key'], order)                  # key[sort_order], uq.py:798
+            narrow = self.ctx.narrow_u32(k32, size)
+            h = narrow.download(dtype=np.dtype('uint%d' % (8 * size))).reshape(-1)
+            narrow.free()
+            if tmp is not None:
+                tmp.free()
+            return h
+        return self._cached(('key', t, s_on), make)
+
+    def free(self):
+        for d in self.sorted.values():
+            for k in ('perm', 'key', 'uniq', 'key_sorted'):
+                d[k].free()
+        for tag, v in self.cache.items():
+            if isinstance(v, DeviceArray):
+                v.free()
+        if self.tables['QNAME'] is not None:
+            self.tables['QNAME'].free()
+        for a in [self.p['dna'], self.p['qual']] + self.p['cols']:
+            a.free()
+        self.sorted, self.cache = {}, {}
 
 
 def encode(fastq, sort=None, raw=None, pattern=None, pad=False, notricks=False, ctx=None, stages=None):
@@ -665,6 +798,59 @@ def decode_device(ctx, dna, qual, dcols, config):
     handles = (C.c_void_p * max(ncol, 1))(*[c.h for c in dcols])
     ctx.check(ctx.lib.uqb_decode(ctx.h, dna.h, qual.h, handles, C.byref(p), C.byref(h)))
     return DeviceArray(ctx, h)
+
+
+def decode_members_device(ctx, dm, config):
+    """The decoder's front (load_from_tar + key expansion, uq.py:943-973) and decode_device on members that are already
+    in HBM (a DeviceMembers as encode_device returns it): streams are un-laid-out, keys widened and bound-checked, rows
+    gathered, text produced - all on the device.  -> DeviceArray with the FASTQ text."""
+    it = dm.items
+    pat = config['pattern']
+    tmp = []
+
+    def key_of(name, n_rows):
+        arr = it[name][0]
+        k32, bad = ctx.index_u32(arr, n_rows)
+        tmp.append(k32)
+        if bad >= 0:
+            raise UQError('ERROR: %s[%d] points outside its table of %d rows (malformed uQ file)' % (name, bad, n_rows))
+        return k32
+
+    def table(name, pattern):
+        def logical(entry):
+            stream, _, (n, width, p) = entry
+            if p == '0.1':
+                return ctx.wrap(stream.device_ptr.value, n, width), True
+            t = ctx.unlayout(stream, n, width, p)
+            return t, True
+        if name + '.raw' in it:
+            t, own = logical(it[name + '.raw'])
+            tmp.append(t)
+            return t
+        uniq, _ = logical(it[name])
+        tmp.append(uniq)
+        t = ctx.gather_rows(uniq, key_of(name + '.key', uniq.n))                   # uq.py:953, 957
+        tmp.append(t)
+        return t
+
+    try:
+        dna, qual = table('DNA', pat[0]), table('QUAL', pat[1])
+        dcols = []
+        keyed = 'QNAME.key' in it
+        key = None
+        for meta in config['QNAME_columns']:
+            nm = meta['name'] + ('' if keyed else '.raw')
+            c = it[nm][0]
+            if keyed:
+                if key is None:
+                    key = key_of('QNAME.key', c.n)
+                c = ctx.gather_rows(c, key)                                        # uq.py:973
+                tmp.append(c)
+            dcols.append(c)
+        return decode_device(ctx, dna, qual, dcols, config)
+    finally:
+        for a in tmp:
+            a.free()
 
 
 def decode(members, config, ctx=None, out=None):

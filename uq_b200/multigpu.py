@@ -873,6 +873,49 @@ def assemble(comm, res):
     return out
 
 
+def write_container_sharded(comm, path, res, config):
+    """ONE container file written by all ranks: rank 0 plans the byte layout from the global
+    shapes and writes the tar / NPY headers and config.json, then every rank puts its slices at their byte offsets
+    with pwrite - vectors and row-major streams as one range, column-major streams as one run per byte column.
+    `path` must be reachable by every rank (one node).  The file is byte-identical to the single-GPU container."""
+    from . import container
+    desc = res.describe()
+    data = res.download()
+    offsets = None
+    if comm.rank == 0:
+        entries = {}
+        for name, (kind, meta, _, total) in desc.items():
+            if kind == 'vector':
+                entries[name] = (np.dtype(meta), (total,), False)
+            else:
+                w, pat = meta['width'], meta['pattern']
+                shape = (total, w) if pat[0] in '02' else (w, total)
+                entries[name] = (np.uint8, shape, pat[2] == '2' and total > 1 and w > 1)     # numpy writes both-contiguous arrays as C
+        plan = container.Plan(entries, config)
+        plan.create(path)
+        offsets = plan.offsets
+    offsets = comm.all_gather_object(offsets)[0]             # doubles as the barrier behind the file's creation
+    fd = os.open(path, os.O_WRONLY)
+    try:
+        for name, (kind, meta, first, total) in desc.items():
+            base = offsets[name][1]
+            buf = data[name]
+            if kind == 'vector':
+                container._pwrite_all(fd, buf.view(np.uint8), base + first * buf.dtype.itemsize)
+                continue
+            width, pattern, rows = meta['width'], meta['pattern'], meta['rows']
+            transposed, rev_r, _ = host.PATTERN_DESC[pattern]
+            at = total - first - rows if rev_r else first
+            if not transposed:
+                container._pwrite_all(fd, buf, base + at * width)
+            else:
+                for col in range(width):
+                    container._pwrite_all(fd, buf[col * rows:(col + 1) * rows], base + col * total + at)
+    finally:
+        os.close(fd)
+    comm.barrier()
+
+
 # ------------------------------------------------------------------------------------------------
 # the decode (uq.py:926-1060) over the ranks: every rank produces the text of a contiguous range of records
 # ------------------------------------------------------------------------------------------------

@@ -50,20 +50,27 @@ def compressed_size(arr, compressor):
 
 
 def run_test_search(ctx, fq_bytes, args):
-    """The --test loop (uq.py:855-889).  Every candidate mix is produced on the device; the compressor
-    and the argmin stay on the CPU exactly as in the reference."""
+    """The --test loop (uq.py:855-889).  The FASTQ is loaded and Pass 1-4 run ONCE; host.MixFeed keeps the packed tables
+    and at most one sort per table in HBM and serves every candidate member as a gather / layout of those (SURVEY
+    section 8 f1).  The compressor and the argmin stay on the CPU exactly as in the reference."""
+    fq = ctx.load_fastq(fq_bytes)
+    feed = host.MixFeed(ctx, fq, pad=args.pad, notricks=args.notricks)
     results = []
     patterns = [args.pattern[0]] if args.pattern else (host.PATTERNS if args.compressor else ['0.1'])
     raws = ALL_RAW if args.raw is None else [tuple(args.raw)]
     sorts = (['DNA', 'QUAL', 'QNAME', None] if args.compressor else [None]) if args.sort is None else [args.sort]
+    sizes = {}                                       # id of the cached host array -> compressed size (members repeat between mixes)
     for raw_tables in raws:
         for to_sort in sorts:
             best = {}
             for pat in patterns:
-                members, _ = host.encode(fq_bytes, sort=to_sort if to_sort else 'None', raw=[r if r else 'none' for r in raw_tables],
-                                         pattern=[pat, pat] if not args.pattern else args.pattern, pad=args.pad, notricks=args.notricks, ctx=ctx)
+                members = feed.members(sort=to_sort if to_sort else 'None', raw=[r if r else 'none' for r in raw_tables],
+                                       pattern=[pat, pat] if not args.pattern else args.pattern)
                 for name, arr in members.items():
-                    size = compressed_size(arr, args.compressor)
+                    key = (name, to_sort if not name.endswith(('DNA', 'QUAL')) else None, pat if name.startswith(('DNA', 'QUAL')) and not name.endswith('.key') else None)
+                    if key not in sizes:
+                        sizes[key] = compressed_size(arr, args.compressor)
+                    size = sizes[key]
                     if name.startswith(('DNA', 'QUAL')) and not name.endswith('.key'):
                         if name not in best or size < best[name][0]:
                             best[name] = (size, pat)
@@ -72,6 +79,8 @@ def run_test_search(ctx, fq_bytes, args):
             total = sum(v[0] for v in best.values())
             results.append(dict(total_size=total, sorted_on=to_sort, raw_tables=raw_tables, detail=best))
             print(str(total).rjust(17), str(to_sort).ljust(8), str(tuple(raw_tables)).ljust(27))
+    feed.free()
+    fq.free()
     win = sorted(results, key=lambda k: k['total_size'])[0]
     d = win['detail']
     pat_d = next((v[1] for k, v in d.items() if k in ('DNA', 'DNA.raw')), '0.1') or '0.1'
@@ -94,8 +103,17 @@ def main(argv=None):
         if args.output is None:
             args.output = args.input + '.uQ'                                            # uq.py:75
         t0 = time.time()
+        size = os.path.getsize(args.input)
+        pin_in = ctx.pinned_empty(size)                                                 # the file goes straight into pinned memory
         with open(args.input, 'rb') as f:
-            data = f.read()
+            got = 0
+            view = memoryview(pin_in.array)
+            while got < size:
+                k = f.readinto(view[got:])
+                if not k:
+                    break
+                got += k
+        data = pin_in.array[:got]
         sort, raw, pattern = args.sort, args.raw, args.pattern
         host.normalise_options(sort, raw, pattern)                                      # validates like uq.py:52-69
         if args.peek:                                                                   # uq.py:698-702
@@ -111,10 +129,23 @@ def main(argv=None):
             s, r, p = run_test_search(ctx, data, args)
             sort, raw, pattern = (s if s else 'None'), [x if x else 'none' for x in r], p
             print('Parameters found to be the best for this data type:\n   --sort', sort, '--raw', ' '.join(map(str, raw)), '--pattern', ' '.join(pattern))
-        members, config = host.encode(data, sort=sort, raw=raw, pattern=pattern, pad=args.pad, notricks=args.notricks, ctx=ctx)
+        # H2D in chunks overlapped with the record split and the Pass-1 statistics; every member starts its device->host
+        # copy into its own pinned buffer the moment it is final; the container is written from those buffers
+        pins = []
+
+        def sink(name, nbytes):
+            pins.append(ctx.pinned_empty(nbytes))
+            return pins[-1].array
+
+        fq = ctx.load_fastq_streamed(data) if got >= (1 << 20) else ctx.load_fastq(data)
+        dmembers, config = host.encode_device(ctx, fq, sort=sort, raw=raw, pattern=pattern, pad=args.pad, notricks=args.notricks, sink=sink)
+        members = dmembers.download()
         print('\nWriting final config...')
         print('Archiving results...')
         container.write_container(args.output, members, config)
+        dmembers.free(); fq.free()
+        for p in pins:
+            p.free()
         print('All Done! :)  (%d reads, %.2f s, %d kernel launches on cuda:%d)' % (config['reads'], time.time() - t0, ctx.launches, args.device))
     except host.UQError as e:                                                           # uq.py:48-50: print, exit status 0
         print(e)
