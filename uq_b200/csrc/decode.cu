@@ -262,6 +262,45 @@ __device__ __forceinline__ uint32_t qname_write(const dec_params& P, uint64_t r,
     return n;
 }
 
+// One QNAME column of record r -> text at w + (offset of that column inside the line): every (record, column) pair is a
+// work item of its own, so the QNAME lines of a tile are formatted by all threads instead of one thread per record.
+// The item recomputes the text lengths of the columns in front of it (a few compares each) to find its place.
+__device__ __forceinline__ uint32_t col_text_len(const dec_col& dc, uint64_t r, unsigned long long* raw_out, long long* v_out) {
+    const unsigned long long raw = load_le(dc.data + r * dc.itemsize, dc.itemsize);
+    *raw_out = raw;
+    if (dc.format == 0) { *v_out = 0; return raw < dc.dict_count ? dc.dict_len[raw] : 0u; }
+    const long long v = (long long)raw + (dc.offset ? dc.min_val : 0ll);
+    *v_out = v;
+    return dec_digits(v);
+}
+
+__device__ __forceinline__ void qname_write_col(const dec_params& P, uint64_t r, uint32_t c, uint8_t* w) {
+    uint32_t at = P.prefix_len;
+    unsigned long long raw = 0;
+    long long v = 0;
+    for (uint32_t k = 0; k < c; k++) at += col_text_len(P.cols[k], r, &raw, &v) + 1u;      // + separator (k < nseps since k < c <= ncols - 1)
+    const dec_col& dc = P.cols[c];
+    const uint32_t tl = col_text_len(dc, r, &raw, &v);
+    uint8_t* o = w + at;
+    if (dc.format == 0) {
+        if (raw < dc.dict_count) {
+            const uint8_t* sp = dc.dict + raw * dc.dict_width;
+            for (uint32_t i = 0; i < tl; i++) o[i] = sp[i];
+        }
+    } else {
+        const unsigned long long a = v < 0 ? (unsigned long long)(-(v + 1)) + 1ull : (unsigned long long)v;
+        if (v < 0) o[0] = '-';
+        dec_write(o + (v < 0 ? 1u : 0u), a, tl - (v < 0 ? 1u : 0u));
+    }
+    if (c < P.nseps) o[tl] = P.seps[c];
+    if (c == 0) for (uint32_t i = 0; i < P.prefix_len; i++) w[i] = P.prefix[i];
+    if (c + 1 == P.ncols) {
+        uint8_t* e = o + tl + (c < P.nseps ? 1u : 0u);
+        for (uint32_t i = 0; i < P.suffix_len; i++) e[i] = P.suffix[i];
+        e[P.suffix_len] = '\n';
+    }
+}
+
 struct dt_smem {
     alignas(16) uint8_t text[DT_TEXT_CAP + 32];
     alignas(16) uint32_t in_d[DT_IN_CAP / 4 + 8];
@@ -293,6 +332,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_decode_tiles(const dec_params* _
         const uint32_t nrec = (uint32_t)(r1 - r0);
         const uint64_t o0 = rec_off[r0], o1 = r1 < n ? rec_off[r1] : total;
         const uint64_t a0 = o0 & ~15ull;
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the bulk store of the previous tile has read its text
         __syncthreads();                                                   // previous tile fully stored
         if (o1 - a0 > DT_TEXT_CAP) { if (tid == 0) atomicOr(fallback, 1u); continue; }
         // ---- packed rows -> shared memory (big-endian words) ----
@@ -315,12 +355,20 @@ __global__ void __launch_bounds__(DT_THREADS) k_decode_tiles(const dec_params* _
         __syncthreads();
         // ---- work items: chunks of 16 positions (record index fastest), then one QNAME line per item ----
         const uint32_t nsymitems = nrec * chunks;
-        for (uint32_t item = tid; item < nsymitems + nrec; item += DT_THREADS) {
+        const uint32_t ncol = P.ncols ? P.ncols : 1u;
+        for (uint32_t item = tid; item < nsymitems + nrec * ncol; item += DT_THREADS) {
             if (item >= nsymitems) {
-                const uint32_t i = item - nsymitems;
+                const uint32_t qi = item - nsymitems, c = qi / nrec, i = qi - c * nrec;       // record index fastest
                 uint8_t* w = S->text + S->toff[i];
-                const uint32_t hl = qname_write(P, r0 + i, w);
-                w[hl + L] = '\n'; w[hl + L + 1] = '+'; w[hl + L + 2] = '\n'; w[hl + 2 * L + 3] = '\n';
+                if (P.ncols == 0) {
+                    qname_write(P, r0 + i, w);
+                } else {
+                    qname_write_col(P, r0 + i, c, w);
+                }
+                if (c == 0) {
+                    const uint32_t hl = S->toff[i + 1] - S->toff[i] - 2u * L - 4u;             // record length - (2 L + 4) = QNAME line length
+                    w[hl + L] = '\n'; w[hl + L + 1] = '+'; w[hl + L + 2] = '\n'; w[hl + 2 * L + 3] = '\n';
+                }
                 continue;
             }
             const uint32_t c = item / nrec, i = item - c * nrec;
@@ -345,9 +393,15 @@ __global__ void __launch_bounds__(DT_THREADS) k_decode_tiles(const dec_params* _
         {
             const uint32_t lo = (uint32_t)(o0 - a0), hi = (uint32_t)(o1 - a0);
             const uint32_t v0 = (lo + 15) / 16, v1 = hi / 16;
-            uint4* gout = reinterpret_cast<uint4*>(out + a0);
-            const uint4* sin = reinterpret_cast<const uint4*>(S->text);
-            for (uint32_t v = v0 + tid; v < v1; v += DT_THREADS) gout[v] = sin[v];
+            // the aligned interior of the tile's text leaves as ONE TMA bulk store (shared -> global); the next tile
+            // waits for its read side (wait_group.read) before it touches the text buffer again
+            if (tid == 0 && v1 > v0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + a0 + 16ull * v0),
+                             "r"((uint32_t)__cvta_generic_to_shared(S->text + 16u * v0)), "r"(16u * (v1 - v0))
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
             if (v0 <= v1) {
                 for (uint32_t b = lo + tid; b < v0 * 16 && b < hi; b += DT_THREADS) out[a0 + b] = S->text[b];
                 for (uint32_t b = v1 * 16 + tid; b < hi; b += DT_THREADS) if (b >= lo) out[a0 + b] = S->text[b];
@@ -356,6 +410,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_decode_tiles(const dec_params* _
             }
         }
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the last bulk store has landed
 }
 
 extern "C" int uqb_decode(uqb_ctx* ctx, const uqb_array* dna, const uqb_array* qual, uqb_array* const* cols,
