@@ -592,6 +592,7 @@ __device__ __forceinline__ void pt_chunks(pt_smem* S, uint32_t dna_a, uint32_t q
 }
 
 #include "scan_kernel.cuh"
+#include "hist_units.cuh"
 
 __global__ void __launch_bounds__(PT_THREADS, 1) k_pair_hist_tiles(const uint8_t* __restrict__ d, uint64_t n_bytes,
                                                                const uint64_t* __restrict__ line_off, uint64_t r_begin, uint64_t n_reads,
@@ -815,7 +816,14 @@ static int stats_tiles_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsig
     // names only: 32 B of offsets, the name's sectors and the '+' sector per record
     UQB_LAUNCH_B((r1 - r0) * 128, k_record_stats_names, uqb_grid(ctx, r1 - r0, RD_THREADS, 8), RD_THREADS, sizeof(rd_smem), fq->d, fq->line_off, r0, r1,
                  fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb, (const uint8_t*)nullptr, 0u);
-    UQB_LAUNCH_B(ab, k_pair_hist_tiles, g2, PT_THREADS, sizeof(pt_smem), fq->d, fq->n, fq->line_off, r0, r1, s, d_fb);
+    static const bool hist_v1 = [] { const char* e = getenv("UQB_HIST_V1"); return e && e[0] == '1'; }();
+    if (hist_v1) {
+        UQB_LAUNCH_B(ab, k_pair_hist_tiles, g2, PT_THREADS, sizeof(pt_smem), fq->d, fq->n, fq->line_off, r0, r1, s, d_fb);
+        return 0;
+    }
+    static_assert(sizeof(h2_smem) <= 227 * 1024, "unit histogram shared memory");
+    UQB_CUDA(cudaFuncSetAttribute(k_pair_hist_units, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(h2_smem)));
+    UQB_LAUNCH_B(ab, k_pair_hist_units, g2, H2_THREADS, sizeof(h2_smem), fq->d, fq->n, fq->line_off, r0, r1, s, d_fb);
     return 0;
 }
 

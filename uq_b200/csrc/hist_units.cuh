@@ -1,0 +1,326 @@
+// k_pair_hist_units: base / quality byte histograms and "does this base always carry one single quality"
+// (static_qualities, uq.py:369-375, 420-425, read at uq.py:480-494) over shared-memory record tiles, sixteen
+// positions per work item.
+//
+// A tile is 128 records (tile.cuh, double-buffered TMA bulk copies).  The 1024 threads of the CTA are bound to the
+// 256 DNA / QUAL lines of the tile: thread t owns line (t & 255) - lines 0..127 are the DNA lines, 128..255 the QUAL
+// lines of records 0..127 - and walks the ALIGNED 16-byte units k = t >> 8, +4, +8, ... of that line (one
+// ld.shared.v4 each; units are warp-uniform, so the masked first / last units of the lines gather in few warps).
+//
+// Qualities: private 8-bit counters in shared memory, one column per QUAL thread ([value - 33][512 threads], bank =
+// lane: no conflicts, no atomics), bumped with byte loads / stores; a word is range-checked with SIMD-in-register
+// arithmetic (33..126, anything else raises `fallback` and the host runs the generic kernel).  The columns are
+// summed by the whole CTA before any counter can pass 255 (the tile-end barrier carries the vote).
+//
+// Bases: no memory traffic at all in the common case.  Every CTA learns up to four HINT bytes - bases that have
+// already been seen with more than one quality, one per value of the 2-bit code (byte >> 1) & 3, e.g. A C T G - from
+// its own first tile.  A word of four bases is validated against the hints with two byte permutes (the codes select
+// the expected bytes, which must equal the word), and counted by adding its code bit planes to three packed 8-bit
+// accumulators in registers (code bit 0, code bit 1, both); the four hint counts follow from them and the number of
+// words.  Bytes that are not hints ("offenders": N, IUPAC codes, anything while the hints are still unknown) are
+// handled one by one: count in the CTA histogram, compare the quality of that very position with the base's single
+// quality so far.  They stay in the accumulators (under their code) and are subtracted at the flush.
+#pragma once
+#include "tile.cuh"
+
+#define H2_THREADS 1024
+#define H2_QLO 33u
+#define H2_ROWS 95               // quality values 33..126, row 94 (value 127) takes the masked-out bytes of edge units
+#define H2_COLS 512              // QUAL threads per CTA
+#define H2_NOHINT 0x00060402u    // slot c holds a byte whose code is c + 1: nothing validates
+
+struct h2_smem {
+    tile2_smem T;
+    alignas(16) uint8_t qcnt[H2_ROWS * H2_COLS];
+    unsigned hist_b[256];
+    unsigned hist_q[H2_ROWS + 1];
+    int state[256];                 // per base byte: -1 unseen, 0..255 its only quality so far, 256 = several
+    unsigned hints, dirty, oor;
+};
+
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+// 0xFF in every byte j of a word whose unit-relative position 4 * k + j lies in [lo, hi)
+__device__ __forceinline__ uint32_t h2_bytemask(int lo, int hi) {
+    lo = lo < 0 ? 0 : (lo > 4 ? 4 : lo);
+    hi = hi < 0 ? 0 : (hi > 4 ? 4 : hi);
+    if (hi <= lo) return 0u;
+    const unsigned long long ones = (1ull << (8 * hi)) - 1ull;
+    return (uint32_t)((ones >> (8 * lo)) << (8 * lo));
+}
+
+__device__ __forceinline__ unsigned h2_bytesum(unsigned x) {
+    const unsigned y = (x & 0x00FF00FFu) + ((x >> 8) & 0x00FF00FFu);
+    return (y & 0xFFFFu) + (y >> 16);
+}
+
+// one base that is not a hint: CTA histogram + single-quality state
+__device__ __forceinline__ void h2_slow_byte(h2_smem* S, unsigned b, unsigned q) {
+    atomicAdd(&S->hist_b[b], 1u);
+    int f = S->state[b];
+    if (f != (int)q && f != 256) {
+        if (f < 0) {
+            const int old = atomicCAS(&S->state[b], -1, (int)q);
+            if (old >= 0 && old != (int)q) { S->state[b] = 256; S->dirty = 1u; }
+        } else {
+            S->state[b] = 256; S->dirty = 1u;
+        }
+    }
+}
+
+struct h2_dna_acc {
+    unsigned p0, p1, p01;        // packed 8-bit sums of code bit 0, 2 * code bit 1, both bits
+    unsigned ocnt;               // offenders per code (packed 8-bit)
+    unsigned words, zeroed, noff;
+};
+
+// thread-private flush of the base accumulators (H = the hints they were collected under); by value, so that the
+// accumulators stay in registers
+__device__ __noinline__ void h2_dna_flush_vals(h2_smem* S, unsigned p0, unsigned p1, unsigned p01, unsigned ocnt, unsigned words,
+                                               unsigned zeroed, unsigned H) {
+    const unsigned s0 = h2_bytesum(p0), s1 = h2_bytesum(p1) >> 1, s01 = h2_bytesum(p01);
+    const unsigned n3 = s01, n1 = s0 - s01, n2 = s1 - s01, n0 = 4u * words - zeroed - n1 - n2 - n3;
+    const unsigned v0 = n0 - (ocnt & 255u), v1 = n1 - ((ocnt >> 8) & 255u), v2 = n2 - ((ocnt >> 16) & 255u), v3 = n3 - (ocnt >> 24);
+    if (v0) atomicAdd(&S->hist_b[H & 255u], v0);
+    if (v1) atomicAdd(&S->hist_b[(H >> 8) & 255u], v1);
+    if (v2) atomicAdd(&S->hist_b[(H >> 16) & 255u], v2);
+    if (v3) atomicAdd(&S->hist_b[H >> 24], v3);
+}
+__device__ __forceinline__ void h2_dna_flush(h2_smem* S, h2_dna_acc& A, unsigned H) {
+    h2_dna_flush_vals(S, A.p0, A.p1, A.p01, A.ocnt, A.words, A.zeroed, H);
+    A.p0 = A.p1 = A.p01 = A.ocnt = A.words = A.zeroed = A.noff = 0;
+}
+
+// the same for a whole warp (all 32 lanes call it): shuffle reductions, lane 0 adds
+__device__ __forceinline__ void h2_dna_flush_warp(h2_smem* S, h2_dna_acc& A, unsigned H, unsigned lane) {
+    unsigned s0 = h2_bytesum(A.p0), s1 = h2_bytesum(A.p1) >> 1, s01 = h2_bytesum(A.p01);
+    unsigned nw = A.words, nz = A.zeroed;
+    unsigned oc[4];
+#pragma unroll
+    for (unsigned c = 0; c < 4; c++) oc[c] = (A.ocnt >> (8 * c)) & 255u;
+    s0 = __reduce_add_sync(0xffffffffu, s0); s1 = __reduce_add_sync(0xffffffffu, s1); s01 = __reduce_add_sync(0xffffffffu, s01);
+    nw = __reduce_add_sync(0xffffffffu, nw); nz = __reduce_add_sync(0xffffffffu, nz);
+#pragma unroll
+    for (unsigned c = 0; c < 4; c++) oc[c] = __reduce_add_sync(0xffffffffu, oc[c]);
+    if (lane == 0 && nw) {
+        unsigned n[4];
+        n[3] = s01; n[1] = s0 - s01; n[2] = s1 - s01;
+        n[0] = 4u * nw - nz - n[1] - n[2] - n[3];
+#pragma unroll
+        for (unsigned c = 0; c < 4; c++) {
+            const unsigned v = n[c] - oc[c];
+            if (v) atomicAdd(&S->hist_b[(H >> (8 * c)) & 255u], v);
+        }
+    }
+    A.p0 = A.p1 = A.p01 = A.ocnt = A.words = A.zeroed = A.noff = 0;
+}
+
+// sixteen bases: v = the unit's four words, ua = its shared-memory address, delta = distance to the quality of the same
+// position, [lo, hi) = valid bytes of the unit
+__device__ __forceinline__ void h2_dna_unit(h2_smem* S, const uint4 v, uint32_t ua, uint32_t delta, int lo, int hi, unsigned H,
+                                            h2_dna_acc& A) {
+    unsigned w[4] = {v.x, v.y, v.z, v.w}, t[4], bad[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        t[k] = (w[k] >> 1) & 0x03030303u;
+        const unsigned u2 = t[k] | (t[k] >> 4);
+        const unsigned sel = __byte_perm(u2, 0u, 0x4420);                // nibble i = code of byte i
+        unsigned ex;                                                     // the codes never set bit 3 of a nibble: plain prmt
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(ex) : "r"(H), "r"(0u), "r"(sel));
+        bad[k] = ex ^ w[k];
+    }
+    if (lo > 0 || hi < 16) {                                             // edge unit: bytes outside the line count as zeroed
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned vm = h2_bytemask(lo - 4 * k, hi - 4 * k);
+            bad[k] &= vm;
+            t[k] &= vm;
+            A.zeroed += 4u - (__popc(vm) >> 3);
+        }
+    }
+    if (bad[0] | bad[1] | bad[2] | bad[3]) {
+        // offender map: bit 8 j + k <-> byte j of word k
+        unsigned m = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned z = (((bad[k] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | bad[k]) & 0x80808080u;
+            m |= z >> (7 - k);
+        }
+        A.noff += __popc(m);
+        do {
+            const unsigned i = (unsigned)__ffs((int)m) - 1u;
+            m &= m - 1u;
+            const unsigned pos = 4u * (i & 7u) + (i >> 3);
+            const unsigned b = lds_u8(ua + pos), q = lds_u8(ua + pos + delta);
+            A.ocnt += 1u << (8u * ((b >> 1) & 3u));
+            h2_slow_byte(S, b, q);
+        } while (m);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        A.p0 += t[k] & 0x01010101u;
+        A.p1 += t[k] & 0x02020202u;
+        A.p01 += t[k] & (t[k] >> 1) & 0x01010101u;
+    }
+    A.words += 4u;
+}
+
+// sixteen qualities into the thread's counter column (qcol = column address - 33 rows).  Returns false when a byte
+// outside 33..126 was met (nothing is counted then).
+__device__ __forceinline__ bool h2_qual_unit(const uint4 v, int lo, int hi, uint32_t qcol) {
+    unsigned w[4] = {v.x, v.y, v.z, v.w};
+    unsigned bad = 0;
+    if (lo > 0 || hi < 16) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned vm = h2_bytemask(lo - 4 * k, hi - 4 * k);
+            const unsigned chk = (w[k] & vm) | (0x21212121u & ~vm);
+            bad |= ((chk | (chk + 0x01010101u)) | ~((chk & 0x7F7F7F7Fu) + 0x5F5F5F5Fu)) & 0x80808080u;
+            w[k] = (w[k] & vm) | (0x7F7F7F7Fu & ~vm);                    // masked-out bytes go to the spare row
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            bad |= ((w[k] | (w[k] + 0x01010101u)) | ~((w[k] & 0x7F7F7F7Fu) + 0x5F5F5F5Fu)) & 0x80808080u;
+    }
+    if (bad) return false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t a = qcol + (__byte_perm(w[k], 0u, 0x4440 | j) << 9);
+            sts_u8(a, lds_u8m(a) + 1u);
+        }
+    }
+    return true;
+}
+
+// thread-private flush of one counter column (only when a single tile gives a thread more than ~240 qualities)
+__device__ __noinline__ void h2_qual_flush(h2_smem* S, uint32_t qcol) {
+    for (unsigned r = 0; r < H2_ROWS; r++) {
+        const uint32_t a = qcol + ((r + H2_QLO) << 9);
+        const unsigned c = lds_u8m(a);
+        if (c) { atomicAdd(&S->hist_q[r], c); sts_u8(a, 0u); }
+    }
+}
+
+__global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_units(const uint8_t* __restrict__ d, uint64_t n_bytes,
+                                                                  const uint64_t* __restrict__ line_off, uint64_t r_begin, uint64_t n_reads,
+                                                                  an_dev* __restrict__ s, unsigned int* __restrict__ fallback) {
+    static_assert(TL_R == 128, "thread <-> line binding assumes 128 records per tile");
+    extern __shared__ __align__(128) uint8_t h2_raw[];
+    h2_smem* S = reinterpret_cast<h2_smem*>(h2_raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    for (unsigned i = tid; i < H2_ROWS * H2_COLS / 4; i += H2_THREADS) reinterpret_cast<uint32_t*>(S->qcnt)[i] = 0;
+    for (unsigned i = tid; i <= H2_ROWS; i += H2_THREADS) S->hist_q[i] = 0;
+    if (tid < 256) { S->hist_b[tid] = 0; S->state[tid] = -1; }
+    if (tid == 0) { S->hints = H2_NOHINT; S->dirty = 0; S->oor = 0; }
+    __syncthreads();
+    const unsigned line = tid & 255u, rec = line & 127u, k0 = tid >> 8;
+    const bool isq = (line >> 7) != 0;
+    const unsigned cw = ((wid >> 3) << 2) | (wid & 3u);                       // QUAL warps 4-7, 12-15, ... -> 0..15
+    const uint32_t qcol = smem_u32(S->qcnt) + lane * 4u + (cw & 3u) + 128u * (cw >> 2) - (H2_QLO << 9);
+    unsigned qsym = 0;                                                        // increments of this column since its last flush
+    h2_dna_acc A;
+    A.p0 = A.p1 = A.p01 = A.ocnt = A.words = A.zeroed = A.noff = 0;
+    unsigned H = H2_NOHINT;
+    tile2_pipe<H2_THREADS> P;
+    P.begin(&S->T, d, n_bytes, line_off, r_begin, n_reads);
+    while (P.valid()) {
+        const uint32_t nrec = P.acquire();
+        unsigned tile_sym = 0;                                                // symbols this thread took from this tile
+        if (!nrec) {
+            if (tid == 0) atomicOr(fallback, 1u);
+        } else if (rec < nrec) {
+            const uint32_t bytes_a = smem_u32(P.bytes());
+            const uint32_t* loff = P.loff();
+            const uint32_t o1 = loff[4 * rec + 1], o2 = loff[4 * rec + 2], o3 = loff[4 * rec + 3], o4 = loff[4 * rec + 4];
+            uint32_t len = o2 - o1 - 1;
+            const uint32_t qlen = o4 - o3 - 1;
+            if (qlen < len) len = qlen;                // malformed records are reported by the record-stats kernel
+            const uint32_t sb = isq ? o3 : o1, eb = sb + len;
+            for (uint32_t u = (sb & ~15u) + 16u * k0; u < eb; u += 64u) {
+                const uint4 v = lds_v4(bytes_a + u);
+                const int lo = (int)sb - (int)u, hi = (int)eb - (int)u;      // valid bytes of the unit: [lo, hi) clipped to 0..16
+                if (isq) {
+                    if (qsym > 255u - 16u) { h2_qual_flush(S, qcol); qsym = 0; }
+                    if (!h2_qual_unit(v, lo, hi, qcol)) S->oor = 1u;
+                    qsym += 16u;
+                } else {
+                    if (A.words > 120u || A.noff > 224u) h2_dna_flush(S, A, H);
+                    h2_dna_unit(S, v, bytes_a + u, o3 - o1, lo, hi, H, A);
+                }
+                tile_sym += 16u;
+            }
+        }
+        // CTA-wide flush before any 8-bit field can overflow in the next tile (assumed no larger than this one), or when
+        // a base has become a hint candidate
+        const bool vote = isq ? (qsym + tile_sym > 255u - 16u) : (A.words + (tile_sym >> 2) > 120u || A.noff + tile_sym > 224u || (tid == 0 && S->dirty));
+        if (P.finish_or(vote)) {
+            for (unsigned r = wid; r < H2_ROWS; r += H2_THREADS / 32) {
+                uint32_t* row = reinterpret_cast<uint32_t*>(S->qcnt + r * H2_COLS);
+                unsigned e = 0, o = 0;
+#pragma unroll
+                for (int j = 0; j < H2_COLS / 128; j++) {
+                    const unsigned x = row[lane + 32 * j];
+                    row[lane + 32 * j] = 0;
+                    e += x & 0x00FF00FFu; o += (x >> 8) & 0x00FF00FFu;
+                }
+                unsigned tot = (e & 0xFFFFu) + (e >> 16) + (o & 0xFFFFu) + (o >> 16);
+                tot = __reduce_add_sync(0xffffffffu, tot);
+                if (lane == 0) S->hist_q[r] += tot;
+            }
+            qsym = 0;
+            h2_dna_flush_warp(S, A, H, lane);
+            __syncthreads();
+            if (S->dirty) {                                                   // uniform: written before the barrier above
+                if (wid == 0) {
+                    unsigned best[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (unsigned j = 0; j < 8; j++) {
+                        const unsigned b = lane + 32u * j;
+                        if (S->state[b] == 256) {
+                            const unsigned cnt = S->hist_b[b] < 0xFFFFFFu ? S->hist_b[b] : 0xFFFFFFu;
+                            const unsigned key = ((cnt + 1u) << 8) | b;
+                            const unsigned c = (b >> 1) & 3u;
+#pragma unroll
+                            for (unsigned cc = 0; cc < 4; cc++) if (c == cc && key > best[cc]) best[cc] = key;
+                        }
+                    }
+                    unsigned h = 0;
+#pragma unroll
+                    for (unsigned c = 0; c < 4; c++) {
+                        const unsigned m = __reduce_max_sync(0xffffffffu, best[c]);
+                        h |= (m ? (m & 255u) : ((H2_NOHINT >> (8 * c)) & 255u)) << (8 * c);
+                    }
+                    if (lane == 0) { S->hints = h; S->dirty = 0; }
+                }
+                __syncthreads();
+            }
+            H = S->hints;
+        }
+    }
+    // ---- final flush ----
+    __syncthreads();
+    if (isq) h2_qual_flush(S, qcol);
+    h2_dna_flush_warp(S, A, H, lane);
+    __syncthreads();
+    if (tid < 256) {
+        if (S->hist_b[tid]) atomicAdd(&s->base_count[tid], (unsigned long long)S->hist_b[tid]);
+        if (tid < H2_ROWS - 1 && S->hist_q[tid]) atomicAdd(&s->qual_count[tid + H2_QLO], (unsigned long long)S->hist_q[tid]);
+        if (tid == 0 && S->oor) atomicOr(fallback, 1u);
+        const int f = S->state[tid];
+        if (f >= 0) {
+            if (f == 256) {
+                s->multi[tid] = 1;
+                atomicCAS(&s->first_q[tid], -1, 0);                 // mark the base as present
+            } else {
+                const int old = atomicCAS(&s->first_q[tid], -1, f);
+                if (old >= 0 && old != f) s->multi[tid] = 1;
+            }
+        }
+    }
+}

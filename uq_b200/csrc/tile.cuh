@@ -233,4 +233,12 @@ struct tile2_pipe {
         t += gridDim.x;
         buf ^= 1u;
     }
+    // the same, and the barrier also tells every thread whether any thread raised `pred`
+    __device__ __forceinline__ bool finish_or(bool pred) {
+        if (has_next) store_offsets(t + gridDim.x, buf ^ 1u);
+        const int any = __syncthreads_or(pred ? 1 : 0);
+        t += gridDim.x;
+        buf ^= 1u;
+        return any != 0;
+    }
 };
