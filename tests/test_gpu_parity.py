@@ -173,6 +173,39 @@ def test_sort_rows_matches_numpy_stable(ctx, n, width, alphabet):
         a.free()
 
 
+@pytest.mark.parametrize("kind,n,width", [("prefix64", 30000, 113), ("staircase", 20000, 113), ("staircase", 6000, 38),
+                                          ("zeros", 4000, 300), ("prefix64", 5000, 700), ("blocks", 50000, 113)])
+def test_sort_rows_shared_prefixes(ctx, kind, n, width):
+    """Tables whose rows agree far beyond the 8-byte round-0 key (binned qualities, right-aligned variable-length rows):
+    tie groups of more than 32 differing rows go through the per-group common-prefix rounds (sort.cu)."""
+    rng = np.random.default_rng(n + width)
+    if kind == "prefix64":                   # four-letter alphabet, the first 64 bytes identical for all rows
+        t = rng.integers(0, 4, size=(n, width), dtype=np.uint8)
+        t[:, :64] = t[0, :64]
+    elif kind == "staircase":                # every row differs from row 0 at one position only, positions spread over the row
+        t = np.repeat(rng.integers(0, 4, size=(1, width), dtype=np.uint8), n, axis=0)
+        pos = 8 + (np.arange(n) % (width - 8))
+        t[np.arange(n), pos] = rng.integers(4, 9, size=n).astype(np.uint8)
+    elif kind == "blocks":                   # 200 distinct 40-byte prefixes, each followed by one of a few tails
+        pre = rng.integers(0, 4, size=(200, 40), dtype=np.uint8)
+        tails = rng.integers(0, 4, size=(37, width - 40), dtype=np.uint8)
+        t = np.concatenate([pre[rng.integers(0, 200, n)], tails[rng.integers(0, 37, n)]], axis=1)
+    else:                                    # right-aligned rows: many leading zero bytes, a few significant bytes
+        t = np.zeros((n, width), dtype=np.uint8)
+        sig = rng.integers(1, 40, size=n)
+        for i in range(n):
+            t[i, width - sig[i]:] = rng.integers(1, 3, size=sig[i])
+    perm_w, key_w, uniq_w = _np_sort_unique(t)
+    d = ctx.upload(t)
+    perm, key, uniq, nu = ctx.sort_rows(d, want_perm=True, want_key=True, want_uniq=True)
+    assert nu == len(uniq_w)
+    assert np.array_equal(perm.download(dtype=np.uint32).reshape(-1), perm_w.astype(np.uint32))
+    assert np.array_equal(key.download(dtype=np.uint32).reshape(-1), key_w.astype(np.uint32))
+    assert np.array_equal(uniq.download().reshape(nu, width), uniq_w)
+    for a in (d, perm, key, uniq):
+        a.free()
+
+
 @pytest.mark.parametrize("n,width", [(1, 1), (1, 7), (9, 1), (65, 64), (64, 65), (1000, 38), (777, 113), (5, 300), (130, 129)])
 def test_layouts_match_numpy(ctx, n, width):
     from oracle.uq_literal import PATTERNS, apply_pattern

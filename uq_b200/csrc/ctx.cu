@@ -1,5 +1,6 @@
 // Context, memory, arrays and the per-kernel timing facility of libuqb200.so.
 #include "common.cuh"
+#include <cstdlib>
 #include <cuda.h>
 #include <stdarg.h>
 #include <new>

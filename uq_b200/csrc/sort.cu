@@ -88,43 +88,123 @@ __global__ void __launch_bounds__(ST) k_mark_heads(const uint64_t* __restrict__ 
 }
 
 // gid[p] = excl[p] + head[p] - 1 ; headpos[gid] = p for heads
+#define GLCP_EQUAL 0xFFFFFFFFu       // glcp[g]: every row of group g equals the group's first row
 __global__ void __launch_bounds__(ST) k_headpos(const uint32_t* __restrict__ head, const uint32_t* __restrict__ excl, uint64_t n,
-                                               uint32_t* __restrict__ headpos) {
+                                               uint32_t* __restrict__ headpos, uint32_t* __restrict__ glcp) {
     uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
     if (p >= n) return;
-    if (head[p]) headpos[excl[p]] = (uint32_t)p;
+    if (head[p]) { headpos[excl[p]] = (uint32_t)p; glcp[excl[p]] = GLCP_EQUAL; }
     if (p == n - 1) headpos[excl[p] + head[p]] = (uint32_t)n;      // sentinel: headpos[number of groups] = n
 }
 
-// a non-head member that differs from its group's first row in bytes [off, width) marks the group
-__global__ void __launch_bounds__(ST) k_group_diff(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
-                                                  const uint32_t* __restrict__ zoff,
-                                                  const uint32_t* __restrict__ perm, const uint32_t* __restrict__ head,
-                                                  const uint32_t* __restrict__ excl, const uint32_t* __restrict__ headpos,
-                                                  const uint8_t* __restrict__ done, uint64_t n, uint32_t* __restrict__ gdiff) {
-    uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
-    if (p >= n || head[p] || done[p]) return;
-    uint32_t g = excl[p] - 1;           // inclusive scan - 1 with head[p] == 0
-    if (gdiff[g]) return;
-    const uint32_t ra = perm[p], rb = perm[headpos[g]];
-    const uint32_t z = zoff ? zoff[ra] : 0u;          // the rows of a group share their zoff
-    if (z + off >= width) return;
-    const uint8_t* a = rows + (uint64_t)ra * width + z + off;
-    const uint8_t* b = rows + (uint64_t)rb * width + z + off;
-    for (uint32_t i = 0; i < width - z - off; i++) {
-        if (__ldg(a + i) != __ldg(b + i)) { gdiff[g] = 1; return; }
+// Common prefix of every tie group with its first row: glcp[g] = min over the members of the first byte offset (>= off,
+// relative to the row's first significant byte) at which a member differs from the group's first row; stays
+// GLCP_EQUAL when all members are identical.  One pass with every row read exactly once by SUB lanes (aligned 32-bit
+// words, funnel shifted to the row's byte phase; 32 / SUB rows per warp step, four steps in flight), the first rows
+// come from the caches.  Identical-row groups - the bulk of duplicated reads / qualities - are finished by this
+// pass alone; the others continue, each from ITS OWN common prefix, so a table whose rows share long prefixes does
+// not pay one refinement round per 8 bytes.
+template <int SUB>
+__global__ void __launch_bounds__(ST) k_group_lcp(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off, const uint32_t* __restrict__ zoff,
+                                                 const uint32_t* __restrict__ perm, const uint32_t* __restrict__ head,
+                                                 const uint32_t* __restrict__ excl, const uint32_t* __restrict__ headpos,
+                                                 const uint8_t* __restrict__ done, uint64_t n, uint32_t* __restrict__ glcp) {
+    constexpr uint32_t NP = 32u / SUB;
+    constexpr int UN = 4;
+    const unsigned lane = threadIdx.x & 31u, sg = lane / SUB, sl = lane % SUB;
+    const uint64_t nblk = (n + 31) / 32, wstride = (uint64_t)gridDim.x * (ST / 32);
+    for (uint64_t blk = (uint64_t)blockIdx.x * (ST / 32) + (threadIdx.x >> 5); blk < nblk; blk += wstride) {
+        const uint64_t p = blk * 32 + lane;
+        uint32_t ra = 0, rb = 0, g = 0, z = 0;
+        bool live = false;
+        if (p < n && !head[p] && !done[p]) {
+            live = true;
+            g = excl[p] - 1;                           // exclusive scan of the head flags; head[p] == 0
+            ra = perm[p];
+            rb = perm[headpos[g]];
+            if (zoff) z = zoff[ra];                    // the rows of a group share their leading-zero count
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, live);
+        if (!todo) continue;
+        uint32_t mine = GLCP_EQUAL;                    // result of the row at this lane's position
+        for (uint32_t j0 = 0; j0 < 32; j0 += NP * UN) {
+            if (!((todo >> j0) & ((NP * UN >= 32) ? 0xffffffffu : ((1u << (NP * UN)) - 1u)))) continue;
+            uint32_t res[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) res[u] = GLCP_EQUAL;
+            // rows of this batch
+            uint32_t a_r[UN], b_r[UN], zz[UN];
+            bool lv[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const uint32_t j = j0 + u * NP + sg;
+                a_r[u] = __shfl_sync(0xffffffffu, ra, j & 31u);
+                b_r[u] = __shfl_sync(0xffffffffu, rb, j & 31u);
+                zz[u] = __shfl_sync(0xffffffffu, z, j & 31u);
+                lv[u] = j < 32u && ((todo >> (j & 31u)) & 1u);
+            }
+            const uint32_t maxrem = width - off;       // upper bound of the bytes to compare (z only shortens it)
+            for (uint32_t w0 = 0; 4u * w0 < maxrem; w0 += SUB) {
+                const uint32_t wd = w0 + sl;
+                uint32_t xa[UN], xb[UN];
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    xa[u] = 0; xb[u] = 0;
+                    const uint32_t start = zz[u] + off;
+                    if (lv[u] && start + 4u * wd < width) {
+                        const uint64_t A = (uint64_t)(uintptr_t)rows + (uint64_t)a_r[u] * width + start;
+                        const uint64_t B = (uint64_t)(uintptr_t)rows + (uint64_t)b_r[u] * width + start;
+                        const uint32_t pa = (uint32_t)A & 3u, pb = (uint32_t)B & 3u;
+                        const uint32_t* wa = reinterpret_cast<const uint32_t*>(A - pa) + wd;
+                        const uint32_t* wb = reinterpret_cast<const uint32_t*>(B - pb) + wd;
+                        // the word after the row's last one may be read (never used): every table has >= 8 bytes of slack
+                        xa[u] = __funnelshift_r(__ldg(wa), __ldg(wa + 1), pa * 8u);
+                        xb[u] = __funnelshift_r(__ldg(wb), __ldg(wb + 1), pb * 8u);
+                    }
+                }
+                bool any_live = false;
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const uint32_t start = zz[u] + off;
+                    uint32_t d = xa[u] ^ xb[u];
+                    const uint32_t left = (lv[u] && start + 4u * wd < width) ? width - start - 4u * wd : 0u;   // valid bytes of this word
+                    if (left < 4u) d &= left ? (0xffffffffu >> (8u * (4u - left))) : 0u;
+                    uint32_t m = d ? 4u * wd + (((uint32_t)__ffs((int)d) - 1u) >> 3) : GLCP_EQUAL;
+#pragma unroll
+                    for (int o = SUB / 2; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    if (res[u] == GLCP_EQUAL && m != GLCP_EQUAL) { res[u] = off + m; lv[u] = false; }
+                    any_live |= lv[u];
+                }
+                if (!__any_sync(0xffffffffu, any_live)) break;
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const uint32_t j = j0 + u * NP;       // rows j .. j + NP - 1: sub-group s holds row j + s
+                // hand the result to the lane that owns the position
+#pragma unroll
+                for (uint32_t s2 = 0; s2 < NP; s2++) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, res[u], s2 * SUB);
+                    if (lane == j + s2) mine = v;
+                }
+            }
+        }
+        if (live && mine != GLCP_EQUAL) atomicMin(&glcp[g], mine);
     }
 }
 
+// rows that go into the next radix round: members of groups whose rows are not all identical and that the small-group
+// finisher has not completed.  Members of identical-row groups are marked done (nothing more to compare).
 __global__ void __launch_bounds__(ST) k_active_flags(const uint32_t* __restrict__ head, const uint32_t* __restrict__ excl,
-                                                    const uint32_t* __restrict__ gdiff, const uint8_t* __restrict__ done,
+                                                    const uint32_t* __restrict__ glcp, uint8_t* __restrict__ done,
                                                     uint64_t n, uint32_t* __restrict__ act) {
     uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
     if (p >= n) return;
     if (done[p]) { act[p] = 0u; return; }       // finished by k_small_groups (its excl / head may be stale)
     uint32_t g = excl[p] + head[p] - 1;
     bool single = head[p] && (p + 1 == n || head[p + 1]);
-    act[p] = (!single && gdiff[g]) ? 1u : 0u;
+    const bool differ = glcp[g] != GLCP_EQUAL;
+    if (!single && !differ) done[p] = 1;
+    act[p] = (!single && differ) ? 1u : 0u;
 }
 
 // ---- small tie groups: finished in one pass ------------------------------------------------------
@@ -151,6 +231,19 @@ __global__ void __launch_bounds__(ST) k_active_flags(const uint32_t* __restrict_
 // The first pass (pivot = first row of the group) is fused with the staging: the pivot's words stay in
 // registers and every row is compared with them the moment it arrives, so a group of identical rows is
 // finished without reading shared memory at all.
+// all lanes: request the rows of the group held by the lane of the lowest set bit of `mask` (none when mask == 0)
+__device__ __forceinline__ void sg_prefetch(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off, const uint32_t* __restrict__ perm,
+                                            uint32_t start, uint32_t size, unsigned mask, unsigned lane) {
+    if (!mask) return;
+    const int src = __ffs((int)mask) - 1;
+    const uint32_t s = __shfl_sync(0xffffffffu, start, src), sz = __shfl_sync(0xffffffffu, size, src);
+    if (lane < sz) {
+        const uint8_t* a = rows + (uint64_t)__ldg(perm + s + lane) * width;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a + off));
+        if ((((uintptr_t)(a + off)) ^ ((uintptr_t)(a + width - 1))) >> 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + width - 1));
+    }
+}
+
 template <int SUB, int TRIPS>      // TRIPS = ceil(pitch / SUB): 1, or 2 for SUB == 32 and 33..64 words
 __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
                                                     uint32_t* __restrict__ perm, uint32_t* __restrict__ head, uint8_t* __restrict__ done,
@@ -182,12 +275,16 @@ __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__
         const uint64_t g = g0 + lane;
         uint32_t start = 0, size = 0;
         if (g < G) { start = headpos[g]; size = headpos[g + 1] - start; }
-        const bool fin = size >= 2 && done[start];
+        const bool fin = size < 2 || done[start];
         if (size > SG_MAX && !fin) my_large += size;
-        unsigned need = __ballot_sync(0xffffffffu, size >= 2 && size <= SG_MAX && !fin);
+        unsigned need = __ballot_sync(0xffffffffu, size <= SG_MAX && !fin);
+        // the rows of the next two groups are requested (L2 prefetch) while the current one is staged and sorted: one group
+        // alone keeps only a handful of random row reads in flight per warp
+        sg_prefetch(rows, width, off, perm, start, size, need & (need - 1u), lane);
         while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
+            sg_prefetch(rows, width, off, perm, start, size, need & (need - 1u), lane);
             const uint32_t s = __shfl_sync(0xffffffffu, start, src), sz = __shfl_sync(0xffffffffu, size, src);
             const uint32_t r = lane < sz ? perm[s + lane] : 0u;
             // ---- stage, and compare with the first row ----
@@ -313,9 +410,9 @@ __global__ void __launch_bounds__(ST) k_small_groups_gmem(const uint8_t* __restr
         const uint64_t g = g0 + lane;
         uint32_t start = 0, size = 0;
         if (g < G) { start = headpos[g]; size = headpos[g + 1] - start; }
-        const bool fin = size >= 2 && done[start];
+        const bool fin = size < 2 || done[start];
         if (size > SG_MAX && !fin) my_large += size;
-        unsigned need = __ballot_sync(0xffffffffu, size >= 2 && size <= SG_MAX && !fin);
+        unsigned need = __ballot_sync(0xffffffffu, size <= SG_MAX && !fin);
         while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
@@ -354,7 +451,7 @@ __global__ void __launch_bounds__(ST) k_small_groups_gmem(const uint8_t* __restr
     if (lane == 0 && my_large) atomicAdd(large_rows, my_large);
 }
 
-__global__ void __launch_bounds__(ST) k_compact_active(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
+__global__ void __launch_bounds__(ST) k_compact_active(const uint8_t* __restrict__ rows, uint32_t width, const uint32_t* __restrict__ glcp,
                                                       const uint32_t* __restrict__ zoff, const uint32_t* __restrict__ act, const uint32_t* __restrict__ apos,
                                                       const uint32_t* __restrict__ head, const uint32_t* __restrict__ excl,
                                                       const uint32_t* __restrict__ perm, uint64_t n, uint32_t* __restrict__ pos_list,
@@ -365,9 +462,11 @@ __global__ void __launch_bounds__(ST) k_compact_active(const uint8_t* __restrict
     uint32_t row = perm[p];
     pos_list[j] = (uint32_t)p;
     const uint32_t z = zoff ? zoff[row] : 0u;
+    const uint32_t g = excl[p] + head[p] - 1;
+    const uint32_t off = glcp[g];                     // the group's rows agree before this offset: the next 8 bytes decide
     const uint32_t rem = z + off < width ? width - z - off : 0u;
     key[j] = load_be64(rows + (uint64_t)row * width + z + off, rem < 8 ? rem : 8);
-    aux[j] = excl[p] + head[p] - 1;
+    aux[j] = g;
     val[j] = row;
 }
 
@@ -428,26 +527,27 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
         UQB_CUDA(cudaMemcpyAsync(perm, sb.val[sb.cur], n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         UQB_TRY(uqb_sortbuf_free(ctx, &sb));
     }
-    // ---- refinement rounds ----
-    const uint32_t nchunks = (width + 7) / 8;
-    if (nchunks > 1) {
-        uint32_t *headpos, *gdiff, *act, *apos;
+    // ---- refinement ----
+    // Every round: group heads -> per-group common prefix with the first row (k_group_lcp: identical-row groups end here)
+    // -> groups of up to 32 rows are completed by one warp each -> the rows of larger groups are sorted by (group, the
+    // 8 bytes at the group's common prefix) and the loop repeats for what is still tied.
+    if (width > 8) {
+        const uint32_t off = 8;                  // after round 0 the rows of a group agree in their first 8 (significant) bytes
+        uint32_t *headpos, *glcp, *act = nullptr, *apos = nullptr;
         uint8_t* done;
         unsigned long long* d_large;
         UQB_TRY(uqb_dalloc_t(ctx, &headpos, n + 1));
-        UQB_TRY(uqb_dalloc_t(ctx, &gdiff, n));
-        UQB_TRY(uqb_dalloc_t(ctx, &act, n));
-        UQB_TRY(uqb_dalloc_t(ctx, &apos, n));
+        UQB_TRY(uqb_dalloc_t(ctx, &glcp, n));
         UQB_TRY(uqb_dalloc_t(ctx, &done, n));
         UQB_TRY(uqb_dalloc_t(ctx, &d_large, 1));
         UQB_CUDA(cudaMemsetAsync(done, 0, n, ctx->stream));
-        for (uint32_t c = 1; c < nchunks; c++) {
-            const uint32_t off = 8 * c;
+        const uint32_t max_rounds = (width + 7) / 8 + 1;
+        for (uint32_t round = 0; round < max_rounds; round++) {
             UQB_TRY(uqb_scan_u32(ctx, head, excl, n, d_tot));
-            UQB_LAUNCH(k_headpos, nb, ST, 0, head, excl, n, headpos);
-            // small tie groups are finished right here
-            UQB_CUDA(cudaMemsetAsync(d_large, 0, 8, ctx->stream));
+            UQB_LAUNCH(k_headpos, nb, ST, 0, head, excl, n, headpos, glcp);
             const uint32_t rem = width - off;
+            // tie groups of up to 32 rows are finished right here
+            UQB_CUDA(cudaMemsetAsync(d_large, 0, 8, ctx->stream));
             const unsigned sg_grid = uqb_grid(ctx, n, ST, 16);
             if (rem <= SG_STAGE_BYTES && !zoff) {
                 const uint32_t pitch = (rem + 3) / 4;
@@ -473,29 +573,39 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
             unsigned long long large = 0;
             UQB_TRY(uqb_readback(ctx, &large, d_large, 8));
             if (large == 0) break;                                 // no tie group of more than 32 rows is left
-            // large tie groups: all-equal check, then one more 8-byte radix round over the still active rows
-            UQB_CUDA(cudaMemsetAsync(gdiff, 0, n * 4, ctx->stream));
-            UQB_LAUNCH(k_group_diff, nb, ST, 0, rows, width, off, zoff, perm, head, excl, headpos, done, n, gdiff);
-            UQB_LAUNCH(k_active_flags, nb, ST, 0, head, excl, gdiff, done, n, act);
+            // large tie groups: common prefix with the group's first row (identical-row groups end here), then one 8-byte
+            // radix round at each group's own common prefix over the still active rows
+            const uint64_t ab_lcp = n * ((uint64_t)rem + 16);
+            if (rem <= 32) {
+                auto k_group_lcp_8 = k_group_lcp<8>;
+                UQB_LAUNCH_B(ab_lcp, k_group_lcp_8, uqb_grid(ctx, n, ST, 16), ST, 0, rows, width, off, zoff, perm, head, excl, headpos, done, n, glcp);
+            } else {
+                auto k_group_lcp_32 = k_group_lcp<32>;
+                UQB_LAUNCH_B(ab_lcp, k_group_lcp_32, uqb_grid(ctx, n, ST, 16), ST, 0, rows, width, off, zoff, perm, head, excl, headpos, done, n, glcp);
+            }
+            if (!act) {
+                UQB_TRY(uqb_dalloc_t(ctx, &act, n));
+                UQB_TRY(uqb_dalloc_t(ctx, &apos, n));
+            }
+            UQB_LAUNCH(k_active_flags, nb, ST, 0, head, excl, glcp, done, n, act);
             UQB_TRY(uqb_scan_u32(ctx, act, apos, n, d_tot + 1));
             uint32_t tot[2];
             UQB_TRY(uqb_readback(ctx, tot, d_tot, 8));
             const uint64_t m = tot[1];
-            if (m == 0) break;                                     // only identical rows remain tied
+            if (m == 0) break;
             uqb_sortbuf sb;
             uint32_t* pos_list;
             UQB_TRY(uqb_sortbuf_alloc(ctx, &sb, m, true));
             UQB_TRY(uqb_dalloc_t(ctx, &pos_list, m));
-            UQB_LAUNCH_B(n * 8 + m * 32, k_compact_active, nb, ST, 0, rows, width, off, zoff, act, apos, head, excl, perm, n, pos_list, sb.key[0], sb.aux[0], sb.val[0]);
+            UQB_LAUNCH_B(n * 8 + m * 32, k_compact_active, nb, ST, 0, rows, width, glcp, zoff, act, apos, head, excl, perm, n, pos_list, sb.key[0], sb.aux[0], sb.val[0]);
             UQB_TRY(uqb_radix_sort(ctx, &sb, m, true));
             UQB_LAUNCH_B(m * 28, k_write_back, uqb_blocks(m, ST), ST, 0, sb.key[sb.cur], sb.aux[sb.cur], sb.val[sb.cur], pos_list, m, perm, head);
             UQB_TRY(uqb_dfree(ctx, pos_list, m * 4));
             UQB_TRY(uqb_sortbuf_free(ctx, &sb));
         }
         UQB_TRY(uqb_dfree(ctx, headpos, (n + 1) * 4));
-        UQB_TRY(uqb_dfree(ctx, gdiff, n * 4));
-        UQB_TRY(uqb_dfree(ctx, act, n * 4));
-        UQB_TRY(uqb_dfree(ctx, apos, n * 4));
+        UQB_TRY(uqb_dfree(ctx, glcp, n * 4));
+        if (act) { UQB_TRY(uqb_dfree(ctx, act, n * 4)); UQB_TRY(uqb_dfree(ctx, apos, n * 4)); }
         UQB_TRY(uqb_dfree(ctx, done, n));
         UQB_TRY(uqb_dfree(ctx, d_large, 8));
     }
@@ -519,6 +629,40 @@ __global__ void __launch_bounds__(ST) k_scatter_key(const uint32_t* __restrict__
     uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x;
     if (p >= n) return;
     key[perm[p]] = gid[p];
+}
+
+// The same scatter for arrays much larger than the L2: the destination is taken in windows of 2^wshift entries, one window
+// per sweep over perm, so that the 4-byte stores of a window meet in the L2 and leave as full sectors (a plain random
+// scatter over 400 MB costs a sector fill and a write-back per element).  perm is read once per window (sequential).
+__global__ void __launch_bounds__(ST) k_scatter_key_windows(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ gid, uint64_t n,
+                                                           uint32_t wshift, uint32_t nwin, uint32_t* __restrict__ key) {
+    const uint64_t stride = (uint64_t)gridDim.x * ST * 4;
+    for (uint32_t w = 0; w < nwin; w++) {
+        for (uint64_t p0 = ((uint64_t)blockIdx.x * ST + threadIdx.x) * 4; p0 < n; p0 += stride) {
+            if (p0 + 4 <= n) {
+                const uint4 d = __ldg(reinterpret_cast<const uint4*>(perm + p0));
+                if ((d.x >> wshift) == w) key[d.x] = __ldg(gid + p0);
+                if ((d.y >> wshift) == w) key[d.y] = __ldg(gid + p0 + 1);
+                if ((d.z >> wshift) == w) key[d.z] = __ldg(gid + p0 + 2);
+                if ((d.w >> wshift) == w) key[d.w] = __ldg(gid + p0 + 3);
+            } else {
+                for (uint64_t p = p0; p < n; p++) { const uint32_t d = perm[p]; if ((d >> wshift) == w) key[d] = gid[p]; }
+            }
+        }
+    }
+}
+
+// key[perm[p]] = gid[p] for all p
+static int scatter_key(uqb_ctx* ctx, const uint32_t* perm, const uint32_t* gid, uint64_t n, uint32_t* key) {
+    if (n == 0) return 0;
+    const uint32_t wshift = 23;                                    // 8 M entries = 32 MB per window
+    if (n <= (3ull << wshift)) {
+        UQB_LAUNCH_B(n * 12, k_scatter_key, uqb_blocks(n, ST), ST, 0, perm, gid, n, key);
+        return 0;
+    }
+    const uint32_t nwin = (uint32_t)((n + (1ull << wshift) - 1) >> wshift);
+    UQB_LAUNCH_B(n * 12, k_scatter_key_windows, uqb_grid(ctx, n, ST * 4, 4), ST, 0, perm, gid, n, wshift, nwin, key);
+    return 0;
 }
 
 __global__ void __launch_bounds__(ST) k_first_of_group(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ gid, uint64_t n,
@@ -646,7 +790,7 @@ extern "C" int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** p
     const unsigned nb = uqb_blocks(n, ST);
     if (key) {
         UQB_TRY(uqb_new_array(ctx, n, 4, key));
-        if (n) UQB_LAUNCH(k_scatter_key, nb, ST, 0, d_perm, d_gid, n, (uint32_t*)(*key)->d);
+        UQB_TRY(scatter_key(ctx, d_perm, d_gid, n, (uint32_t*)(*key)->d));
     }
     if (uniq) {
         UQB_TRY(uqb_new_array(ctx, u, table->width, uniq));
