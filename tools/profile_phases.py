@@ -24,7 +24,10 @@ def step():
 step(); step()
 ctx.timing(True); ctx.timing_reset()
 host.PHASE_LOG = {}
+host.PHASE_KERNELS = {}
 step()
 rep = ctx.timing_report()
+per_phase = {ph: sorted(([k, v[0], round(v[1], 3)] for k, v in ks.items()), key=lambda r: -r[2]) for ph, ks in host.PHASE_KERNELS.items()}
 print(json.dumps({"workload": "%d %s reads x %d, %s" % (n, kind, length, opts), "fastq_gb": dev.nbytes / 1e9, "phases_ms": host.PHASE_LOG,
+                  "phase_kernels": per_phase,
                   "kernels": sorted(([k, v[0], round(v[1], 3), round(v[2] / 1e9 / (v[1] / 1e3), 1) if v[1] > 0 and v[2] else None] for k, v in rep.items()), key=lambda r: -r[2])}, indent=1))

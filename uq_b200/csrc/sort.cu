@@ -396,6 +396,138 @@ __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__
     if (lane == 0 && my_large) atomicAdd(large_rows, my_large);
 }
 
+// ---- first refinement pass: several small tie groups per warp -------------------------------------
+// Right after round 0 nothing is done yet, group sizes are small (duplicated reads / qualities come in handfuls) and a
+// warp that takes ONE group at a time leaves most of its lanes idle and keeps a handful of random row reads in flight.
+// Here a warp walks its chunk of sorted positions and packs as many WHOLE groups as fit into 32 rows: the group
+// boundaries come straight from ballots over the head flags of the next 64 positions (no scan, no head-position array).
+//   staging   every row of a group of 2+ rows is fetched once as aligned 32-bit words (SUB lanes per row, funnel shifted to
+//             the row's byte phase, big-endian in shared memory), up to 32 rows in flight per warp;
+//   masks     d[j] = set of words in which row j differs from the first row of its group (one ballot per row);
+//   ranking   lane j compares its row with every other row i of its group, looking only at the words of d[i] | d[j] in
+//             increasing order (rows that both equal the first row in a word equal each other there): typically one
+//             or two word compares per pair.  rank = rows before it (ties keep their current = input order);
+//   output    permutation, heads of the distinct rows and done flags, in place.
+// Groups of more than 32 rows are skipped and their rows counted; the caller then runs the general rounds for them.
+#define SGP_CHUNK 2048
+template <int SUB>
+__global__ void __launch_bounds__(ST) k_small_groups_packed(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
+                                                           uint32_t* __restrict__ perm, const uint32_t* __restrict__ head, uint32_t* __restrict__ head_out,
+                                                           uint8_t* __restrict__ done, uint64_t n, uint32_t pitch,
+                                                           unsigned long long* __restrict__ large_rows) {
+    // head: the group starts of round 0, read only (neighbouring warps look at each other's positions to find their
+    // first group); head_out: a copy of it, in which the starts of the distinct rows are added
+    extern __shared__ uint32_t sg_smem[];
+    constexpr uint32_t NP = 32u / SUB;
+    constexpr uint32_t SUBMASK = SUB == 32 ? 0xffffffffu : ((1u << (SUB & 31)) - 1u);
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const unsigned sg = lane / SUB, sl = lane % SUB;
+    uint32_t* srows = sg_smem + (size_t)w * (32 * pitch);
+    const uint32_t rem = width - off;
+    const bool wvalid = sl < pitch;
+    const uint32_t nvalid = wvalid ? rem - 4u * sl : 0u;
+    const uint32_t tailmask = nvalid >= 4u ? 0xffffffffu : (nvalid ? 0xffffffffu << ((4u - nvalid) * 8u) : 0u);
+    const uint64_t nchunks = (n + SGP_CHUNK - 1) / SGP_CHUNK, warps_total = (uint64_t)gridDim.x * (ST / 32);
+    unsigned long long my_large = 0;
+    for (uint64_t ck = (uint64_t)blockIdx.x * (ST / 32) + w; ck < nchunks; ck += warps_total) {
+        const uint64_t c0 = ck * SGP_CHUNK, c1 = (c0 + SGP_CHUNK < n) ? c0 + SGP_CHUNK : n;
+        uint64_t cur = c0;
+        // the first group that STARTS in this chunk
+        while (cur < c1) {
+            const unsigned hb = __ballot_sync(0xffffffffu, cur + lane < n ? head[cur + lane] != 0u : true);
+            if (hb) { cur += (unsigned)__ffs((int)hb) - 1u; break; }
+            cur += 32;
+        }
+        while (cur < c1) {
+            const unsigned h1 = __ballot_sync(0xffffffffu, cur + lane < n ? head[cur + lane] != 0u : true);             // bit 0 is set
+            const unsigned h2 = __ballot_sync(0xffffffffu, cur + 32 + lane < n ? head[cur + 32 + lane] != 0u : true);
+            const unsigned hi = (h1 >> 1) | (h2 << 31);            // bit k: a group starts at cur + 1 + k
+            if (!hi) {
+                // more than 32 rows: find where the group ends, count, skip
+                uint64_t nxt;
+                if (h2 >> 1) nxt = cur + 32 + ((unsigned)__ffs((int)(h2 >> 1)));
+                else {
+                    uint64_t q = cur + 64;
+                    for (;;) {
+                        const unsigned hb = __ballot_sync(0xffffffffu, q + lane < n ? head[q + lane] != 0u : true);
+                        if (hb) { nxt = q + (unsigned)__ffs((int)hb) - 1u; break; }
+                        q += 32;
+                    }
+                }
+                if (lane == 0) my_large += nxt - cur;
+                cur = nxt;
+                continue;
+            }
+            const uint32_t cnt = 32u - (uint32_t)__clz((int)hi);   // rows cur .. cur + cnt - 1 are whole groups, cnt <= 32
+            const unsigned live = cnt == 32u ? 0xffffffffu : ((1u << cnt) - 1u);
+            const unsigned hm = h1 & live;
+            if (hm == live) { cur += cnt; continue; }              // single rows only
+            const uint32_t r = lane < cnt ? perm[cur + lane] : 0u;
+            const unsigned upto = (2u << lane) - 1u;               // lanes 0 .. lane
+            const uint32_t gs = 31u - (uint32_t)__clz((int)(hm & upto));
+            const unsigned above = hm & ~upto;
+            const uint32_t ge = above ? (uint32_t)__ffs((int)above) - 1u : cnt;
+            const bool multi = lane < cnt && ge - gs > 1u;
+            const unsigned need = __ballot_sync(0xffffffffu, multi);
+            // ---- stage ----
+#pragma unroll 4
+            for (uint32_t j0 = 0; j0 < cnt; j0 += NP) {
+                const uint32_t j = j0 + sg;
+                const uint32_t rj = __shfl_sync(0xffffffffu, r, j & 31u);
+                if (j < cnt && ((need >> j) & 1u) && wvalid) {
+                    const uint64_t A = (uint64_t)(uintptr_t)rows + (uint64_t)rj * width + off;
+                    const uint32_t ph = (uint32_t)A & 3u;
+                    const uint32_t* base = reinterpret_cast<const uint32_t*>(A - ph) + sl;
+                    // the word after the row's last one may be read (never used): every table has >= 8 bytes of slack
+                    const uint32_t lo = __ldg(base), hi2 = __ldg(base + 1);
+                    srows[j * pitch + sl] = __byte_perm(__funnelshift_r(lo, hi2, ph * 8u), 0u, 0x0123) & tailmask;
+                }
+            }
+            __syncwarp();
+            // ---- difference masks against the first row of the group ----
+            const uint32_t maxsz = __reduce_max_sync(0xffffffffu, multi ? ge - gs : 0u);
+            unsigned dmask = 0;
+            for (uint32_t j0 = 0; j0 < cnt; j0 += NP) {
+                const uint32_t j = j0 + sg;
+                const uint32_t sj = __shfl_sync(0xffffffffu, gs, j & 31u);
+                bool ne = false;
+                if (j < cnt && ((need >> j) & 1u) && wvalid) ne = srows[j * pitch + sl] != srows[sj * pitch + sl];
+                const unsigned b = __ballot_sync(0xffffffffu, ne);
+#pragma unroll
+                for (uint32_t s2 = 0; s2 < NP; s2++) if (lane == j0 + s2) dmask = (b >> (s2 * SUB)) & SUBMASK;
+            }
+            // ---- rank inside the group ----
+            uint32_t rank = 0;
+            bool eq_before = false;
+            for (uint32_t t = 0; t < maxsz; t++) {
+                const uint32_t i = gs + t;
+                const bool act = multi && i < ge && i != lane;
+                const unsigned di = __shfl_sync(0xffffffffu, dmask, act ? i : lane);
+                if (act) {
+                    unsigned m = di | dmask;
+                    int c = 0;          // memcmp(row i, row lane)
+                    while (m) {
+                        const uint32_t wd = (uint32_t)__ffs((int)m) - 1u;
+                        m &= m - 1u;
+                        const uint32_t a = srows[i * pitch + wd], b = srows[lane * pitch + wd];
+                        if (a != b) { c = a < b ? -1 : 1; break; }
+                    }
+                    if (c < 0 || (c == 0 && i < lane)) rank++;
+                    if (c == 0 && i < lane) eq_before = true;
+                }
+            }
+            __syncwarp();
+            if (multi) {
+                perm[cur + gs + rank] = r;
+                if (rank > 0) head_out[cur + gs + rank] = eq_before ? 0u : 1u;
+                done[cur + lane] = 1;
+            }
+            cur += cnt;
+        }
+    }
+    if (lane == 0 && my_large) atomicAdd(large_rows, my_large);
+}
+
 // Rows whose remainder is wider than SG_STAGE_BYTES: lane i ranks row i against the others straight from
 // global memory (rare: only very long variable-length reads get here).
 __global__ void __launch_bounds__(ST) k_small_groups_gmem(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
@@ -542,7 +674,34 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
         UQB_TRY(uqb_dalloc_t(ctx, &d_large, 1));
         UQB_CUDA(cudaMemsetAsync(done, 0, n, ctx->stream));
         const uint32_t max_rounds = (width + 7) / 8 + 1;
-        for (uint32_t round = 0; round < max_rounds; round++) {
+        bool finished = false;
+        if (width - off <= 128 && !zoff) {
+            // first pass: whole small groups packed 32 rows to a warp, boundaries straight from the head flags
+            const uint32_t rem = width - off, pitch = (rem + 3) / 4;
+            uint32_t* head2;
+            UQB_TRY(uqb_dalloc_t(ctx, &head2, n));
+            UQB_CUDA(cudaMemcpyAsync(head2, head, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            UQB_CUDA(cudaMemsetAsync(d_large, 0, 8, ctx->stream));
+            const size_t smem = (size_t)(ST / 32) * 32 * pitch * 4;
+            const unsigned grid = uqb_grid(ctx, (n + SGP_CHUNK - 1) / SGP_CHUNK, ST / 32, 16);
+            const uint64_t ab = n * ((uint64_t)rem + 13);
+            if (pitch <= 8) {
+                auto k_small_groups_packed_8 = k_small_groups_packed<8>;
+                UQB_LAUNCH_B(ab, k_small_groups_packed_8, grid, ST, smem, rows, width, off, perm, head, head2, done, n, pitch, d_large);
+            } else if (pitch <= 16) {
+                auto k_small_groups_packed_16 = k_small_groups_packed<16>;
+                UQB_LAUNCH_B(ab, k_small_groups_packed_16, grid, ST, smem, rows, width, off, perm, head, head2, done, n, pitch, d_large);
+            } else {
+                auto k_small_groups_packed_32 = k_small_groups_packed<32>;
+                UQB_LAUNCH_B(ab, k_small_groups_packed_32, grid, ST, smem, rows, width, off, perm, head, head2, done, n, pitch, d_large);
+            }
+            UQB_TRY(uqb_dfree(ctx, head, n * 4));
+            head = head2;
+            unsigned long long large = 0;
+            UQB_TRY(uqb_readback(ctx, &large, d_large, 8));
+            finished = large == 0;
+        }
+        for (uint32_t round = 0; round < max_rounds && !finished; round++) {
             UQB_TRY(uqb_scan_u32(ctx, head, excl, n, d_tot));
             UQB_LAUNCH(k_headpos, nb, ST, 0, head, excl, n, headpos, glcp);
             const uint32_t rem = width - off;

@@ -34,6 +34,7 @@ class UQError(Exception):
 
 
 PHASE_LOG = None     # set to a dict to collect wall-clock milliseconds per phase (adds stream syncs; diagnostics only)
+PHASE_KERNELS = None # set to a dict (with the context's kernel timing on) to also collect the kernels of every phase
 
 
 def _timed(ctx, name, fn, *args, **kw):
@@ -41,10 +42,18 @@ def _timed(ctx, name, fn, *args, **kw):
         return fn(*args, **kw)
     import time
     ctx.sync()
+    before = ctx.timing_report() if PHASE_KERNELS is not None else None
     t0 = time.perf_counter()
     out = fn(*args, **kw)
     ctx.sync()
     PHASE_LOG[name] = PHASE_LOG.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+    if before is not None:
+        slot = PHASE_KERNELS.setdefault(name, {})
+        for k, v in ctx.timing_report().items():
+            b = before.get(k, (0, 0.0, 0))
+            if v[0] > b[0]:
+                c = slot.get(k, (0, 0.0))
+                slot[k] = (c[0] + v[0] - b[0], c[1] + v[1] - b[1])
     return out
 
 
