@@ -259,7 +259,9 @@ __global__ void __launch_bounds__(RD_THREADS) k_record_stats_names(const uint8_t
                                                                   uint64_t r_begin, uint64_t n_reads, const uint8_t* __restrict__ ref,
                                                                   uint64_t rbase, uint32_t first_len, an_dev* __restrict__ s,
                                                                   unsigned int* __restrict__ fallback,
-                                                                  const uint8_t* __restrict__ names, uint32_t name_pitch) {
+                                                                  const uint8_t* __restrict__ names, uint32_t name_pitch, int checks) {
+    // checks == 0: the FASTQ shape checks and the read lengths are produced by the histogram kernel, which has the whole
+    // record in shared memory anyway; this kernel then touches the first two line offsets and the name only
     // names != nullptr: the QNAME lines come from the compact side array of sweep A (row r: length byte + text); the
     // per-record FASTQ checks and read lengths were done there, only the name statistics are produced here
     extern __shared__ __align__(16) uint8_t rd_raw[];
@@ -310,6 +312,11 @@ __global__ void __launch_bounds__(RD_THREADS) k_record_stats_names(const uint8_t
             if (names) {
                 name = names + r * name_pitch + 1;
                 name_len = __ldg(name - 1);
+            } else if (!checks) {
+                const ulonglong2 oa = __ldg(reinterpret_cast<const ulonglong2*>(line_off + 4 * r));
+                const uint64_t nl64 = oa.y - oa.x - 1;
+                name_len = nl64 > 0xFFFFu ? 0xFFFFu : (unsigned)nl64;
+                name = d + oa.x;
             } else {
                 const ulonglong2 oa = __ldg(reinterpret_cast<const ulonglong2*>(line_off + 4 * r));
                 const ulonglong2 ob = __ldg(reinterpret_cast<const ulonglong2*>(line_off + 4 * r + 2));
@@ -796,7 +803,7 @@ static int stats_long_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsign
     if (r1 <= r0) return 0;
     UQB_CUDA(cudaFuncSetAttribute(k_pair_hist_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pt_smem)));
     UQB_LAUNCH_B((r1 - r0) * 128, k_record_stats_names, uqb_grid(ctx, r1 - r0, RD_THREADS, 8), RD_THREADS, sizeof(rd_smem), fq->d, fq->line_off, r0, r1,
-                 fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb, (const uint8_t*)nullptr, 0u);
+                 fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb, (const uint8_t*)nullptr, 0u, 1);
     const uint64_t ab = (uint64_t)((double)fq->n * (double)(r1 - r0) / (double)(fq->n_reads ? fq->n_reads : 1)) + 32 * (r1 - r0);
     const uint64_t warps = (r1 - r0 + 0) ;
     const unsigned g = (unsigned)((warps + PT_THREADS / 32 - 1) / (PT_THREADS / 32) < (uint64_t)ctx->sm_count ? (warps + PT_THREADS / 32 - 1) / (PT_THREADS / 32)
@@ -813,10 +820,10 @@ static int stats_tiles_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsig
     const unsigned g2 = (unsigned)(ntiles < (uint64_t)ctx->sm_count ? ntiles : (uint64_t)ctx->sm_count);      // one 1024-thread CTA per SM
     static_assert(sizeof(pt_smem) <= 227 * 1024, "pair histogram shared memory");
     const uint64_t ab = (uint64_t)((double)fq->n * (double)(r1 - r0) / (double)(fq->n_reads ? fq->n_reads : 1)) + 32 * (r1 - r0);
-    // names only: 32 B of offsets, the name's sectors and the '+' sector per record
-    UQB_LAUNCH_B((r1 - r0) * 128, k_record_stats_names, uqb_grid(ctx, r1 - r0, RD_THREADS, 8), RD_THREADS, sizeof(rd_smem), fq->d, fq->line_off, r0, r1,
-                 fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb, (const uint8_t*)nullptr, 0u);
     static const bool hist_v1 = [] { const char* e = getenv("UQB_HIST_V1"); return e && e[0] == '1'; }();
+    // names only: 32 B of offsets and the name's sectors per record (plus the '+' sector when it also makes the record checks)
+    UQB_LAUNCH_B((r1 - r0) * (hist_v1 ? 128 : 96), k_record_stats_names, uqb_grid(ctx, r1 - r0, RD_THREADS, 8), RD_THREADS, sizeof(rd_smem), fq->d, fq->line_off, r0, r1,
+                 fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb, (const uint8_t*)nullptr, 0u, hist_v1 ? 1 : 0);
     if (hist_v1) {
         UQB_LAUNCH_B(ab, k_pair_hist_tiles, g2, PT_THREADS, sizeof(pt_smem), fq->d, fq->n, fq->line_off, r0, r1, s, d_fb);
         return 0;
@@ -1053,7 +1060,7 @@ extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
         UQB_CUDA(cudaMemsetAsync(d_fb, 0, 4, ctx->stream));
         UQB_LAUNCH(k_an_init_names, 1, 256, 0, acc);
         UQB_LAUNCH_B(N * fq->name_pitch, k_record_stats_names, uqb_grid(ctx, N, RD_THREADS, 8), RD_THREADS, sizeof(rd_smem), fq->d, fq->line_off,
-                     0ull, N, fq->ref_name ? fq->ref_name : fq->d, fq->rbase, (uint32_t)flen, acc, d_fb, (const uint8_t*)fq->names, fq->name_pitch);
+                     0ull, N, fq->ref_name ? fq->ref_name : fq->d, fq->rbase, (uint32_t)flen, acc, d_fb, (const uint8_t*)fq->names, fq->name_pitch, 1);
         unsigned int fb = 0;
         UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
         UQB_TRY(uqb_dfree(ctx, d_fb, 4));

@@ -56,6 +56,7 @@ struct uqb_array {
     uint64_t n = 0;
     uint32_t width = 0;
     bool owned = true;
+    uint64_t* key0 = nullptr;     // optional (owned): be64 of the first 8 bytes of every row, written by the producer of the table
     uint64_t nbytes() const { return n * (uint64_t)width; }
 };
 
@@ -205,8 +206,9 @@ struct uqb_sortbuf {
 };
 int uqb_sortbuf_alloc(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool with_aux);
 int uqb_sortbuf_free(uqb_ctx* ctx, uqb_sortbuf* sb);
-int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux);
+// key_first != nullptr: the input of the first pass is (key_first[i], i) - buffer 0 of sb is scratch then
+int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux, const uint64_t* key_first = nullptr);
 
 // rows (sort.cu)
 int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t width,
-                       uint32_t** d_perm, uint32_t** d_gid_sorted, uint64_t* n_unique);
+                       uint32_t** d_perm, uint32_t** d_gid_sorted, uint64_t* n_unique, const uint64_t* key0 = nullptr);

@@ -487,6 +487,7 @@ extern "C" int uqb_array_free(uqb_ctx* ctx, uqb_array* a) {
     if (!a) return 0;
     int r = 0;
     if (a->owned) r = uqb_dfree(ctx, a->d, a->nbytes() + 64);
+    if (a->key0) { const int r2 = uqb_dfree(ctx, a->key0, a->n * 8); if (!r) r = r2; }
     delete a;
     return r;
 }

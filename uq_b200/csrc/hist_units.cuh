@@ -227,6 +227,9 @@ __global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_units(const uint8_t
     h2_dna_acc A;
     A.p0 = A.p1 = A.p01 = A.ocnt = A.words = A.zeroed = A.noff = 0;
     unsigned H = H2_NOHINT;
+    // FASTQ shape checks and read-length range (uq.py:360-366, 382-388): the thread of a record's first DNA unit
+    unsigned long long len_min = ~0ull, len_max = 0ull;
+    long long bad_plus = LLONG_MAX, bad_len = LLONG_MAX;
     tile2_pipe<H2_THREADS> P;
     P.begin(&S->T, d, n_bytes, line_off, r_begin, n_reads);
     while (P.valid()) {
@@ -240,7 +243,15 @@ __global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_units(const uint8_t
             const uint32_t o1 = loff[4 * rec + 1], o2 = loff[4 * rec + 2], o3 = loff[4 * rec + 3], o4 = loff[4 * rec + 4];
             uint32_t len = o2 - o1 - 1;
             const uint32_t qlen = o4 - o3 - 1;
-            if (qlen < len) len = qlen;                // malformed records are reported by the record-stats kernel
+            if (tid < TL_R) {                          // DNA thread of unit 0: the record's checks
+                const long long r = (long long)(P.first_record() + rec);
+                const uint32_t dlen = len;
+                if (dlen != qlen && r < bad_len) bad_len = r;
+                len_min = dlen < len_min ? dlen : len_min; len_max = dlen > len_max ? dlen : len_max;
+                const unsigned plus = o3 - o2 < 2u ? 0u : lds_u8(bytes_a + o2);
+                if (plus != '+' && r < bad_plus) bad_plus = r;
+            }
+            if (qlen < len) len = qlen;
             const uint32_t sb = isq ? o3 : o1, eb = sb + len;
             for (uint32_t u = (sb & ~15u) + 16u * k0; u < eb; u += 64u) {
                 const uint4 v = lds_v4(bytes_a + u);
@@ -304,6 +315,21 @@ __global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_units(const uint8_t
         }
     }
     // ---- final flush ----
+    if (tid < TL_R) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long a = __shfl_xor_sync(0xffffffffu, len_min, o), b = __shfl_xor_sync(0xffffffffu, len_max, o);
+            const long long e = __shfl_xor_sync(0xffffffffu, bad_plus, o), f = __shfl_xor_sync(0xffffffffu, bad_len, o);
+            len_min = a < len_min ? a : len_min; len_max = b > len_max ? b : len_max;
+            bad_plus = e < bad_plus ? e : bad_plus; bad_len = f < bad_len ? f : bad_len;
+        }
+        if (lane == 0) {
+            if (len_min != ~0ull) atomicMin(&s->dna_min, len_min);
+            atomicMax(&s->dna_max, len_max);
+            if (bad_plus != LLONG_MAX) atomicMin(&s->bad_plus, bad_plus);
+            if (bad_len != LLONG_MAX) atomicMin(&s->bad_len, bad_len);
+        }
+    }
     __syncthreads();
     if (isq) h2_qual_flush(S, qcol);
     h2_dna_flush_warp(S, A, H, lane);

@@ -229,7 +229,10 @@ __global__ void __launch_bounds__(PKT_THREADS) k_pack_tiles(const uint8_t* __res
                                                            const uint64_t* __restrict__ line_off, uint64_t n_reads, pack_lut lut_in,
                                                            uint32_t bb, uint32_t bq, uint32_t wd, uint32_t wq, uint32_t L,
                                                            uint8_t* __restrict__ dna_out, uint8_t* __restrict__ qual_out,
+                                                           uint64_t* __restrict__ key_d, uint64_t* __restrict__ key_q,
                                                            unsigned int* __restrict__ fallback) {
+    // key_d / key_q (optional): be64 of the first 8 bytes of every packed row = the round-0 key of the row sort, taken
+    // from the staging area so that the sort does not have to re-read the strided rows
     extern __shared__ __align__(128) uint8_t pkt_raw[];
     tile_smem* T = reinterpret_cast<tile_smem*>(pkt_raw);
     pkt_lut* lut = reinterpret_cast<pkt_lut*>(pkt_raw + sizeof(tile_smem));
@@ -301,6 +304,18 @@ __global__ void __launch_bounds__(PKT_THREADS) k_pack_tiles(const uint8_t* __res
             place_chunk16_any(bq, cqv, stage_q, gq);
         }
         __syncthreads();
+        if (tid < nrec) {
+            if (key_d) {
+                const uint32_t B = tid * wd, sh = (B & 3u) * 8u;
+                const uint32_t w0 = stage_d[B >> 2], w1 = stage_d[(B >> 2) + 1], w2 = stage_d[(B >> 2) + 2];
+                key_d[r0 + tid] = ((uint64_t)__funnelshift_l(w1, w0, sh) << 32) | __funnelshift_l(w2, w1, sh);
+            }
+            if (key_q) {
+                const uint32_t B = tid * wq, sh = (B & 3u) * 8u;
+                const uint32_t w0 = stage_q[B >> 2], w1 = stage_q[(B >> 2) + 1], w2 = stage_q[(B >> 2) + 2];
+                key_q[r0 + tid] = ((uint64_t)__funnelshift_l(w1, w0, sh) << 32) | __funnelshift_l(w2, w1, sh);
+            }
+        }
         // staging (big-endian words) -> global bytes
         {
             const uint64_t out0 = r0 * wd, nb = (uint64_t)nrec * wd;
@@ -366,13 +381,19 @@ extern "C" int uqb_pack(uqb_ctx* ctx, uqb_fastq* fq, const uqb_pack_params* p, u
         const uint64_t ntiles = (N + TL_R - 1) / TL_R;
         const unsigned per_sm = (unsigned)(220 * 1024 / (smem + 1024)) ? (unsigned)(220 * 1024 / (smem + 1024)) : 1u;
         const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
-        UQB_LAUNCH_B(abytes, k_pack_tiles, (unsigned)(ntiles < cap ? ntiles : cap), PKT_THREADS, smem, fq->d, fq->n, fq->line_off, N, lut,
+        // round-0 sort keys of rows of 8+ bytes come for free here (16 bytes per record more to write)
+        if (p->dna_bytes >= 8) UQB_TRY(uqb_dalloc_t(ctx, &(*dna)->key0, N));
+        if (p->qual_bytes >= 8) UQB_TRY(uqb_dalloc_t(ctx, &(*qual)->key0, N));
+        UQB_LAUNCH_B(abytes + 8 * N * (((*dna)->key0 ? 1 : 0) + ((*qual)->key0 ? 1 : 0)), k_pack_tiles, (unsigned)(ntiles < cap ? ntiles : cap), PKT_THREADS, smem,
+                     fq->d, fq->n, fq->line_off, N, lut,
                      p->bits_per_base, p->bits_per_quality, p->dna_bytes, p->qual_bytes, p->dna_max,
-                     (uint8_t*)(*dna)->d, (uint8_t*)(*qual)->d, d_fb);
+                     (uint8_t*)(*dna)->d, (uint8_t*)(*qual)->d, (*dna)->key0, (*qual)->key0, d_fb);
         unsigned int fb = 0;
         UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
         UQB_TRY(uqb_dfree(ctx, d_fb, 4));
         if (fb == 0) return 0;
+        if ((*dna)->key0) { UQB_TRY(uqb_dfree(ctx, (*dna)->key0, N * 8)); (*dna)->key0 = nullptr; }
+        if ((*qual)->key0) { UQB_TRY(uqb_dfree(ctx, (*qual)->key0, N * 8)); (*qual)->key0 = nullptr; }
         if (fb & 2u) return uqb_fail(ctx, "uqb_pack: a record is not dna_max long although variable == 0");
         // a tile did not fit: fall through to the direct-from-global kernel
     }

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const uint64_t*
         key[j] = 0; val[j] = 0; aux[j] = 0;
         if (idx < n) {
             key[j] = kin[idx];
-            val[j] = vin[idx];
+            val[j] = vin ? vin[idx] : (uint32_t)idx;          // first pass over producer-written keys: value = row index
             if (HASAUX) aux[j] = ain[idx];
         }
     }
@@ -330,21 +330,32 @@ static int plan_windows(uint64_t varying, int nbits, int* shifts) {
     return cnt;
 }
 
-int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux) {
+__global__ void __launch_bounds__(256) k_key_iota(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, uint32_t* __restrict__ vout, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) { kout[i] = kin[i]; vout[i] = (uint32_t)i; }
+}
+
+int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux, const uint64_t* key_first) {
+    if (key_first && (use_aux || n < 2)) {            // plain path: materialise (key, index) in buffer 0
+        if (n) UQB_LAUNCH_B(n * 20, k_key_iota, uqb_grid(ctx, n, 256 * 8), 256, 0, key_first, sb->key[sb->cur], sb->val[sb->cur], n);
+        key_first = nullptr;
+    }
     if (n < 2) return 0;
     if (n >= (1ull << 32)) return uqb_fail(ctx, "radix sort: %llu items exceed the 32-bit index range", (unsigned long long)n);
     bits_summary init = {0ull, ~0ull, 0u, ~0u}, got;
     bits_summary* d_bits;
     UQB_TRY(uqb_dalloc_t(ctx, &d_bits, 1));
     UQB_CUDA(cudaMemcpyAsync(d_bits, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-    UQB_LAUNCH_B(n * (use_aux ? 12 : 8), k_bits_reduce, uqb_grid(ctx, n, 256 * 8), 256, 0, sb->key[sb->cur], use_aux ? sb->aux[sb->cur] : nullptr, n, d_bits);
+    UQB_LAUNCH_B(n * (use_aux ? 12 : 8), k_bits_reduce, uqb_grid(ctx, n, 256 * 8), 256, 0, key_first ? key_first : sb->key[sb->cur], use_aux ? sb->aux[sb->cur] : nullptr, n, d_bits);
     UQB_TRY(uqb_readback(ctx, &got, d_bits, sizeof(got)));
     UQB_TRY(uqb_dfree(ctx, d_bits, sizeof(bits_summary)));
 
     int kshift[16], ashift[8];
     int nk = plan_windows(got.or64 ^ got.and64, 64, kshift);
     int na = use_aux ? plan_windows((uint64_t)(got.or32 ^ got.and32), 32, ashift) : 0;
-    if (nk + na == 0) return 0;
+    if (nk + na == 0) {
+        if (key_first) UQB_LAUNCH_B(n * 20, k_key_iota, uqb_grid(ctx, n, 256 * 8), 256, 0, key_first, sb->key[sb->cur], sb->val[sb->cur], n);
+        return 0;
+    }
 
     uint32_t nblk = (uint32_t)((n + PR_TILE - 1) / PR_TILE);
     uint32_t* ghist;
@@ -355,8 +366,10 @@ int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux) {
         bool auxd = p >= nk;
         int shift = auxd ? ashift[p - nk] : kshift[p];
         int c = sb->cur, o = c ^ 1;
-        if (auxd) UQB_LAUNCH_B(n * 4, k_radix_hist<true>, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], n, shift, ghist, nblk);
-        else      UQB_LAUNCH_B(n * 8, k_radix_hist<false>, nblk, PR_THREADS, 0, sb->key[c], sb->aux[c], n, shift, ghist, nblk);
+        const uint64_t* kin = (p == 0 && key_first) ? key_first : sb->key[c];
+        const uint32_t* vin = (p == 0 && key_first) ? nullptr : sb->val[c];
+        if (auxd) UQB_LAUNCH_B(n * 4, k_radix_hist<true>, nblk, PR_THREADS, 0, kin, sb->aux[c], n, shift, ghist, nblk);
+        else      UQB_LAUNCH_B(n * 8, k_radix_hist<false>, nblk, PR_THREADS, 0, kin, sb->aux[c], n, shift, ghist, nblk);
         UQB_TRY(uqb_scan_u32(ctx, ghist, ghist, hist_n, nullptr));
         auto k_radix_scatter_aux = k_radix_scatter<true, true>;
         auto k_radix_scatter_key_aux = k_radix_scatter<false, true>;
@@ -365,9 +378,9 @@ int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux) {
         UQB_CUDA(cudaFuncSetAttribute(k_radix_scatter_aux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
         UQB_CUDA(cudaFuncSetAttribute(k_radix_scatter_key_aux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
         UQB_CUDA(cudaFuncSetAttribute(k_radix_scatter_key, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
-        if (auxd)         UQB_LAUNCH_B(n * 32, k_radix_scatter_aux, nblk, RS_THREADS, rs_smem, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
-        else if (has_aux) UQB_LAUNCH_B(n * 32, k_radix_scatter_key_aux, nblk, RS_THREADS, rs_smem, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
-        else              UQB_LAUNCH_B(n * 24, k_radix_scatter_key, nblk, RS_THREADS, rs_smem, sb->key[c], sb->aux[c], sb->val[c], sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        if (auxd)         UQB_LAUNCH_B(n * 32, k_radix_scatter_aux, nblk, RS_THREADS, rs_smem, kin, sb->aux[c], vin, sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        else if (has_aux) UQB_LAUNCH_B(n * 32, k_radix_scatter_key_aux, nblk, RS_THREADS, rs_smem, kin, sb->aux[c], vin, sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
+        else              UQB_LAUNCH_B(n * 24, k_radix_scatter_key, nblk, RS_THREADS, rs_smem, kin, sb->aux[c], vin, sb->key[o], sb->aux[o], sb->val[o], n, shift, ghist, nblk);
         sb->cur = o;
     }
     UQB_TRY(uqb_dfree(ctx, ghist, hist_n * 4));

@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(ST) k_iota_zero(uint32_t* __restrict__ perm, u
 }
 
 int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t width,
-                       uint32_t** d_perm, uint32_t** d_gid_sorted, uint64_t* n_unique) {
+                       uint32_t** d_perm, uint32_t** d_gid_sorted, uint64_t* n_unique, const uint64_t* key0) {
     *d_perm = nullptr; *d_gid_sorted = nullptr; *n_unique = 0;
     if (n >= (1ull << 32)) return uqb_fail(ctx, "sort_rows: %llu rows exceed the 32-bit index range", (unsigned long long)n);
     uint32_t *perm, *head, *excl;
@@ -652,9 +652,10 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
     {
         uqb_sortbuf sb;
         UQB_TRY(uqb_sortbuf_alloc(ctx, &sb, n, zoff != nullptr));
+        const uint64_t* kf = (!zoff && width >= 8) ? key0 : nullptr;        // keys written by the table's producer
         if (zoff) UQB_LAUNCH_B(n * 24, k_chunk0_keys_z, nb, ST, 0, rows, n, width, zoff, sb.key[0], sb.aux[0], sb.val[0]);
-        else UQB_LAUNCH_B(n * ((width < 8 ? width : 8) + 12), k_chunk0_keys, nb, ST, 0, rows, n, width, sb.key[0], sb.val[0]);
-        UQB_TRY(uqb_radix_sort(ctx, &sb, n, zoff != nullptr));
+        else if (!kf) UQB_LAUNCH_B(n * ((width < 8 ? width : 8) + 12), k_chunk0_keys, nb, ST, 0, rows, n, width, sb.key[0], sb.val[0]);
+        UQB_TRY(uqb_radix_sort(ctx, &sb, n, zoff != nullptr, kf));
         UQB_LAUNCH(k_mark_heads, nb, ST, 0, sb.key[sb.cur], zoff ? sb.aux[sb.cur] : (const uint32_t*)nullptr, n, head);
         UQB_CUDA(cudaMemcpyAsync(perm, sb.val[sb.cur], n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         UQB_TRY(uqb_sortbuf_free(ctx, &sb));
@@ -863,12 +864,15 @@ __global__ void __launch_bounds__(ST) k_gather_rows32(const uint8_t* __restrict_
         const uint32_t total = nr * width, nwords = total >> 2;
         uint32_t* dst = reinterpret_cast<uint32_t*>(out + i0 * width);
         uint32_t r = (4u * lane) / width, o = 4u * lane - r * width;
-#pragma unroll 4
+#pragma unroll 8
         for (uint32_t k = lane; k < nwords; k += 32) {
             const uint8_t* s = table + (uint64_t)sidx[w][r] * width + o;
             uint32_t v;
             if (o + 4u <= width) {
-                v = (uint32_t)__ldg(s) | ((uint32_t)__ldg(s + 1) << 8) | ((uint32_t)__ldg(s + 2) << 16) | ((uint32_t)__ldg(s + 3) << 24);
+                // two aligned words + funnel shift (the second one may reach up to 3 bytes past the row: table slack)
+                const uint32_t ph = (uint32_t)(uintptr_t)s & 3u;
+                const uint32_t* a = reinterpret_cast<const uint32_t*>(s - ph);
+                v = __funnelshift_r(__ldg(a), __ldg(a + 1), ph * 8u);
             } else {
                 const uint32_t n0 = width - o;                                  // 1..3 bytes from row r, the rest from row r + 1
                 const uint8_t* s2 = table + (uint64_t)sidx[w][(r + 1) & 31u] * width;
@@ -944,7 +948,7 @@ extern "C" int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** p
     uint32_t *d_perm, *d_gid;
     uint64_t u = 0;
     const uint64_t n = table->n;
-    UQB_TRY(uqb_sort_rows_impl(ctx, (const uint8_t*)table->d, n, table->width, &d_perm, &d_gid, &u));
+    UQB_TRY(uqb_sort_rows_impl(ctx, (const uint8_t*)table->d, n, table->width, &d_perm, &d_gid, &u, table->key0));
     if (n_unique) *n_unique = u;
     const unsigned nb = uqb_blocks(n, ST);
     if (key) {
