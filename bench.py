@@ -135,7 +135,13 @@ def run_ours(args):
     red = shard.Reducer(dist, "cuda")
     barrier, max_over_ranks, sum_over_ranks = red.barrier, red.max, red.sum
 
-    ctx = Context(local_rank)
+    tstream = None
+    if world > 1 and args.multi == "global":
+        # the context runs on a torch stream, so that the NCCL exchanges can be ordered against it on the device
+        tstream = torch.cuda.Stream(device=local_rank)
+        ctx = Context(local_rank, stream=tstream.cuda_stream)
+    else:
+        ctx = Context(local_rank)
     n = args.reads
     # weak scaling keeps the per-GPU work fixed: the genome and the quality pool grow with the total number of reads, so
     # that the duplication structure of the file (reads per genome position, reads per quality string) stays that of
@@ -150,7 +156,7 @@ def run_ours(args):
     global_mode = world > 1 and args.multi == "global"
     if global_mode:
         from uq_b200 import multigpu
-        comm = multigpu.Comm(dist, "cuda:%d" % local_rank)
+        comm = multigpu.Comm(dist, "cuda:%d" % local_rank, stream=tstream)
 
     parity = None
     if global_mode and not args.no_parity:

@@ -210,6 +210,15 @@ int uqb_partition_rows(uqb_ctx* ctx, const uqb_array* table, const uint64_t* spl
  * 16-byte aligned pointers); seg_offsets_host receives the byte offset of every segment */
 int uqb_gather_rows_segmented(uqb_ctx* ctx, const uqb_array* table, const uqb_array* order, uint32_t nseg,
                               const uint64_t* seg_counts_host, uint32_t align, uqb_array** out, uint64_t* seg_offsets_host);
+/* The streaming form of the two calls above (rows of up to 224 bytes): the table is read once, sequentially.
+ * uqb_partition_positions: pos = uint32[n], pos[i] = index of row i in the destination-grouped, stable order (what
+ * order^-1 would be); counts_host[0..nsplit] = rows per destination.  uqb_scatter_rows_segmented: row i of `table`
+ * (the partitioned table itself, or any per-record payload that has to follow it) lands at byte
+ * seg_offsets[d] + (pos[i] - first row of d) * width of a byte array laid out like uqb_gather_rows_segmented's. */
+int uqb_partition_positions(uqb_ctx* ctx, const uqb_array* table, const uint64_t* split_keys_host, uint32_t nsplit,
+                            uqb_array** pos, uint64_t* counts_host);
+int uqb_scatter_rows_segmented(uqb_ctx* ctx, const uqb_array* table, const uqb_array* pos, uint32_t nseg,
+                               const uint64_t* seg_counts_host, uint32_t align, uqb_array** out, uint64_t* seg_offsets_host);
 /* the inverse on the receiving side: byte array with aligned segments -> dense table of `width`-byte rows */
 int uqb_compact_segments(uqb_ctx* ctx, const uqb_array* padded, uint32_t nseg, const uint64_t* seg_offsets_host,
                          const uint64_t* seg_counts_host, uint32_t width, uqb_array** out);

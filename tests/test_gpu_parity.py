@@ -173,6 +173,47 @@ def test_sort_rows_matches_numpy_stable(ctx, n, width, alphabet):
         a.free()
 
 
+@pytest.mark.parametrize("n,width,nsplit", [(1, 9, 1), (5000, 113, 1), (70001, 38, 3), (30000, 10, 7), (9000, 4, 2), (4100, 224, 2), (3000, 3, 4)])
+def test_streaming_partition_equals_stable_order(ctx, n, width, nsplit):
+    """uqb_partition_positions / uqb_scatter_rows_segmented (multi-GPU sample sort) against numpy: pos is the inverse of
+    the stable destination order, the byte buffer holds the rows of every destination in input order."""
+    rng = np.random.default_rng(n + width)
+    t = rng.integers(0, 256, size=(n, width), dtype=np.uint8)
+    if n > 100:
+        t[: n // 3] = t[rng.integers(0, n, n // 3)]
+    key = np.zeros(n, dtype=np.uint64)
+    for b in range(min(8, width)):
+        key |= t[:, b].astype(np.uint64) << np.uint64(8 * (7 - b))
+    splits = np.sort(key[rng.integers(0, n, nsplit)])
+    dest = np.searchsorted(splits, key, side="right")
+    order_w = np.argsort(dest, kind="stable")
+    pos_w = np.empty(n, dtype=np.uint32)
+    pos_w[order_w] = np.arange(n, dtype=np.uint32)
+    counts_w = np.bincount(dest, minlength=nsplit + 1)
+    d = ctx.upload(t)
+    pos, counts = ctx.partition_positions(d, splits)
+    assert counts == counts_w.tolist()
+    assert np.array_equal(pos.download(dtype=np.uint32).reshape(-1), pos_w)
+    buf, offs = ctx.scatter_rows_segmented(d, pos, counts, 128)
+    got = buf.download().reshape(-1)
+    first = 0
+    for k, c in enumerate(counts):
+        assert offs[k] % 128 == 0
+        seg = got[offs[k]:offs[k] + c * width].reshape(c, width)
+        assert np.array_equal(seg, t[order_w[first:first + c]]), k
+        first += c
+    # a uint32 payload follows the same positions
+    pay = ctx.upload(np.arange(n, dtype=np.uint32).view(np.uint8).reshape(n, 4))
+    pbuf, poffs = ctx.scatter_rows_segmented(pay, pos, counts, 128)
+    pgot = pbuf.download().reshape(-1)
+    first = 0
+    for k, c in enumerate(counts):
+        assert np.array_equal(pgot[poffs[k]:poffs[k] + 4 * c].view(np.uint32), order_w[first:first + c].astype(np.uint32))
+        first += c
+    for a in (d, pos, buf, pay, pbuf):
+        a.free()
+
+
 @pytest.mark.parametrize("kind,n,width", [("prefix64", 30000, 113), ("staircase", 20000, 113), ("staircase", 6000, 38),
                                           ("zeros", 4000, 300), ("prefix64", 5000, 700), ("blocks", 50000, 113)])
 def test_sort_rows_shared_prefixes(ctx, kind, n, width):

@@ -34,8 +34,9 @@ def _worker(rank, world, port, q):
     from oracle import synth
     from uq_b200 import host, multigpu as mg
     from uq_b200.device import Context
-    ctx = Context(rank)
-    comm = mg.Comm(dist, "cuda:%d" % rank)
+    ts = torch.cuda.Stream(device=rank)                  # stream-ordered exchanges, as bench.py runs them
+    ctx = Context(rank, stream=ts.cuda_stream)
+    comm = mg.Comm(dist, "cuda:%d" % rank, stream=ts)
     results = []
     # every case through the partition-first sample sort, and the first three again through the merge variant
     runs = [(c, "0") for c in CASES] + [(c, "1") for c in CASES[:3]]

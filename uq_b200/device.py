@@ -148,6 +148,26 @@ class Context:
         self.check(self.lib.uqb_gather_rows_segmented(self.h, table.h, order.h, len(counts), _ptr(counts), int(align), C.byref(h), _ptr(offs)))
         return DeviceArray(self, h), [int(o) for o in offs]
 
+    SCATTER_MAX_WIDTH = 224
+
+    def partition_positions(self, table, split_keys):
+        """streaming form of partition_rows: -> (pos: uint32[n], pos[i] = index of row i in the destination-grouped stable
+        order; counts per destination)"""
+        keys = np.ascontiguousarray(split_keys, dtype=np.uint64)
+        counts = np.zeros(len(keys) + 1, dtype=np.uint64)
+        h = C.c_void_p()
+        self.check(self.lib.uqb_partition_positions(self.h, table.h, _ptr(keys), len(keys), C.byref(h), _ptr(counts)))
+        return DeviceArray(self, h), [int(c) for c in counts]
+
+    def scatter_rows_segmented(self, table, pos, seg_counts, align=128):
+        """row i of `table` -> its place pos[i] in a byte array whose segments start at multiples of `align` bytes
+        -> (DeviceArray of bytes, byte offset of every segment); same layout as gather_rows_segmented"""
+        counts = np.ascontiguousarray(seg_counts, dtype=np.uint64)
+        offs = np.zeros(len(counts), dtype=np.uint64)
+        h = C.c_void_p()
+        self.check(self.lib.uqb_scatter_rows_segmented(self.h, table.h, pos.h, len(counts), _ptr(counts), int(align), C.byref(h), _ptr(offs)))
+        return DeviceArray(self, h), [int(o) for o in offs]
+
     def compact_segments(self, padded, seg_offsets, seg_counts, width):
         """byte array with aligned segments -> dense table [sum(seg_counts)][width]"""
         offs = np.ascontiguousarray(seg_offsets, dtype=np.uint64)

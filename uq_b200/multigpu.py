@@ -187,11 +187,35 @@ def trace_dump():
 # ------------------------------------------------------------------------------------------------
 # communication
 # ------------------------------------------------------------------------------------------------
+def _segmented(ctx, table, router, seg_counts, align=128):
+    """the rows of `table` grouped by destination in a byte buffer with aligned segments.  router = ("pos", pos) from
+    uqb_partition_positions (streaming scatter, rows of up to Context.SCATTER_MAX_WIDTH bytes) or ("order", order) from
+    uqb_partition_rows (gather)."""
+    kind, arr = router
+    if kind == "pos" and 0 < table.width <= ctx.SCATTER_MAX_WIDTH:
+        return ctx.scatter_rows_segmented(table, arr, seg_counts, align)
+    if kind == "pos":                                    # a wide payload behind a narrow sorted-on table: order = pos^-1
+        if len(router) < 3:
+            iota = ctx.upload(np.arange(arr.n, dtype=np.uint32))
+            router.append(ctx.scatter_u32(iota, arr))
+            iota.free()
+        return ctx.gather_rows_segmented(table, router[2], seg_counts, align)
+    return ctx.gather_rows_segmented(table, arr, seg_counts, align)
+
+
+def _router_free(router):
+    for a in router[1:]:
+        a.free()
+
+
 class Comm:
     """torch.distributed behind four calls; `dist=None` is the single-rank case."""
 
-    def __init__(self, dist=None, device=None):
-        self.dist, self.device = dist, device
+    def __init__(self, dist=None, device=None, stream=None):
+        """stream: the torch.cuda.Stream whose cuda_stream the Context was created on.  With it the exchanges are ordered
+        on the device (the collective waits for the rows on that stream, the stream waits for the collective) and the host
+        never blocks around them; without it every exchange is bracketed by host synchronisations."""
+        self.dist, self.device, self.stream = dist, device, stream
         self.rank = dist.get_rank() if dist else 0
         self.world = dist.get_world_size() if dist else 1
         # the small object collectives run over gloo next to NCCL: queued on the NCCL communicator they would wait
@@ -218,6 +242,24 @@ class Comm:
             return torch.empty(0, dtype=torch.uint8, device=self.device)
         return torch.as_tensor(arr, device=self.device)
 
+    def _issue(self, ctx, fn):
+        """run a torch.distributed call after the work queued on the context's stream"""
+        import torch
+        if self.stream is None or _TRACE["on"]:
+            ctx.sync()                                   # the rows are produced on the context's stream
+            return fn()
+        with torch.cuda.stream(self.stream):             # NCCL's stream waits for an event of the current stream
+            return fn()
+
+    def _complete(self, work):
+        import torch
+        if self.stream is None or _TRACE["on"]:
+            work.wait()
+            torch.cuda.current_stream().synchronize()
+            return
+        with torch.cuda.stream(self.stream):             # the context's stream waits for the collective; the host goes on
+            work.wait()
+
     def all_to_all_rows_start(self, ctx, send, send_counts, recv_counts):
         """send: DeviceArray whose rows are grouped by destination rank in rank order.  Starts the NCCL all-to-all (over
         NVLink, on torch's NCCL stream) and returns (recv, work): recv holds the rows of rank 0, 1, ... in that order
@@ -226,23 +268,22 @@ class Comm:
         recv = ctx.alloc(sum(recv_counts), w)
         if not self.dist:
             raise RuntimeError("all_to_all on a single rank")
-        ctx.sync()                                       # the rows are produced on the context's stream
         if _TRACE["on"]:
+            ctx.sync()
             self._a2a_t0, self._a2a_bytes = _time.perf_counter(), sum(send_counts) * w
         if isinstance(send, _Repeated):                  # the same rows to every peer (all-gather with uneven sizes)
             st, rt = self._tensor(send.arr), self._tensor(recv)
             roffs = [sum(recv_counts[:d]) * w for d in range(self.world)]
             outs = [rt[roffs[d]:roffs[d] + recv_counts[d] * w] for d in range(self.world)]
-            work = self.dist.all_to_all(outs, [st] * self.world, async_op=True)
+            work = self._issue(ctx, lambda: self.dist.all_to_all(outs, [st] * self.world, async_op=True))
             return recv, work
-        work = self.dist.all_to_all_single(self._tensor(recv), self._tensor(send), [c * w for c in recv_counts],
-                                           [c * w for c in send_counts], async_op=True)
+        rt, st = self._tensor(recv), self._tensor(send)
+        work = self._issue(ctx, lambda: self.dist.all_to_all_single(rt, st, [c * w for c in recv_counts],
+                                                                     [c * w for c in send_counts], async_op=True))
         return recv, work
 
     def all_to_all_rows_wait(self, work):
-        import torch
-        work.wait()
-        torch.cuda.current_stream().synchronize()
+        self._complete(work)
         if _TRACE["on"] and self.rank == 0 and getattr(self, "_a2a_t0", None) is not None:
             _TRACE["log"].append(("a2a %.2f GB sent" % (self._a2a_bytes / 1e9), round((_time.perf_counter() - self._a2a_t0) * 1e3, 2)))
             self._a2a_t0 = None
@@ -256,23 +297,24 @@ class Comm:
     # of a table of 113-byte rows start anywhere, and such an exchange runs at less than half the speed (measured:
     # 11.3 GB per rank in 32 ms against 13.6 ms).  The large exchanges therefore go through byte buffers whose
     # segments start at multiples of 128 bytes on both sides (uqb_gather_rows_segmented / uqb_compact_segments).
-    def exchange_rows_start(self, ctx, table, order, send_counts, recv_counts):
-        """the rows table[order] (grouped by destination: send_counts rows each) leave for their ranks.  Returns a handle
-        for exchange_rows_wait, which yields the DeviceArray of the rows received from rank 0, 1, ... in that order."""
+    def exchange_rows_start(self, ctx, table, router, send_counts, recv_counts):
+        """the rows of `table`, grouped by destination through `router` (see _segmented; send_counts rows each), leave for
+        their ranks.  Returns a handle for exchange_rows_wait, which yields the DeviceArray of the rows received from
+        rank 0, 1, ... in that order."""
         w = table.width
-        send_pad, soffs = ctx.gather_rows_segmented(table, order, send_counts, 128)
+        send_pad, soffs = _segmented(ctx, table, router, send_counts, 128)
         roffs, total = [], 0
         for c in recv_counts:
             roffs.append(total)
             total = (total + c * w + 127) // 128 * 128
         recv_pad = ctx.alloc(total, 1)
-        ctx.sync()                                       # the rows are produced on the context's stream
         if _TRACE["on"]:
+            ctx.sync()
             self._a2a_t0, self._a2a_bytes = _time.perf_counter(), sum(send_counts) * w
         st, rt = self._tensor(send_pad), self._tensor(recv_pad)
         ins = [st[soffs[d]:soffs[d] + send_counts[d] * w] for d in range(self.world)]
         outs = [rt[roffs[d]:roffs[d] + recv_counts[d] * w] for d in range(self.world)]
-        work = self.dist.all_to_all(outs, ins, async_op=True)
+        work = self._issue(ctx, lambda: self.dist.all_to_all(outs, ins, async_op=True))
         return dict(work=work, send=send_pad, recv=recv_pad, roffs=roffs, recv_counts=list(recv_counts), width=w)
 
     def exchange_rows_wait(self, ctx, ex):
@@ -365,9 +407,9 @@ class LocalComm:
     def all_to_all_rows(self, ctx, send, send_counts, recv_counts):
         return self.all_to_all_rows_start(ctx, send, send_counts, recv_counts)[0]
 
-    def exchange_rows_start(self, ctx, table, order, send_counts, recv_counts):
+    def exchange_rows_start(self, ctx, table, router, send_counts, recv_counts):
         w = table.width
-        send_pad, soffs = ctx.gather_rows_segmented(table, order, send_counts, 128)
+        send_pad, soffs = _segmented(ctx, table, router, send_counts, 128)
         roffs, total = [], 0
         for c in recv_counts:
             roffs.append(total)
@@ -467,29 +509,43 @@ def global_unique(ctx, comm, table, want_perm=False):
     return global_unique_end(ctx, comm, global_unique_begin(ctx, comm, table, want_perm=want_perm))
 
 
-def global_unique_begin(ctx, comm, table, want_perm=False):
+def gather_samples(ctx, comm, tables):
+    """row samples of several tables in ONE collective -> {name: what global_unique_begin(gathered=...) expects}"""
+    mine = {t: (_sample_rows(ctx, a, SAMPLES_PER_RANK), a.n) for t, a in tables.items()}
+    parts = comm.all_gather_object(mine)
+    return {t: [p[t] for p in parts] for t in tables}
+
+
+def global_unique_begin(ctx, comm, table, want_perm=False, gathered=None):
     if comm.world == 1:
         perm, key_local, uniq_local, nu = ctx.sort_rows(table, want_perm=want_perm, want_key=True, want_uniq=True)
         return dict(done=dict(key=key_local, uniq=uniq_local, n_unique=nu, counts=[nu], route=("local", perm)))
     _mark(ctx, comm, None)
-    samples = _sample_rows(ctx, table, SAMPLES_PER_RANK)
-    gathered = comm.all_gather_object((samples, table.n))
+    if gathered is None:
+        samples = _sample_rows(ctx, table, SAMPLES_PER_RANK)
+        gathered = comm.all_gather_object((samples, table.n))
     _mark(ctx, comm, "gu.sample")
     splitters = pick_splitters(np.concatenate([g[0] for g in gathered]), comm.world)
-    order, send_counts = ctx.partition_rows(table, np.sort(row_key64(splitters)))
+    if 0 < table.width <= ctx.SCATTER_MAX_WIDTH and os.environ.get("UQB_MG_GATHER") != "1":
+        pos, send_counts = ctx.partition_positions(table, np.sort(row_key64(splitters)))      # one sequential sweep
+        router = ["pos", pos]
+    else:
+        order, send_counts = ctx.partition_rows(table, np.sort(row_key64(splitters)))
+        router = ["order", order]
     send_counts += [0] * (comm.world - len(send_counts))
-    recv_counts = comm.exchange_counts(send_counts)
-    worst = max(comm.all_gather_object(sum(recv_counts)))
+    count_table = comm.all_gather_object(list(map(int, send_counts)))            # one collective: who sends how much to whom
+    recv_counts = [count_table[src][comm.rank] for src in range(comm.world)]
+    worst = max(sum(count_table[src][dst] for src in range(comm.world)) for dst in range(comm.world))
     _mark(ctx, comm, "gu.partition")
     if worst > SKEW_LIMIT * max(g[1] for g in gathered) + 4096 or os.environ.get("UQB_MG_MERGE") == "1":
-        order.free()
+        _router_free(router)
         return dict(done=global_unique_merge(ctx, comm, table, want_perm=want_perm))
-    ex = comm.exchange_rows_start(ctx, table, order, send_counts, recv_counts)
+    ex = comm.exchange_rows_start(ctx, table, router, send_counts, recv_counts)
     recv = None
     if _TRACE["on"]:                                     # diagnostics: time the exchange on its own (no overlap)
         recv = comm.exchange_rows_wait(ctx, ex)
         _mark(ctx, comm, "gu.exchange(sync)")
-    return dict(done=None, ex=ex, recv=recv, order=order, send_counts=send_counts, recv_counts=recv_counts, want_perm=want_perm)
+    return dict(done=None, ex=ex, recv=recv, router=router, send_counts=send_counts, recv_counts=recv_counts, want_perm=want_perm)
 
 
 def global_unique_end(ctx, comm, st):
@@ -498,7 +554,7 @@ def global_unique_end(ctx, comm, st):
     _mark(ctx, comm, None)
     recv = st["recv"] if st["recv"] is not None else comm.exchange_rows_wait(ctx, st["ex"])
     _mark(ctx, comm, "gu.exchange_wait")
-    order, send_counts, recv_counts, want_perm = st["order"], st["send_counts"], st["recv_counts"], st["want_perm"]
+    router, send_counts, recv_counts, want_perm = st["router"], st["send_counts"], st["recv_counts"], st["want_perm"]
     perm_r, key_r, uniq_range, nr = ctx.sort_rows(recv, want_perm=want_perm, want_key=True, want_uniq=True)
     recv.free()
     _mark(ctx, comm, "gu.sort")
@@ -506,13 +562,14 @@ def global_unique_end(ctx, comm, st):
     ctx.add_scalar_u32(key_r, sum(counts[:comm.rank]))       # global id of every received row
     ids_back = comm.all_to_all_rows(ctx, key_r, recv_counts, send_counts)        # in the order the rows were sent
     key_r.free()
-    key_global = ctx.scatter_u32(ids_back, order)
+    # ids_back is in the order the rows were sent: row i was sent at position pos[i] (= order^-1)
+    key_global = ctx.gather_rows(ids_back, router[1]) if router[0] == "pos" else ctx.scatter_u32(ids_back, router[1])
     ids_back.free()
     _mark(ctx, comm, "gu.ids_back")
     if want_perm:
-        route = ("partition", order, send_counts, recv_counts, perm_r)
+        route = ("partition", router, send_counts, recv_counts, perm_r)
     else:
-        order.free()
+        _router_free(router)
         route = None
     return dict(key=key_global, uniq=uniq_range, n_unique=sum(counts), counts=counts, route=route)
 
@@ -560,11 +617,11 @@ def global_order(ctx, comm, route, payloads):
     if kind == "partition":
         # the records follow their rows: same partition, same all-to-all, then the receiving rank's stable argsort.
         # Source ranks arrive in rank order and every source keeps its record order, so ties end in global record order.
-        _, order, send_counts, recv_counts, perm_r = route
+        _, router, send_counts, recv_counts, perm_r = route
         out = {}
         pending = None
         for name, arr in payloads.items():               # the exchange of one array overlaps the final gather of the previous one
-            ex = comm.exchange_rows_start(ctx, arr, order, send_counts, recv_counts)
+            ex = comm.exchange_rows_start(ctx, arr, router, send_counts, recv_counts)
             if pending is not None:
                 out[pending[0]] = ctx.gather_rows(pending[1], perm_r)
                 pending[1].free()
@@ -572,7 +629,7 @@ def global_order(ctx, comm, route, payloads):
         if pending is not None:
             out[pending[0]] = ctx.gather_rows(pending[1], perm_r)
             pending[1].free()
-        order.free(); perm_r.free()
+        _router_free(router); perm_r.free()
         _mark(ctx, comm, "global_order")
         return out
     _, key_global, perm, counts = route
@@ -741,16 +798,17 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
             hfq.free()
     early = comm.all_gather_object(early)[0]
     cols0, bad0 = fq.qname_scan(len(prefix), len(suffix), separators, col_mode=[1 if e else 2 for e in early])
-    bads = comm.all_gather_object(bad0)
-    if any(b >= 0 for b in bads):
-        raise host.UQError('Encoding QNAMEs as strings has not been implimented yet.')
     my_dicts = {}
-    for c in range(ncols):
-        if not early[c]:
-            toks = fq.qname_dict(c)
-            my_dicts[c] = (toks, (fq.qname_dict_first(c).astype(np.int64) + base).tolist())
-    all_plain = comm.all_gather_object(colstats_to_plain(cols0, ncols))
-    all_dicts = comm.all_gather_object(my_dicts)
+    if bad0 < 0:
+        for c in range(ncols):
+            if not early[c]:
+                toks = fq.qname_dict(c)
+                my_dicts[c] = (toks, (fq.qname_dict_first(c).astype(np.int64) + base).tolist())
+    pass2 = comm.all_gather_object((bad0, colstats_to_plain(cols0, ncols) if bad0 < 0 else None, my_dicts))
+    if any(p[0] >= 0 for p in pass2):
+        raise host.UQError('Encoding QNAMEs as strings has not been implimented yet.')
+    all_plain = [p[1] for p in pass2]
+    all_dicts = [p[2] for p in pass2]
     colstats, gdicts = merge_colstats(all_plain, n_total, early, all_dicts)
     columns = host.decide_columns(colstats, n_total, lambda i: gdicts[i])
     _mark(ctx, comm, "pass2")
@@ -819,9 +877,10 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
     # sampled / partitioned / gathered and the previous one is sorted (context stream).  DNA goes first: its exchange is
     # the shortest one to leave uncovered, and the long QUAL exchange then hides behind the DNA sort.
     todo = [t for t in ('DNA', 'QUAL', 'QNAME') if keyed[t] or t == sorted_on]
+    samples = gather_samples(ctx, comm, {t: tables[t] for t in todo}) if comm.world > 1 and todo else {}
     pending = None
     for t in todo:
-        st = global_unique_begin(ctx, comm, tables[t], want_perm=(t == sorted_on))
+        st = global_unique_begin(ctx, comm, tables[t], want_perm=(t == sorted_on), gathered=samples.get(t))
         if pending is not None:
             finish(*pending)
         pending = (t, st)
