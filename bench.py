@@ -148,6 +148,10 @@ def run_ours(args):
     # configs[1] - with a fixed 10 Mbp genome an N-GPU file would hold N times as many copies of every read
     genome = GENOME * world
     pool = max(1, n * world // 5)
+    if args.strong and world > 1:
+        # strong scaling (diagnostics, profiles/): ONE configs[1] file of --reads reads in total, 1/N of it per GPU
+        genome, pool = GENOME, max(1, n // 5)
+        n = n // world
     first, n = shard.shard_range(rank, world, n)
     dev = ctx.synth("genome", n, READ_LEN, SEED, first=first, genome=genome, pool=pool)
     fbytes = dev.nbytes
@@ -349,7 +353,7 @@ def run_ours(args):
         line = {
             "metric": "fastq_to_uq_encode_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "configs[1]: %d reads x %d bp per GPU, --sort DNA, keyed DNA/QUAL/QNAME tables, pattern 0.1 0.1"
                                    % (n, READ_LEN),
                        "reads_per_gpu": n, "read_len": READ_LEN, "fastq_bytes_per_gpu": int(fbytes),
@@ -539,6 +543,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=20000)
     ap.add_argument("--multi", default=os.environ.get("UQ_BENCH_MULTI", "global"), choices=["shards", "global"],
                     help="N>1: independent container shards per rank, or one global container (collectives on the data path)")
+    ap.add_argument("--strong", action="store_true", help="N>1: --reads is the TOTAL number of reads (strong scaling) instead of reads per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e without copy/compute overlap (diagnostics)")

@@ -829,8 +829,50 @@ static int stats_tiles_range(uqb_ctx* ctx, const uqb_fastq* fq, an_dev* s, unsig
         return 0;
     }
     static_assert(sizeof(h2_smem) <= 227 * 1024, "unit histogram shared memory");
-    UQB_CUDA(cudaFuncSetAttribute(k_pair_hist_units, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(h2_smem)));
-    UQB_LAUNCH_B(ab, k_pair_hist_units, g2, H2_THREADS, sizeof(h2_smem), fq->d, fq->n, fq->line_off, r0, r1, s, d_fb);
+    static_assert(sizeof(h3_smem) <= 227 * 1024, "pipelined unit histogram shared memory");
+    static const bool hist_v2 = [] { const char* e = getenv("UQB_HIST_V2"); return e && e[0] == '1'; }();
+    if (hist_v2) {
+        UQB_CUDA(cudaFuncSetAttribute(k_pair_hist_units, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(h2_smem)));
+        UQB_LAUNCH_B(ab, k_pair_hist_units, g2, H2_THREADS, sizeof(h2_smem), fq->d, fq->n, fq->line_off, r0, r1, s, d_fb);
+        return 0;
+    }
+    UQB_CUDA(cudaFuncSetAttribute(k_pair_hist_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(h3_smem)));
+    UQB_LAUNCH_B(ab, k_pair_hist_pipe, g2, H2_THREADS, sizeof(h3_smem), fq->d, fq->n, fq->line_off, r0, r1, s, d_fb, (uint8_t*)nullptr, 0u);
+    return 0;
+}
+
+// The whole file is resident (uqb_analyze): the histogram kernel also writes the compact QNAME array (fq->names), and the
+// name statistics - like the tokeniser and the dictionary rows later - read that instead of the FASTQ.
+// *fb_out: bit 0 = use the generic kernels, bit 2 = a name did not fit the compact rows (they are dropped)
+static int stats_tiles_resident(uqb_ctx* ctx, uqb_fastq* fq, an_dev* s, unsigned int* d_fb, uint32_t flen, uint32_t own_first_len,
+                                unsigned int* fb_out) {
+    const uint64_t N = fq->n_reads;
+    static const bool plain = [] { const char* e = getenv("UQB_NO_NAMES"); return (e && e[0] == '1') || getenv("UQB_HIST_V1") || getenv("UQB_HIST_V2"); }();
+    uint32_t pitch = (own_first_len + 1 + 24 + 15) / 16 * 16;
+    if (pitch < 32) pitch = 32;
+    if (plain || pitch > 256 || fq->names) {
+        UQB_TRY(stats_tiles_range(ctx, fq, s, d_fb, flen, 0, N));
+        UQB_TRY(uqb_readback(ctx, fb_out, d_fb, 4));
+        return 0;
+    }
+    uint8_t* names;
+    UQB_TRY(uqb_dalloc(ctx, (void**)&names, N * pitch + 64));
+    const uint64_t ntiles = (N + TL_R - 1) / TL_R;
+    const unsigned g2 = (unsigned)(ntiles < (uint64_t)ctx->sm_count ? ntiles : (uint64_t)ctx->sm_count);
+    UQB_CUDA(cudaFuncSetAttribute(k_pair_hist_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(h3_smem)));
+    UQB_LAUNCH_B(fq->n + 32 * N + N * pitch, k_pair_hist_pipe, g2, H2_THREADS, sizeof(h3_smem), fq->d, fq->n, fq->line_off, 0ull, N, s, d_fb, names, pitch);
+    UQB_TRY(uqb_readback(ctx, fb_out, d_fb, 4));
+    if (*fb_out & 5u) {                                  // generic kernels, or a long name: no compact array
+        UQB_TRY(uqb_dfree(ctx, names, 0));
+        if (!(*fb_out & 1u))
+            UQB_LAUNCH_B(N * 96, k_record_stats_names, uqb_grid(ctx, N, RD_THREADS, 8), RD_THREADS, sizeof(rd_smem), fq->d, fq->line_off, 0ull, N,
+                         fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb, (const uint8_t*)nullptr, 0u, 0);
+    } else {
+        fq->names = names; fq->name_pitch = pitch; fq->names_cap = N;
+        UQB_LAUNCH_B(N * pitch, k_record_stats_names, uqb_grid(ctx, N, RD_THREADS, 8), RD_THREADS, sizeof(rd_smem), fq->d, fq->line_off, 0ull, N,
+                     fq->ref_name ? fq->ref_name : fq->d, fq->rbase, flen, s, d_fb, (const uint8_t*)names, pitch, 0);
+    }
+    UQB_TRY(uqb_readback(ctx, fb_out, d_fb, 4));         // the name statistics may ask for the generic kernels, too
     return 0;
 }
 
@@ -1081,11 +1123,10 @@ extern "C" int uqb_analyze(uqb_ctx* ctx, uqb_fastq* fq, uqb_stats* out) {
         UQB_TRY(uqb_dalloc_t(ctx, &d_fb, 1));
         UQB_CUDA(cudaMemsetAsync(d_fb, 0, 4, ctx->stream));
         UQB_LAUNCH(k_an_init, 1, 256, 0, s);
-        UQB_TRY(stats_tiles_range(ctx, fq, s, d_fb, (uint32_t)flen, 0, N));
         unsigned int fb = 0;
-        UQB_TRY(uqb_readback(ctx, &fb, d_fb, 4));
+        UQB_TRY(stats_tiles_resident(ctx, fq, s, d_fb, (uint32_t)flen, out->first_len, &fb));
         UQB_TRY(uqb_dfree(ctx, d_fb, 4));
-        done_fast = fb == 0;
+        done_fast = (fb & 3u) == 0;
     } else if ((((uintptr_t)fq->d) & 15) == 0) {
         // long reads: the same counters straight from global memory
         unsigned int* d_fb;

@@ -29,13 +29,17 @@
 #define H2_COLS 512              // QUAL threads per CTA
 #define H2_NOHINT 0x00060402u    // slot c holds a byte whose code is c + 1: nothing validates
 
-struct h2_smem {
-    tile2_smem T;
-    alignas(16) uint8_t qcnt[H2_ROWS * H2_COLS];
+struct h2_core {                    // CTA-wide results
     unsigned hist_b[256];
     unsigned hist_q[H2_ROWS + 1];
     int state[256];                 // per base byte: -1 unseen, 0..255 its only quality so far, 256 = several
-    unsigned hints, dirty, oor;
+    unsigned hints, dirty, oor, qmax;
+};
+
+struct h2_smem {
+    tile2_smem T;
+    alignas(16) uint8_t qcnt[H2_ROWS * H2_COLS];
+    h2_core C;
 };
 
 __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
@@ -58,7 +62,7 @@ __device__ __forceinline__ unsigned h2_bytesum(unsigned x) {
 }
 
 // one base that is not a hint: CTA histogram + single-quality state
-__device__ __forceinline__ void h2_slow_byte(h2_smem* S, unsigned b, unsigned q) {
+__device__ __forceinline__ void h2_slow_byte(h2_core* S, unsigned b, unsigned q) {
     atomicAdd(&S->hist_b[b], 1u);
     int f = S->state[b];
     if (f != (int)q && f != 256) {
@@ -79,7 +83,7 @@ struct h2_dna_acc {
 
 // thread-private flush of the base accumulators (H = the hints they were collected under); by value, so that the
 // accumulators stay in registers
-__device__ __noinline__ void h2_dna_flush_vals(h2_smem* S, unsigned p0, unsigned p1, unsigned p01, unsigned ocnt, unsigned words,
+__device__ __noinline__ void h2_dna_flush_vals(h2_core* S, unsigned p0, unsigned p1, unsigned p01, unsigned ocnt, unsigned words,
                                                unsigned zeroed, unsigned H) {
     const unsigned s0 = h2_bytesum(p0), s1 = h2_bytesum(p1) >> 1, s01 = h2_bytesum(p01);
     const unsigned n3 = s01, n1 = s0 - s01, n2 = s1 - s01, n0 = 4u * words - zeroed - n1 - n2 - n3;
@@ -89,13 +93,13 @@ __device__ __noinline__ void h2_dna_flush_vals(h2_smem* S, unsigned p0, unsigned
     if (v2) atomicAdd(&S->hist_b[(H >> 16) & 255u], v2);
     if (v3) atomicAdd(&S->hist_b[H >> 24], v3);
 }
-__device__ __forceinline__ void h2_dna_flush(h2_smem* S, h2_dna_acc& A, unsigned H) {
+__device__ __forceinline__ void h2_dna_flush(h2_core* S, h2_dna_acc& A, unsigned H) {
     h2_dna_flush_vals(S, A.p0, A.p1, A.p01, A.ocnt, A.words, A.zeroed, H);
     A.p0 = A.p1 = A.p01 = A.ocnt = A.words = A.zeroed = A.noff = 0;
 }
 
 // the same for a whole warp (all 32 lanes call it): shuffle reductions, lane 0 adds
-__device__ __forceinline__ void h2_dna_flush_warp(h2_smem* S, h2_dna_acc& A, unsigned H, unsigned lane) {
+__device__ __forceinline__ void h2_dna_flush_warp(h2_core* S, h2_dna_acc& A, unsigned H, unsigned lane) {
     unsigned s0 = h2_bytesum(A.p0), s1 = h2_bytesum(A.p1) >> 1, s01 = h2_bytesum(A.p01);
     unsigned nw = A.words, nz = A.zeroed;
     unsigned oc[4];
@@ -120,7 +124,7 @@ __device__ __forceinline__ void h2_dna_flush_warp(h2_smem* S, h2_dna_acc& A, uns
 
 // sixteen bases: v = the unit's four words, ua = its shared-memory address, delta = distance to the quality of the same
 // position, [lo, hi) = valid bytes of the unit
-__device__ __forceinline__ void h2_dna_unit(h2_smem* S, const uint4 v, uint32_t ua, uint32_t delta, int lo, int hi, unsigned H,
+__device__ __forceinline__ void h2_dna_unit(h2_core* S, const uint4 v, uint32_t ua, uint32_t delta, int lo, int hi, unsigned H,
                                             h2_dna_acc& A) {
     unsigned w[4] = {v.x, v.y, v.z, v.w}, t[4], bad[4];
 #pragma unroll
@@ -199,7 +203,7 @@ __device__ __forceinline__ bool h2_qual_unit(const uint4 v, int lo, int hi, uint
 }
 
 // thread-private flush of one counter column (only when a single tile gives a thread more than ~240 qualities)
-__device__ __noinline__ void h2_qual_flush(h2_smem* S, uint32_t qcol) {
+__device__ __noinline__ void h2_qual_flush(h2_core* S, uint32_t qcol) {
     for (unsigned r = 0; r < H2_ROWS; r++) {
         const uint32_t a = qcol + ((r + H2_QLO) << 9);
         const unsigned c = lds_u8m(a);
@@ -215,9 +219,9 @@ __global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_units(const uint8_t
     h2_smem* S = reinterpret_cast<h2_smem*>(h2_raw);
     const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     for (unsigned i = tid; i < H2_ROWS * H2_COLS / 4; i += H2_THREADS) reinterpret_cast<uint32_t*>(S->qcnt)[i] = 0;
-    for (unsigned i = tid; i <= H2_ROWS; i += H2_THREADS) S->hist_q[i] = 0;
-    if (tid < 256) { S->hist_b[tid] = 0; S->state[tid] = -1; }
-    if (tid == 0) { S->hints = H2_NOHINT; S->dirty = 0; S->oor = 0; }
+    for (unsigned i = tid; i <= H2_ROWS; i += H2_THREADS) S->C.hist_q[i] = 0;
+    if (tid < 256) { S->C.hist_b[tid] = 0; S->C.state[tid] = -1; }
+    if (tid == 0) { S->C.hints = H2_NOHINT; S->C.dirty = 0; S->C.oor = 0; }
     __syncthreads();
     const unsigned line = tid & 255u, rec = line & 127u, k0 = tid >> 8;
     const bool isq = (line >> 7) != 0;
@@ -257,19 +261,19 @@ __global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_units(const uint8_t
                 const uint4 v = lds_v4(bytes_a + u);
                 const int lo = (int)sb - (int)u, hi = (int)eb - (int)u;      // valid bytes of the unit: [lo, hi) clipped to 0..16
                 if (isq) {
-                    if (qsym > 255u - 16u) { h2_qual_flush(S, qcol); qsym = 0; }
-                    if (!h2_qual_unit(v, lo, hi, qcol)) S->oor = 1u;
+                    if (qsym > 255u - 16u) { h2_qual_flush(&S->C, qcol); qsym = 0; }
+                    if (!h2_qual_unit(v, lo, hi, qcol)) S->C.oor = 1u;
                     qsym += 16u;
                 } else {
-                    if (A.words > 120u || A.noff > 224u) h2_dna_flush(S, A, H);
-                    h2_dna_unit(S, v, bytes_a + u, o3 - o1, lo, hi, H, A);
+                    if (A.words > 120u || A.noff > 224u) h2_dna_flush(&S->C, A, H);
+                    h2_dna_unit(&S->C, v, bytes_a + u, o3 - o1, lo, hi, H, A);
                 }
                 tile_sym += 16u;
             }
         }
         // CTA-wide flush before any 8-bit field can overflow in the next tile (assumed no larger than this one), or when
         // a base has become a hint candidate
-        const bool vote = isq ? (qsym + tile_sym > 255u - 16u) : (A.words + (tile_sym >> 2) > 120u || A.noff + tile_sym > 224u || (tid == 0 && S->dirty));
+        const bool vote = isq ? (qsym + tile_sym > 255u - 16u) : (A.words + (tile_sym >> 2) > 120u || A.noff + tile_sym > 224u || (tid == 0 && S->C.dirty));
         if (P.finish_or(vote)) {
             for (unsigned r = wid; r < H2_ROWS; r += H2_THREADS / 32) {
                 uint32_t* row = reinterpret_cast<uint32_t*>(S->qcnt + r * H2_COLS);
@@ -282,19 +286,19 @@ __global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_units(const uint8_t
                 }
                 unsigned tot = (e & 0xFFFFu) + (e >> 16) + (o & 0xFFFFu) + (o >> 16);
                 tot = __reduce_add_sync(0xffffffffu, tot);
-                if (lane == 0) S->hist_q[r] += tot;
+                if (lane == 0) S->C.hist_q[r] += tot;
             }
             qsym = 0;
-            h2_dna_flush_warp(S, A, H, lane);
+            h2_dna_flush_warp(&S->C, A, H, lane);
             __syncthreads();
-            if (S->dirty) {                                                   // uniform: written before the barrier above
+            if (S->C.dirty) {                                                   // uniform: written before the barrier above
                 if (wid == 0) {
                     unsigned best[4] = {0, 0, 0, 0};
 #pragma unroll
                     for (unsigned j = 0; j < 8; j++) {
                         const unsigned b = lane + 32u * j;
-                        if (S->state[b] == 256) {
-                            const unsigned cnt = S->hist_b[b] < 0xFFFFFFu ? S->hist_b[b] : 0xFFFFFFu;
+                        if (S->C.state[b] == 256) {
+                            const unsigned cnt = S->C.hist_b[b] < 0xFFFFFFu ? S->C.hist_b[b] : 0xFFFFFFu;
                             const unsigned key = ((cnt + 1u) << 8) | b;
                             const unsigned c = (b >> 1) & 3u;
 #pragma unroll
@@ -307,11 +311,11 @@ __global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_units(const uint8_t
                         const unsigned m = __reduce_max_sync(0xffffffffu, best[c]);
                         h |= (m ? (m & 255u) : ((H2_NOHINT >> (8 * c)) & 255u)) << (8 * c);
                     }
-                    if (lane == 0) { S->hints = h; S->dirty = 0; }
+                    if (lane == 0) { S->C.hints = h; S->C.dirty = 0; }
                 }
                 __syncthreads();
             }
-            H = S->hints;
+            H = S->C.hints;
         }
     }
     // ---- final flush ----
@@ -331,14 +335,267 @@ __global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_units(const uint8_t
         }
     }
     __syncthreads();
-    if (isq) h2_qual_flush(S, qcol);
-    h2_dna_flush_warp(S, A, H, lane);
+    if (isq) h2_qual_flush(&S->C, qcol);
+    h2_dna_flush_warp(&S->C, A, H, lane);
     __syncthreads();
     if (tid < 256) {
-        if (S->hist_b[tid]) atomicAdd(&s->base_count[tid], (unsigned long long)S->hist_b[tid]);
-        if (tid < H2_ROWS - 1 && S->hist_q[tid]) atomicAdd(&s->qual_count[tid + H2_QLO], (unsigned long long)S->hist_q[tid]);
-        if (tid == 0 && S->oor) atomicOr(fallback, 1u);
-        const int f = S->state[tid];
+        if (S->C.hist_b[tid]) atomicAdd(&s->base_count[tid], (unsigned long long)S->C.hist_b[tid]);
+        if (tid < H2_ROWS - 1 && S->C.hist_q[tid]) atomicAdd(&s->qual_count[tid + H2_QLO], (unsigned long long)S->C.hist_q[tid]);
+        if (tid == 0 && S->C.oor) atomicOr(fallback, 1u);
+        const int f = S->C.state[tid];
+        if (f >= 0) {
+            if (f == 256) {
+                s->multi[tid] = 1;
+                atomicCAS(&s->first_q[tid], -1, 0);                 // mark the base as present
+            } else {
+                const int old = atomicCAS(&s->first_q[tid], -1, f);
+                if (old >= 0 && old != f) s->multi[tid] = 1;
+            }
+        }
+    }
+}
+
+// ---- the same counting behind a three-stage, barrier-free tile pipeline ----------------------------------
+// k_pair_hist_units synchronises the whole CTA at the end of every tile (2 us of work): the warps that own the short
+// last units wait for the others, every thread pays the line-offset conversion of the next tile, and the vote for the
+// counter flush rides on that barrier.  Here the tiles flow through THREE buffers guarded by mbarriers:
+//   full[s]    32 arrivals + the transaction count of the TMA bulk copy of the tile's bytes: every warp has converted its 17
+//              of the tile's 513 line offsets (their low 32 bits are enough inside a tile), warp 31 has issued the copy;
+//   empty[s]   32 arrivals: every warp is done with the tile that used the buffer.
+// A warp waits for nothing but these two, so the warps drift apart by up to two tiles and the per-tile work imbalance
+// averages out.  The CTA meets at a real barrier only every F tiles, F adapted so that the 8-bit
+// quality counters reach about 200 between two flushes.
+#define H3_STAGES 3
+struct h3_smem {
+    alignas(128) uint8_t bytes[H3_STAGES][TL_CAP + 32];
+    uint32_t loff[H3_STAGES][4 * TL_R + 4];
+    alignas(8) uint64_t full[H3_STAGES];
+    alignas(8) uint64_t empty[H3_STAGES];
+    uint32_t ok[H3_STAGES];
+    alignas(16) uint8_t qcnt[H2_ROWS * H2_COLS];
+    h2_core C;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_pipe(const uint8_t* __restrict__ d, uint64_t n_bytes,
+                                                                 const uint64_t* __restrict__ line_off, uint64_t r_begin, uint64_t n_reads,
+                                                                 an_dev* __restrict__ s, unsigned int* __restrict__ fallback,
+                                                                 uint8_t* __restrict__ names, uint32_t name_pitch) {
+    // names (optional): compact side array of the QNAME lines, row r = length byte + text in name_pitch (multiple of 16)
+    // bytes.  The name statistics, the tokeniser and the dictionary rows then read 48 bytes per record instead of the
+    // 128-byte lines of the FASTQ that hold the names.  A name that does not fit raises bit 2 of `fallback`.
+    static_assert(TL_R == 128, "thread <-> line binding assumes 128 records per tile");
+    extern __shared__ __align__(128) uint8_t h3_raw[];
+    h3_smem* S = reinterpret_cast<h3_smem*>(h3_raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    for (unsigned i = tid; i < H2_ROWS * H2_COLS / 4; i += H2_THREADS) reinterpret_cast<uint32_t*>(S->qcnt)[i] = 0;
+    for (unsigned i = tid; i <= H2_ROWS; i += H2_THREADS) S->C.hist_q[i] = 0;
+    if (tid < 256) { S->C.hist_b[tid] = 0; S->C.state[tid] = -1; }
+    if (tid == 0) {
+        S->C.hints = H2_NOHINT; S->C.dirty = 0; S->C.oor = 0; S->C.qmax = 0;
+        for (int st = 0; st < H3_STAGES; st++) { mbar_init(&S->full[st], H2_THREADS / 32); mbar_init(&S->empty[st], H2_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned line = tid & 255u, rec = line & 127u, k0 = tid >> 8;
+    const bool isq = (line >> 7) != 0;
+    const bool producer = wid == H2_THREADS / 32 - 1;
+    const unsigned cw = ((wid >> 3) << 2) | (wid & 3u);
+    const uint32_t qcol = smem_u32(S->qcnt) + lane * 4u + (cw & 3u) + 128u * (cw >> 2) - (H2_QLO << 9);
+    unsigned qsym = 0;
+    h2_dna_acc A;
+    A.p0 = A.p1 = A.p01 = A.ocnt = A.words = A.zeroed = A.noff = 0;
+    unsigned H = H2_NOHINT;
+    unsigned long long len_min = ~0ull, len_max = 0ull;
+    long long bad_plus = LLONG_MAX, bad_len = LLONG_MAX;
+
+    const uint64_t ntiles = (n_reads - r_begin + TL_R - 1) / TL_R;
+    const uint32_t K = blockIdx.x < ntiles ? (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;   // tiles of this CTA
+
+    // Tile k of this CTA -> buffer k % 3.  Every warp converts 17 of the tile's 513 line offsets (one global load per lane,
+    // issued two tiles ahead and consumed at the end of the current tile, so its latency is never exposed); warp 31 also
+    // issues the bulk copy.  full[s] therefore takes one arrival per warp plus the copy's transaction count.
+    constexpr uint32_t OPW = (4 * TL_R + 1 + H2_THREADS / 32 - 1) / (H2_THREADS / 32);        // offsets per warp: 17
+    uint64_t pend_off = 0, pend_b0 = 0, pend_b1 = 0;      // loads in flight for the tile that is being prepared
+    auto tile_first = [&](uint32_t k) { return r_begin + ((uint64_t)blockIdx.x + (uint64_t)k * gridDim.x) * TL_R; };
+    auto tile_nrec = [&](uint32_t k) { const uint64_t r0 = tile_first(k); return (uint32_t)(n_reads - r0 < TL_R ? n_reads - r0 : TL_R); };
+    auto prep_load = [&](uint32_t k) {                    // start the loads for tile k
+        const uint64_t* lo = line_off + 4 * tile_first(k);
+        const uint32_t nrec = tile_nrec(k), i = wid * OPW + lane;
+        if (lane < OPW && i <= 4 * nrec) pend_off = __ldg(lo + i);
+        if (producer && lane == 0) { pend_b0 = __ldg(lo); pend_b1 = __ldg(lo + 4 * nrec); }
+    };
+    auto prep_store = [&](uint32_t k) {                   // finish them: offsets into the buffer, bulk copy, arrivals
+        const uint32_t st = k % H3_STAGES;
+        if (k >= H3_STAGES) mbar_wait(&S->empty[st], ((k / H3_STAGES) - 1u) & 1u);        // every warp has left the previous tile of this buffer
+        const uint32_t nrec = tile_nrec(k), i = wid * OPW + lane;
+        if (lane < OPW && i <= 4 * nrec) S->loff[st][i] = (uint32_t)pend_off;
+        if (producer) {
+            const uint64_t b0 = __shfl_sync(0xffffffffu, pend_b0, 0), b1 = __shfl_sync(0xffffffffu, pend_b1, 0);
+            const uint64_t a0 = b0 & ~15ull;
+            const bool fits = b1 - a0 <= TL_CAP;
+            uint64_t a1 = (b1 + 15) & ~15ull;
+            const uint64_t lim = n_bytes & ~15ull;         // never read past the last full 16-byte unit of the buffer
+            if (a1 > lim) a1 = lim;
+            if (a1 < a0) a1 = a0;
+            if (fits) for (uint64_t q = a1 + lane; q < b1; q += 32) S->bytes[st][q - a0] = d[q];   // tail of the stream (last tile only)
+            __syncwarp();
+            if (lane == 0) {
+                S->ok[st] = fits ? 1u : 0u;
+                const uint32_t bulk = fits ? (uint32_t)(a1 - a0) : 0u;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&S->full[st], bulk);        // this warp's arrival
+                if (bulk) bulk_g2s(S->bytes[st], d + a0, bulk, &S->full[st]);
+            }
+        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->full[st]);
+        }
+    };
+
+    for (uint32_t k = 0; k < K && k < H3_STAGES - 1; k++) { prep_load(k); prep_store(k); }
+    uint32_t F = 1, next_flush = 1;
+    for (uint32_t k = 0; k < K; k++) {
+        const uint32_t st = k % H3_STAGES;
+        const bool ahead = k + H3_STAGES - 1 < K;
+        if (ahead) prep_load(k + H3_STAGES - 1);
+        mbar_wait(&S->full[st], (k / H3_STAGES) & 1u);
+        const uint64_t r0 = tile_first(k);
+        const uint32_t nrec = tile_nrec(k);
+        if (S->ok[st] && names) {                      // every thread, whatever its own line: 8 lanes copy one name
+            const uint32_t bytes_a = smem_u32(S->bytes[st]);
+            const uint32_t* loff = S->loff[st];
+            const uint32_t base32 = loff[0] & ~15u;
+            const uint32_t nr = 4u * wid + (lane >> 3), sl = lane & 7u;
+            if (nr < nrec) {
+                const uint32_t n0 = loff[4 * nr] - base32, nlen = loff[4 * nr + 1] - base32 - n0 - 1u;
+                if (nlen + 1u > name_pitch || nlen > 255u) {
+                    if (sl == 0) atomicOr(&S->C.oor, 2u);
+                } else {
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(names + (r0 + nr) * name_pitch);
+                    const uint32_t nwords = (nlen + 4u) >> 2;                  // words that hold the length byte and the text
+                    for (uint32_t q = sl; q < nwords; q += 8) {
+                        // image bytes 4 q .. 4 q + 3: byte 0 is the length, byte b > 0 is text byte b - 1
+                        const uint32_t at = n0 + (q ? 4u * q - 1u : 0u), al = bytes_a + (at & ~3u);
+                        const uint32_t x = __funnelshift_r(lds_u32(al), lds_u32(al + 4u), (at & 3u) * 8u);
+                        dst[q] = q ? x : ((x << 8) | nlen);
+                    }
+                }
+            }
+        }
+        if (!S->ok[st]) {
+            if (tid == 0) atomicOr(fallback, 1u);
+        } else if (rec < nrec) {
+            const uint32_t bytes_a = smem_u32(S->bytes[st]);
+            const uint32_t* loff = S->loff[st];
+            const uint32_t base32 = loff[0] & ~15u;
+            const uint32_t o1 = loff[4 * rec + 1] - base32, o2 = loff[4 * rec + 2] - base32, o3 = loff[4 * rec + 3] - base32,
+                           o4 = loff[4 * rec + 4] - base32;
+            uint32_t len = o2 - o1 - 1;
+            const uint32_t qlen = o4 - o3 - 1;
+            if (tid < TL_R) {                          // DNA thread of unit 0: the record's checks
+                const long long r = (long long)(r0 + rec);
+                if (len != qlen && r < bad_len) bad_len = r;
+                len_min = len < len_min ? len : len_min; len_max = len > len_max ? len : len_max;
+                const unsigned plus = o3 - o2 < 2u ? 0u : lds_u8(bytes_a + o2);
+                if (plus != '+' && r < bad_plus) bad_plus = r;
+            }
+            if (qlen < len) len = qlen;
+            const uint32_t sb = isq ? o3 : o1, eb = sb + len;
+            for (uint32_t u = (sb & ~15u) + 16u * k0; u < eb; u += 64u) {
+                const uint4 v = lds_v4(bytes_a + u);
+                const int lo = (int)sb - (int)u, hi = (int)eb - (int)u;
+                if (isq) {
+                    if (qsym > 255u - 16u) { h2_qual_flush(&S->C, qcol); qsym = 0; }
+                    if (!h2_qual_unit(v, lo, hi, qcol)) atomicOr(&S->C.oor, 1u);
+                    qsym += 16u;
+                } else {
+                    if (A.words > 120u || A.noff > 224u) h2_dna_flush(&S->C, A, H);
+                    h2_dna_unit(&S->C, v, bytes_a + u, o3 - o1, lo, hi, H, A);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S->empty[st]);
+        if (ahead) prep_store(k + H3_STAGES - 1);
+        if (k + 1 == next_flush || k + 1 == K) {
+            // ---- the CTA meets: counter columns -> CTA histograms, hints ----
+            const unsigned wq = __reduce_max_sync(0xffffffffu, isq ? qsym : 0u);
+            if (lane == 0 && wq) atomicMax(&S->C.qmax, wq);
+            __syncthreads();
+            for (unsigned r = wid; r < H2_ROWS; r += H2_THREADS / 32) {
+                uint32_t* row = reinterpret_cast<uint32_t*>(S->qcnt + r * H2_COLS);
+                unsigned e = 0, o = 0;
+#pragma unroll
+                for (int j = 0; j < H2_COLS / 128; j++) {
+                    const unsigned x = row[lane + 32 * j];
+                    row[lane + 32 * j] = 0;
+                    e += x & 0x00FF00FFu; o += (x >> 8) & 0x00FF00FFu;
+                }
+                unsigned tot = (e & 0xFFFFu) + (e >> 16) + (o & 0xFFFFu) + (o >> 16);
+                tot = __reduce_add_sync(0xffffffffu, tot);
+                if (lane == 0) S->C.hist_q[r] += tot;
+            }
+            qsym = 0;
+            h2_dna_flush_warp(&S->C, A, H, lane);
+            const unsigned m = S->C.qmax;                                     // read by every thread before it is reset
+            __syncthreads();
+            if (S->C.dirty && wid == 0) {
+                unsigned best[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (unsigned j = 0; j < 8; j++) {
+                    const unsigned b = lane + 32u * j;
+                    if (S->C.state[b] == 256) {
+                        const unsigned cnt = S->C.hist_b[b] < 0xFFFFFFu ? S->C.hist_b[b] : 0xFFFFFFu;
+                        const unsigned key = ((cnt + 1u) << 8) | b;
+                        const unsigned c = (b >> 1) & 3u;
+#pragma unroll
+                        for (unsigned cc = 0; cc < 4; cc++) if (c == cc && key > best[cc]) best[cc] = key;
+                    }
+                }
+                unsigned h = 0;
+#pragma unroll
+                for (unsigned c = 0; c < 4; c++) {
+                    const unsigned mx = __reduce_max_sync(0xffffffffu, best[c]);
+                    h |= (mx ? (mx & 255u) : ((H2_NOHINT >> (8 * c)) & 255u)) << (8 * c);
+                }
+                if (lane == 0) { S->C.hints = h; S->C.dirty = 0; }
+            }
+            if (tid == 0) S->C.qmax = 0;
+            __syncthreads();
+            H = S->C.hints;
+            // next meeting: the busiest column should reach about 200 increments
+            const unsigned rate = max(m / F, 16u);
+            F = min(max(208u / rate, 1u), 32u);
+            next_flush = k + 1 + F;
+        }
+    }
+    // ---- results ----
+    if (tid < TL_R) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long a = __shfl_xor_sync(0xffffffffu, len_min, o), b = __shfl_xor_sync(0xffffffffu, len_max, o);
+            const long long e = __shfl_xor_sync(0xffffffffu, bad_plus, o), f = __shfl_xor_sync(0xffffffffu, bad_len, o);
+            len_min = a < len_min ? a : len_min; len_max = b > len_max ? b : len_max;
+            bad_plus = e < bad_plus ? e : bad_plus; bad_len = f < bad_len ? f : bad_len;
+        }
+        if (lane == 0) {
+            if (len_min != ~0ull) atomicMin(&s->dna_min, len_min);
+            atomicMax(&s->dna_max, len_max);
+            if (bad_plus != LLONG_MAX) atomicMin(&s->bad_plus, bad_plus);
+            if (bad_len != LLONG_MAX) atomicMin(&s->bad_len, bad_len);
+        }
+    }
+    __syncthreads();
+    if (tid < 256) {
+        if (S->C.hist_b[tid]) atomicAdd(&s->base_count[tid], (unsigned long long)S->C.hist_b[tid]);
+        if (tid < H2_ROWS - 1 && S->C.hist_q[tid]) atomicAdd(&s->qual_count[tid + H2_QLO], (unsigned long long)S->C.hist_q[tid]);
+        if (tid == 0 && (S->C.oor & 1u)) atomicOr(fallback, 1u);
+        if (tid == 0 && (S->C.oor & 2u)) atomicOr(fallback, 4u);
+        const int f = S->C.state[tid];
         if (f >= 0) {
             if (f == 256) {
                 s->multi[tid] = 1;
