@@ -161,6 +161,18 @@ def run_ours(args):
     if global_mode:
         from uq_b200 import multigpu
         comm = multigpu.Comm(dist, "cuda:%d" % local_rank, stream=tstream)
+        if not args.no_p2p:
+            # receive slots every rank can store into (symmetric memory): 3 slots, each holding the largest table a rank can
+            # receive (113-byte QUAL rows, 30 % skew margin).  A table that does not fit goes through NCCL instead.
+            try:
+                slot = int(1.3 * n * 128)
+                comm.window = multigpu.open_peer_window(dist, "cuda:%d" % local_rank, tstream, 3 * slot, slots=3)
+                exchange = "peer window (symmetric memory, %d x %.1f GB per rank): rows stored into the receivers' memory by uqb_scatter_rows_to" % (3, slot / 1e9)
+            except Exception as e:                       # no peer mapping on this box: NCCL all-to-all
+                comm.window = None
+                exchange = "nccl all_to_all (peer window unavailable: %s)" % str(e).splitlines()[0][:120]
+        else:
+            exchange = "nccl all_to_all"
 
     parity = None
     if global_mode and not args.no_parity:
@@ -369,6 +381,8 @@ def run_ours(args):
         }
         if parity is not None:
             line["parity_check"] = parity
+        if global_mode:
+            line["config"]["row_exchange"] = exchange
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -544,6 +558,7 @@ def main():
     ap.add_argument("--multi", default=os.environ.get("UQ_BENCH_MULTI", "global"), choices=["shards", "global"],
                     help="N>1: independent container shards per rank, or one global container (collectives on the data path)")
     ap.add_argument("--strong", action="store_true", help="N>1: --reads is the TOTAL number of reads (strong scaling) instead of reads per GPU")
+    ap.add_argument("--no-p2p", action="store_true", help="N>1: row exchanges through NCCL all-to-all instead of direct stores into peer memory")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e without copy/compute overlap (diagnostics)")

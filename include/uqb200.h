@@ -219,6 +219,11 @@ int uqb_partition_positions(uqb_ctx* ctx, const uqb_array* table, const uint64_t
                             uqb_array** pos, uint64_t* counts_host);
 int uqb_scatter_rows_segmented(uqb_ctx* ctx, const uqb_array* table, const uqb_array* pos, uint32_t nseg,
                                const uint64_t* seg_counts_host, uint32_t align, uqb_array** out, uint64_t* seg_offsets_host);
+/* device-initiated exchange: the rows of segment d go straight to the device address dst_addrs_host[d] (dense, in position
+ * order) - normally the receive buffer of rank d mapped into this process (peer memory over NVLink).  The caller brackets
+ * the call with its own barriers. */
+int uqb_scatter_rows_to(uqb_ctx* ctx, const uqb_array* table, const uqb_array* pos, uint32_t nseg,
+                        const uint64_t* seg_counts_host, const uint64_t* dst_addrs_host);
 /* the inverse on the receiving side: byte array with aligned segments -> dense table of `width`-byte rows */
 int uqb_compact_segments(uqb_ctx* ctx, const uqb_array* padded, uint32_t nseg, const uint64_t* seg_offsets_host,
                          const uint64_t* seg_counts_host, uint32_t width, uqb_array** out);

@@ -247,7 +247,8 @@ def test_sort_rows_shared_prefixes(ctx, kind, n, width):
         a.free()
 
 
-@pytest.mark.parametrize("n,width", [(1, 1), (1, 7), (9, 1), (65, 64), (64, 65), (1000, 38), (777, 113), (5, 300), (130, 129)])
+@pytest.mark.parametrize("n,width", [(1, 1), (1, 7), (9, 1), (65, 64), (64, 65), (1000, 38), (777, 113), (5, 300), (130, 129),
+                                     (1001, 5001), (300, 1000), (3, 17501), (513, 200), (259, 257)])
 def test_layouts_match_numpy(ctx, n, width):
     from oracle.uq_literal import PATTERNS, apply_pattern
     rng = np.random.default_rng(n + 7 * width)

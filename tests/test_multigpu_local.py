@@ -39,14 +39,17 @@ def _gen(kind, n, length, first=0):
     return synth.make_fastq(kind=kind, n=n, length=length, seed=21, first=first, **kwg)
 
 
-def _sharded_encode(world, whole_records, kw, merge=False):
-    """whole_records: list of per-record byte strings -> (members on rank 0, config)"""
+def _sharded_encode(world, whole_records, kw, merge=False, window=0):
+    """whole_records: list of per-record byte strings -> (members on rank 0, config).  window > 0: the row exchanges go
+    through a peer window of that many bytes (direct stores into the other ranks' memory)."""
     import os
     from uq_b200 import multigpu as mg
     cuts = _cuts(len(whole_records), world)
 
     def body(ctx, comm):
         os.environ["UQB_MG_MERGE"] = "1" if merge else "0"
+        if window:
+            comm.open_window(ctx, window)
         shard = b"".join(whole_records[cuts[comm.rank]:cuts[comm.rank + 1]])
         fq = ctx.load_fastq(shard)
         res, cfg = mg.encode_sharded(ctx, comm, fq, **kw)
@@ -86,6 +89,19 @@ def test_sharded_encode_equals_single_gpu(ctx, world, case):
     got, cfg = _sharded_encode(world, _records(whole), kw)
     assert_members_equal(got, want, "%s world=%d %r" % (kind, world, kw))
     assert json.loads(json.dumps(cfg, default=str)) == json.loads(json.dumps(want_cfg, default=str))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_sharded_encode_through_peer_window(ctx, world, case):
+    """the device-initiated exchange (uqb_scatter_rows_to into the peers' receive slots, barriers around it) gives the
+    same container; the window is small enough that the largest table of some cases falls back to the collective"""
+    from uq_b200 import host
+    kind, n, length, kw = CASES[case]
+    whole = _gen(kind, n, length)
+    want, _ = host.encode(whole, ctx=ctx, **kw)
+    got, _ = _sharded_encode(world, _records(whole), kw, window=3 * 600_000)
+    assert_members_equal(got, want, "window %s world=%d %r" % (kind, world, kw))
 
 
 @pytest.mark.parametrize("case", [0, 2, 3])

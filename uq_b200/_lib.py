@@ -119,6 +119,7 @@ SIGNATURES = {
     "uqb_compact_segments": (C.c_int, [P, P, C.c_uint32, P, P, C.c_uint32, PP]),
     "uqb_partition_positions": (C.c_int, [P, P, P, C.c_uint32, PP, P]),
     "uqb_scatter_rows_segmented": (C.c_int, [P, P, P, C.c_uint32, P, C.c_uint32, PP, P]),
+    "uqb_scatter_rows_to": (C.c_int, [P, P, P, C.c_uint32, P, P]),
     "uqb_qname_scan": (C.c_int, [P, P, C.c_uint32, C.c_uint32, P, C.c_uint32, C.POINTER(ColStats), C.POINTER(C.c_int64)]),
     "uqb_qname_dict_info": (C.c_int, [P, P, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "uqb_qname_dict": (C.c_int, [P, P, C.c_uint32, P, C.c_uint64]),

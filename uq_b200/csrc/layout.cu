@@ -185,6 +185,116 @@ __global__ void __launch_bounds__(LT) k_layout_rows_tall(const uint8_t* __restri
     }
 }
 
+// ---- wide rows (long reads: 5 - 17 kB per row) ------------------------------------------------------
+// Column-major forms, panels: a CTA takes PN_R rows x PN_C columns.  The panel lives in shared memory row by row with a
+// pitch of PN_C + 1 BYTES: rows 4 k (k = lane) then fall into different banks, so the stream side can collect the four
+// bytes of a 32-bit word of one column's run (rows 4 k .. 4 k + 3) without bank conflicts, and the table side writes a
+// row's bytes with conflict-free byte stores.  Table side: one coalesced 128-byte segment per row (aligned 32-bit
+// loads + funnel shift, rows start at any byte); stream side: one run of PN_R bytes per column, moved as aligned
+// 32-bit words (the first / last bytes of a run one by one, runs start at any byte because n is arbitrary).
+#define PN_R 256
+#define PN_C 128
+#define PN_P (PN_C + 1)
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(LT) k_layout_transpose_panel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n,
+                                                              uint32_t width, int rev_r, int rev_b) {
+    __shared__ uint8_t pan[PN_R * PN_P + 8];
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t npc = (width + PN_C - 1) / PN_C;
+    const uint64_t npr = (n + PN_R - 1) / PN_R, npan = npr * npc;
+    for (uint64_t pidx = blockIdx.x; pidx < npan; pidx += gridDim.x) {
+        const uint64_t pr = pidx / npc;
+        const uint32_t pc = (uint32_t)(pidx - pr * npc);
+        const uint64_t r0 = pr * PN_R;
+        const uint32_t b0 = pc * PN_C;
+        const uint32_t nr = (uint32_t)(n - r0 < PN_R ? n - r0 : PN_R), nc = width - b0 < PN_C ? width - b0 : PN_C;
+        const uint64_t lo = rev_r ? n - r0 - nr : r0;                  // first stream index (within a column) of this panel
+        __syncthreads();
+        if (!INVERSE) {
+            // table -> panel: warp per row, lane l takes bytes 4 l .. 4 l + 3 of the row's segment
+            for (uint32_t i = w; i < nr; i += LT / 32) {
+                if (4u * lane < nc) {
+                    const uint64_t x = (uint64_t)(uintptr_t)src + (r0 + i) * width + b0 + 4u * lane;
+                    const uint32_t ph = (uint32_t)x & 3u;
+                    const uint32_t* a = reinterpret_cast<const uint32_t*>(x - ph);
+                    const uint32_t v = __funnelshift_r(__ldg(a), __ldg(a + 1), ph * 8u);     // may read up to 3 bytes past the row: table slack
+                    uint8_t* p = pan + i * PN_P + 4u * lane;
+                    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+                }
+            }
+            __syncthreads();
+        }
+        // stream side: warp per column run
+        for (uint32_t c = w; c < nc; c += LT / 32) {
+            const uint32_t b = b0 + c, bp = rev_b ? width - 1 - b : b;
+            const uint64_t a0 = (uint64_t)bp * n + lo;                 // stream address of the run
+            const uint8_t* sp = src + a0;
+            uint8_t* dp = dst + a0;
+            const uint32_t head = min(nr, (uint32_t)((4u - ((uintptr_t)(INVERSE ? (const void*)sp : (const void*)dp) & 3u)) & 3u));
+            const uint32_t nwords = (nr - head) >> 2, tail0 = head + 4u * nwords;
+            // stream offset t <-> panel row: t (or nr - 1 - t when the rows are reversed)
+            if (!INVERSE) {
+                if (lane < head) dp[lane] = pan[(rev_r ? nr - 1 - lane : lane) * PN_P + c];
+                for (uint32_t q = lane; q < nwords; q += 32) {
+                    const uint32_t t = head + 4u * q;
+                    uint32_t v = 0;
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; j++) v |= (uint32_t)pan[(rev_r ? nr - 1 - (t + j) : t + j) * PN_P + c] << (8 * j);
+                    reinterpret_cast<uint32_t*>(dp + head)[q] = v;
+                }
+                if (lane < nr - tail0) dp[tail0 + lane] = pan[(rev_r ? nr - 1 - (tail0 + lane) : tail0 + lane) * PN_P + c];
+            } else {
+                if (lane < head) pan[(rev_r ? nr - 1 - lane : lane) * PN_P + c] = __ldg(sp + lane);
+                for (uint32_t q = lane; q < nwords; q += 32) {
+                    const uint32_t t = head + 4u * q;
+                    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(sp + head) + q);
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; j++) pan[(rev_r ? nr - 1 - (t + j) : t + j) * PN_P + c] = (uint8_t)(v >> (8 * j));
+                }
+                if (lane < nr - tail0) pan[(rev_r ? nr - 1 - (tail0 + lane) : tail0 + lane) * PN_P + c] = __ldg(sp + tail0 + lane);
+            }
+        }
+        if (INVERSE) {
+            __syncthreads();
+            // panel -> table: warp per row, byte stores (a row's segment starts at any byte)
+            for (uint32_t i = w; i < nr; i += LT / 32) {
+                uint8_t* o = dst + (r0 + i) * width + b0;
+                const uint8_t* p = pan + i * PN_P;
+                for (uint32_t x = lane; x < nc; x += 32) o[x] = p[x];
+            }
+        }
+    }
+}
+
+// Row-major forms with reversed rows and / or bytes, any width: warp per row; the output row is written as aligned 32-bit
+// words (its first / last bytes one by one), each taken from the source row with two aligned loads and a funnel shift
+// (byte-swapped when the bytes are reversed).  Reversing is its own inverse.
+__global__ void __launch_bounds__(LT) k_layout_rows_wide(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n, uint32_t width,
+                                                        int rev_r, int rev_b) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t wstride = (uint64_t)gridDim.x * (LT / 32);
+    for (uint64_t r = (uint64_t)blockIdx.x * (LT / 32) + (threadIdx.x >> 5); r < n; r += wstride) {
+        const uint8_t* s = src + r * width;
+        uint8_t* d = dst + (rev_r ? n - 1 - r : r) * width;
+        const uint32_t head = min(width, (uint32_t)((4u - ((uintptr_t)d & 3u)) & 3u));
+        const uint32_t nwords = (width - head) >> 2, tail0 = head + 4u * nwords;
+        if (lane < head) d[lane] = __ldg(s + (rev_b ? width - 1 - lane : lane));
+#pragma unroll 4
+        for (uint32_t q = lane; q < nwords; q += 32) {
+            const uint32_t t = head + 4u * q;                          // output bytes t .. t + 3
+            const uint32_t so = rev_b ? width - 4u - t : t;            // they come from source bytes so .. so + 3 (reversed when rev_b)
+            const uint64_t x = (uint64_t)(uintptr_t)s + so;
+            const uint32_t ph = (uint32_t)x & 3u;
+            const uint32_t* a = reinterpret_cast<const uint32_t*>(x - ph);
+            uint32_t v = __funnelshift_r(__ldg(a), ph ? __ldg(a + 1) : 0u, ph * 8u);
+            if (rev_b) v = __byte_perm(v, 0u, 0x0123);
+            reinterpret_cast<uint32_t*>(d + head)[q] = v;
+        }
+        if (lane < width - tail0) d[tail0 + lane] = __ldg(s + (rev_b ? width - 1 - (tail0 + lane) : tail0 + lane));
+    }
+}
+
 static int layout_impl(uqb_ctx* ctx, const uint8_t* src, uint8_t* dst, uint64_t n, uint32_t width, int pattern, bool inverse) {
     layout_desc ld;
     if (pattern_desc(pattern, &ld)) return uqb_fail(ctx, "layout: pattern id %d out of range", pattern);
@@ -193,6 +303,8 @@ static int layout_impl(uqb_ctx* ctx, const uint8_t* src, uint8_t* dst, uint64_t 
         const size_t smem = (size_t)LR_ROWS * width + 16;
         UQB_CUDA(cudaFuncSetAttribute(k_layout_rows_tall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         UQB_LAUNCH_B(2 * n * width, k_layout_rows_tall, uqb_grid(ctx, n, LR_ROWS, 16), LT, smem, src, dst, n, width, ld.rev_r, ld.rev_b);
+    } else if (!ld.transposed && width >= 64) {
+        UQB_LAUNCH_B(2 * n * width, k_layout_rows_wide, uqb_grid(ctx, n, LT / 32, 16), LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
     } else if (!ld.transposed) {
         unsigned g = uqb_grid(ctx, n, LT / 32, 16);
         if (inverse) UQB_LAUNCH_B(2 * n * width, k_layout_rows<true>, g, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
@@ -207,6 +319,12 @@ static int layout_impl(uqb_ctx* ctx, const uint8_t* src, uint8_t* dst, uint64_t 
             UQB_CUDA(cudaFuncSetAttribute(k_layout_transpose_tall<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             UQB_LAUNCH_B(2 * n * width, k_layout_transpose_tall<false>, g, LT, smem, src, dst, n, width, ld.rev_r, ld.rev_b);
         }
+    } else if (width >= 64) {
+        const uint64_t npan = ((n + PN_R - 1) / PN_R) * ((width + PN_C - 1) / PN_C);
+        const uint64_t cap = (uint64_t)ctx->sm_count * 6;
+        const unsigned g = (unsigned)(npan < cap ? npan : cap);
+        if (inverse) UQB_LAUNCH_B(2 * n * width, k_layout_transpose_panel<true>, g, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
+        else         UQB_LAUNCH_B(2 * n * width, k_layout_transpose_panel<false>, g, LT, 0, src, dst, n, width, ld.rev_r, ld.rev_b);
     } else {
         uint64_t gx = (n + TILE - 1) / TILE;
         if (gx > 0x7fffffffull) return uqb_fail(ctx, "layout: too many rows");

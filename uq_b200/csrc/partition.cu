@@ -217,30 +217,12 @@ __global__ void __launch_bounds__(SR_THREADS) k_scatter_items_by_pos(const T* __
 
 static inline uint64_t pp_round(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
-extern "C" int uqb_scatter_rows_segmented(uqb_ctx* ctx, const uqb_array* table, const uqb_array* pos, uint32_t nseg,
-                                          const uint64_t* seg_counts_host, uint32_t align, uqb_array** out, uint64_t* seg_offsets_host) {
-    if (pos->width != 4 || pos->n != table->n) return uqb_fail(ctx, "scatter_rows_segmented: one uint32 position per row expected");
-    if (nseg == 0 || nseg > PP_MAXW) return uqb_fail(ctx, "scatter_rows_segmented: 1..%d segments", PP_MAXW);
-    if (align == 0 || (align & 15u)) return uqb_fail(ctx, "scatter_rows_segmented: alignment must be a multiple of 16");
+// rows -> place: S.off[d] is either a byte offset into `out` or, with out == nullptr, an absolute device address
+static int scatter_rows_impl(uqb_ctx* ctx, const uqb_array* table, const uqb_array* pos, const pp_segs& S, uint8_t* o) {
     const uint32_t w = table->width;
-    if (w == 0 || w > SR_MAXW) return uqb_fail(ctx, "scatter_rows_segmented: rows of 1..%d bytes (use uqb_gather_rows_segmented for wider ones)", SR_MAXW);
-    pp_segs S;
-    S.n = nseg;
-    uint64_t total = 0, rows = 0;
-    for (uint32_t d = 0; d < nseg; d++) {
-        S.first[d] = rows;
-        S.off[d] = total;
-        seg_offsets_host[d] = total;
-        total = pp_round(total + seg_counts_host[d] * w, align);
-        rows += seg_counts_host[d];
-    }
-    S.first[nseg] = rows;
-    if (rows != table->n) return uqb_fail(ctx, "scatter_rows_segmented: the segments hold %llu rows, the table %llu",
-                                          (unsigned long long)rows, (unsigned long long)table->n);
-    UQB_TRY(uqb_new_array(ctx, total, 1, out));
     const uint64_t n = table->n;
     if (n == 0) return 0;
-    uint8_t* o = (uint8_t*)(*out)->d;
+    if ((reinterpret_cast<uintptr_t>(table->d) & 15u) != 0) return uqb_fail(ctx, "scatter_rows: the table must be 16-byte aligned");
     const uint64_t ab = n * (2ull * w + 4);
     if (w == 4) {
         UQB_LAUNCH_B(ab, k_scatter_items_by_pos<uint32_t>, uqb_grid(ctx, n, SR_THREADS, 8), SR_THREADS, 0, (const uint32_t*)table->d, n, (const uint32_t*)pos->d, S, o);
@@ -270,4 +252,54 @@ extern "C" int uqb_scatter_rows_segmented(uqb_ctx* ctx, const uqb_array* table, 
         }
     }
     return 0;
+}
+
+static int scatter_check(uqb_ctx* ctx, const uqb_array* table, const uqb_array* pos, uint32_t nseg, const char* who) {
+    if (pos->width != 4 || pos->n != table->n) return uqb_fail(ctx, "%s: one uint32 position per row expected", who);
+    if (nseg == 0 || nseg > PP_MAXW) return uqb_fail(ctx, "%s: 1..%d segments", who, PP_MAXW);
+    if (table->width == 0 || table->width > SR_MAXW) return uqb_fail(ctx, "%s: rows of 1..%d bytes (use uqb_gather_rows_segmented for wider ones)", who, SR_MAXW);
+    return 0;
+}
+
+extern "C" int uqb_scatter_rows_segmented(uqb_ctx* ctx, const uqb_array* table, const uqb_array* pos, uint32_t nseg,
+                                          const uint64_t* seg_counts_host, uint32_t align, uqb_array** out, uint64_t* seg_offsets_host) {
+    UQB_TRY(scatter_check(ctx, table, pos, nseg, "scatter_rows_segmented"));
+    if (align == 0 || (align & 15u)) return uqb_fail(ctx, "scatter_rows_segmented: alignment must be a multiple of 16");
+    const uint32_t w = table->width;
+    pp_segs S;
+    S.n = nseg;
+    uint64_t total = 0, rows = 0;
+    for (uint32_t d = 0; d < nseg; d++) {
+        S.first[d] = rows;
+        S.off[d] = total;
+        seg_offsets_host[d] = total;
+        total = pp_round(total + seg_counts_host[d] * w, align);
+        rows += seg_counts_host[d];
+    }
+    S.first[nseg] = rows;
+    if (rows != table->n) return uqb_fail(ctx, "scatter_rows_segmented: the segments hold %llu rows, the table %llu",
+                                          (unsigned long long)rows, (unsigned long long)table->n);
+    UQB_TRY(uqb_new_array(ctx, total, 1, out));
+    return scatter_rows_impl(ctx, table, pos, S, (uint8_t*)(*out)->d);
+}
+
+// The device-initiated form of the exchange: the rows of segment d are written straight to the device address dst_addrs_host[d]
+// (dense, in position order) - the receive buffer of rank d, mapped into this process (peer memory over NVLink), at the
+// place this rank's rows have in it.  No send buffer, no collective, no compaction on the other side; the caller brackets
+// the call with its barriers.
+extern "C" int uqb_scatter_rows_to(uqb_ctx* ctx, const uqb_array* table, const uqb_array* pos, uint32_t nseg,
+                                   const uint64_t* seg_counts_host, const uint64_t* dst_addrs_host) {
+    UQB_TRY(scatter_check(ctx, table, pos, nseg, "scatter_rows_to"));
+    pp_segs S;
+    S.n = nseg;
+    uint64_t rows = 0;
+    for (uint32_t d = 0; d < nseg; d++) {
+        S.first[d] = rows;
+        S.off[d] = dst_addrs_host[d];
+        rows += seg_counts_host[d];
+    }
+    S.first[nseg] = rows;
+    if (rows != table->n) return uqb_fail(ctx, "scatter_rows_to: the segments hold %llu rows, the table %llu",
+                                          (unsigned long long)rows, (unsigned long long)table->n);
+    return scatter_rows_impl(ctx, table, pos, S, nullptr);
 }

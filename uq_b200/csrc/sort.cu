@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(ST) k_small_groups(const uint8_t* __restrict__
 //             increasing order (rows that both equal the first row in a word equal each other there): typically one
 //             or two word compares per pair.  rank = rows before it (ties keep their current = input order);
 //   output    permutation, heads of the distinct rows and done flags, in place.
-// Groups of more than 32 rows are skipped and their rows counted; the caller then runs the general rounds for them.
+// Groups of more than 32 rows are skipped and reported; the caller then runs the general rounds for them.
 #define SGP_CHUNK 2048
 template <int SUB>
 __global__ void __launch_bounds__(ST) k_small_groups_packed(const uint8_t* __restrict__ rows, uint32_t width, uint32_t off,
@@ -443,18 +443,17 @@ __global__ void __launch_bounds__(ST) k_small_groups_packed(const uint8_t* __res
             const unsigned h2 = __ballot_sync(0xffffffffu, cur + 32 + lane < n ? head[cur + 32 + lane] != 0u : true);
             const unsigned hi = (h1 >> 1) | (h2 << 31);            // bit k: a group starts at cur + 1 + k
             if (!hi) {
-                // more than 32 rows: find where the group ends, count, skip
-                uint64_t nxt;
+                // more than 32 rows: report it and skip to the next group that starts inside this chunk (the rest of a group
+                // that runs past the chunk belongs to nobody: the warps of the following chunks start at their first head)
+                uint64_t nxt = c1;
                 if (h2 >> 1) nxt = cur + 32 + ((unsigned)__ffs((int)(h2 >> 1)));
                 else {
-                    uint64_t q = cur + 64;
-                    for (;;) {
+                    for (uint64_t q = cur + 64; q < c1; q += 32) {
                         const unsigned hb = __ballot_sync(0xffffffffu, q + lane < n ? head[q + lane] != 0u : true);
                         if (hb) { nxt = q + (unsigned)__ffs((int)hb) - 1u; break; }
-                        q += 32;
                     }
                 }
-                if (lane == 0) my_large += nxt - cur;
+                if (lane == 0) my_large += 33;                       // only "any large group" matters to the caller
                 cur = nxt;
                 continue;
             }

@@ -168,6 +168,12 @@ class Context:
         self.check(self.lib.uqb_scatter_rows_segmented(self.h, table.h, pos.h, len(counts), _ptr(counts), int(align), C.byref(h), _ptr(offs)))
         return DeviceArray(self, h), [int(o) for o in offs]
 
+    def scatter_rows_to(self, table, pos, seg_counts, dst_addrs):
+        """row i of `table` -> device address dst_addrs[d] + (pos[i] - first row of d) * width (peer memory included)"""
+        counts = np.ascontiguousarray(seg_counts, dtype=np.uint64)
+        addrs = np.ascontiguousarray(dst_addrs, dtype=np.uint64)
+        self.check(self.lib.uqb_scatter_rows_to(self.h, table.h, pos.h, len(counts), _ptr(counts), _ptr(addrs)))
+
     def compact_segments(self, padded, seg_offsets, seg_counts, width):
         """byte array with aligned segments -> dense table [sum(seg_counts)][width]"""
         offs = np.ascontiguousarray(seg_offsets, dtype=np.uint64)

@@ -208,6 +208,66 @@ def _router_free(router):
         a.free()
 
 
+class PeerWindow:
+    """Receive memory that every rank can write: ptrs[r] is the device address, valid in THIS process, of rank r's buffer
+    (symmetric / peer-mapped memory over NVLink; for the emulated ranks of LocalComm plain pointers of the one device).
+    The buffer is cut into `slots` equal slots which the row exchanges use round-robin - every rank runs the same
+    sequence of exchanges, so the slot of an exchange needs no agreement.  barrier() is ordered on the context's stream
+    and spans all ranks: before an exchange it says that nobody reads the slot's previous contents any more, after it
+    that all rows have landed."""
+
+    def __init__(self, ptrs, rank, nbytes, slots, barrier, keep=None):
+        self.ptrs, self.rank, self.slots = [int(p) for p in ptrs], rank, slots
+        self.slot_bytes = nbytes // slots // 256 * 256
+        self.barrier = barrier
+        self.seq = 0
+        self._keep = keep
+
+    def next_slot(self):
+        base = (self.seq % self.slots) * self.slot_bytes
+        self.seq += 1
+        return base
+
+
+def open_peer_window(dist, device, stream, nbytes, slots=3):
+    """torch symmetric memory (CUDA VMM handles exchanged through the process group's store): one allocation per rank,
+    mapped into every other rank of the node.  Collective; call it once, outside the timed loop."""
+    import torch
+    import torch.distributed._symmetric_memory as symm_mem
+    buf = symm_mem.empty(int(nbytes), dtype=torch.uint8, device=device)
+    hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+
+    def barrier():
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                hdl.barrier(channel=0)
+        else:
+            hdl.barrier(channel=0)
+            torch.cuda.current_stream().synchronize()
+    return PeerWindow(list(hdl.buffer_ptrs), dist.get_rank(), int(nbytes), slots, barrier, keep=(buf, hdl))
+
+
+def _p2p_plan(comm, ctx, table, router, count_table):
+    """-> (slot base, destination address of this rank's rows in every rank's slot) when the exchange can go through the
+    peer window, else None.  Decided from the count table alone, so every rank decides alike."""
+    win = getattr(comm, "window", None)
+    w = table.width
+    if win is None or count_table is None or router[0] != "pos" or not (0 < w <= ctx.SCATTER_MAX_WIDTH):
+        return None
+    world = comm.world
+    if max(sum(count_table[s][d] for s in range(world)) for d in range(world)) * w > win.slot_bytes:
+        return None
+    base = win.next_slot()
+    return base, [win.ptrs[d] + base + sum(count_table[s][d] for s in range(comm.rank)) * w for d in range(world)]
+
+
+def _p2p_exchange(comm, ctx, table, router, send_counts, recv_counts, plan):
+    base, addrs = plan
+    comm.window.barrier()                                # nobody reads what the slot held before
+    ctx.scatter_rows_to(table, router[1], send_counts, addrs)
+    return dict(p2p=True, recv=ctx.wrap(comm.window.ptrs[comm.rank] + base, sum(recv_counts), table.width))
+
+
 class Comm:
     """torch.distributed behind four calls; `dist=None` is the single-rank case."""
 
@@ -216,6 +276,7 @@ class Comm:
         on the device (the collective waits for the rows on that stream, the stream waits for the collective) and the host
         never blocks around them; without it every exchange is bracketed by host synchronisations."""
         self.dist, self.device, self.stream = dist, device, stream
+        self.window = None                               # PeerWindow: row exchanges as direct stores into the peers' memory
         self.rank = dist.get_rank() if dist else 0
         self.world = dist.get_world_size() if dist else 1
         # the small object collectives run over gloo next to NCCL: queued on the NCCL communicator they would wait
@@ -297,11 +358,15 @@ class Comm:
     # of a table of 113-byte rows start anywhere, and such an exchange runs at less than half the speed (measured:
     # 11.3 GB per rank in 32 ms against 13.6 ms).  The large exchanges therefore go through byte buffers whose
     # segments start at multiples of 128 bytes on both sides (uqb_gather_rows_segmented / uqb_compact_segments).
-    def exchange_rows_start(self, ctx, table, router, send_counts, recv_counts):
+    def exchange_rows_start(self, ctx, table, router, send_counts, recv_counts, count_table=None):
         """the rows of `table`, grouped by destination through `router` (see _segmented; send_counts rows each), leave for
         their ranks.  Returns a handle for exchange_rows_wait, which yields the DeviceArray of the rows received from
-        rank 0, 1, ... in that order."""
+        rank 0, 1, ... in that order.  With a peer window (and the full count table) the rows are stored straight into
+        the receivers' memory by this rank's own kernel; otherwise NCCL moves them."""
         w = table.width
+        plan = _p2p_plan(self, ctx, table, router, count_table)
+        if plan is not None:
+            return _p2p_exchange(self, ctx, table, router, send_counts, recv_counts, plan)
         send_pad, soffs = _segmented(ctx, table, router, send_counts, 128)
         roffs, total = [], 0
         for c in recv_counts:
@@ -318,6 +383,9 @@ class Comm:
         return dict(work=work, send=send_pad, recv=recv_pad, roffs=roffs, recv_counts=list(recv_counts), width=w)
 
     def exchange_rows_wait(self, ctx, ex):
+        if ex.get("p2p"):
+            self.window.barrier()                        # every rank's rows have landed
+            return ex["recv"]
         self.all_to_all_rows_wait(ex["work"])
         ex["send"].free()
         out = ctx.compact_segments(ex["recv"], ex["roffs"], ex["recv_counts"], ex["width"])
@@ -407,8 +475,23 @@ class LocalComm:
     def all_to_all_rows(self, ctx, send, send_counts, recv_counts):
         return self.all_to_all_rows_start(ctx, send, send_counts, recv_counts)[0]
 
-    def exchange_rows_start(self, ctx, table, router, send_counts, recv_counts):
+    window = None
+
+    def open_window(self, ctx, nbytes, slots=3):
+        """the emulated ranks share one device: every rank's buffer is directly addressable by the others"""
+        buf = ctx.alloc(int(nbytes), 1)
+        ptrs = self.all_gather_object(int(buf.device_ptr.value))
+
+        def barrier():
+            ctx.sync()
+            self.barrier()
+        self.window = PeerWindow(ptrs, self.rank, int(nbytes), slots, barrier, keep=buf)
+
+    def exchange_rows_start(self, ctx, table, router, send_counts, recv_counts, count_table=None):
         w = table.width
+        plan = _p2p_plan(self, ctx, table, router, count_table)
+        if plan is not None:
+            return _p2p_exchange(self, ctx, table, router, send_counts, recv_counts, plan)
         send_pad, soffs = _segmented(ctx, table, router, send_counts, 128)
         roffs, total = [], 0
         for c in recv_counts:
@@ -419,6 +502,9 @@ class LocalComm:
         return dict(work=None, send=send_pad, recv=recv_pad, roffs=roffs, recv_counts=list(recv_counts), width=w)
 
     def exchange_rows_wait(self, ctx, ex):
+        if ex.get("p2p"):
+            self.window.barrier()
+            return ex["recv"]
         ex["send"].free()
         out = ctx.compact_segments(ex["recv"], ex["roffs"], ex["recv_counts"], ex["width"])
         ex["recv"].free()
@@ -540,12 +626,13 @@ def global_unique_begin(ctx, comm, table, want_perm=False, gathered=None):
     if worst > SKEW_LIMIT * max(g[1] for g in gathered) + 4096 or os.environ.get("UQB_MG_MERGE") == "1":
         _router_free(router)
         return dict(done=global_unique_merge(ctx, comm, table, want_perm=want_perm))
-    ex = comm.exchange_rows_start(ctx, table, router, send_counts, recv_counts)
+    ex = comm.exchange_rows_start(ctx, table, router, send_counts, recv_counts, count_table=count_table)
     recv = None
     if _TRACE["on"]:                                     # diagnostics: time the exchange on its own (no overlap)
         recv = comm.exchange_rows_wait(ctx, ex)
         _mark(ctx, comm, "gu.exchange(sync)")
-    return dict(done=None, ex=ex, recv=recv, router=router, send_counts=send_counts, recv_counts=recv_counts, want_perm=want_perm)
+    return dict(done=None, ex=ex, recv=recv, router=router, send_counts=send_counts, recv_counts=recv_counts, want_perm=want_perm,
+                count_table=count_table)
 
 
 def global_unique_end(ctx, comm, st):
@@ -567,7 +654,7 @@ def global_unique_end(ctx, comm, st):
     ids_back.free()
     _mark(ctx, comm, "gu.ids_back")
     if want_perm:
-        route = ("partition", router, send_counts, recv_counts, perm_r)
+        route = ("partition", router, send_counts, recv_counts, perm_r, st["count_table"])
     else:
         _router_free(router)
         route = None
@@ -617,11 +704,11 @@ def global_order(ctx, comm, route, payloads):
     if kind == "partition":
         # the records follow their rows: same partition, same all-to-all, then the receiving rank's stable argsort.
         # Source ranks arrive in rank order and every source keeps its record order, so ties end in global record order.
-        _, router, send_counts, recv_counts, perm_r = route
+        _, router, send_counts, recv_counts, perm_r, count_table = route
         out = {}
         pending = None
         for name, arr in payloads.items():               # the exchange of one array overlaps the final gather of the previous one
-            ex = comm.exchange_rows_start(ctx, arr, router, send_counts, recv_counts)
+            ex = comm.exchange_rows_start(ctx, arr, router, send_counts, recv_counts, count_table=count_table)
             if pending is not None:
                 out[pending[0]] = ctx.gather_rows(pending[1], perm_r)
                 pending[1].free()
