@@ -11,6 +11,7 @@
 //                staged in shared memory with 16-byte loads and leaves as 32-bit words.
 // The same pos moves every per-record payload of global_order, and brings the global ids back with a gather.
 #include "common.cuh"
+#include <cstdlib>
 
 #define PP_THREADS 256
 #define PP_TILE 2048
@@ -205,6 +206,94 @@ __global__ void __launch_bounds__(SR_THREADS) k_scatter_rows_by_pos(const uint8_
     }
 }
 
+// The same move with CONTIGUOUS RUNS on the output side.  The rows of one tile that go to destination d are consecutive in
+// d's stream (pos is stable), so the CTA first regroups the tile by destination inside shared memory - the run of d starts
+// at an image offset with the same 16-byte phase as its global address - and then writes every run with aligned 16-byte
+// stores (only the first / last few bytes of a run go one by one).  The row-at-a-time kernel above writes 113-byte rows as
+// unaligned 4-byte words: fine for local memory, but over NVLink (peer windows) that is a packet per sector - measured 240
+// GB/s against 770 GB/s for large aligned stores.
+#define SRR_MAXD 64
+template <int SUB>
+__global__ void __launch_bounds__(SR_THREADS) k_scatter_rows_runs(const uint8_t* __restrict__ rows, uint64_t n, uint32_t width,
+                                                                 const uint32_t* __restrict__ pos, pp_segs segs, uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t srr_smem[];                 // [input tile | output image]
+    __shared__ uint32_t cnt[SRR_MAXD], minpos[SRR_MAXD], ioff[SRR_MAXD], rowdst[SR_THREADS];
+    __shared__ uint64_t gaddr[SRR_MAXD];
+    constexpr uint32_t NP = 32u / SUB;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    const unsigned sg = lane / SUB, sl = lane % SUB;
+    const uint32_t in_bytes = (SR_THREADS * width + 32u + 15u) & ~15u;
+    uint8_t* in = srr_smem;
+    uint8_t* img = srr_smem + in_bytes;
+    const uint32_t* in32 = reinterpret_cast<const uint32_t*>(in);
+    const uint64_t ntiles = (n + SR_THREADS - 1) / SR_THREADS;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t r0 = t * SR_THREADS;
+        const uint32_t nr = (uint32_t)(n - r0 < SR_THREADS ? n - r0 : SR_THREADS);
+        __syncthreads();
+        if (tid < segs.n) { cnt[tid] = 0; minpos[tid] = 0xFFFFFFFFu; }
+        const uint4* src = reinterpret_cast<const uint4*>(rows + r0 * width);
+        const uint32_t nvec = (nr * width + 15u) / 16u;
+        uint32_t j = 0, d = 0;
+        if (tid < nr) { j = __ldg(pos + r0 + tid); d = pp_seg_of(segs, j); }
+#pragma unroll 4
+        for (uint32_t v = tid; v < nvec; v += SR_THREADS) reinterpret_cast<uint4*>(in)[v] = __ldg(src + v);
+        __syncthreads();
+        if (tid < nr) { atomicAdd(&cnt[d], 1u); atomicMin(&minpos[d], j); }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t at = 0;
+            for (uint32_t k = 0; k < segs.n; k++) {
+                if (!cnt[k]) continue;
+                const uint64_t g = segs.off[k] + (uint64_t)(minpos[k] - segs.first[k]) * width + (uint64_t)(uintptr_t)out;
+                gaddr[k] = g;
+                at = ((at + 15u) & ~15u) + ((uint32_t)g & 15u);          // same 16-byte phase as the global address
+                ioff[k] = at;
+                at += cnt[k] * width;
+            }
+        }
+        __syncthreads();
+        if (tid < nr) rowdst[tid] = ioff[d] + (j - minpos[d]) * width;
+        __syncthreads();
+        // rows -> image (shared to shared), NP rows per warp step
+#pragma unroll 2
+        for (uint32_t k = 0; k < 32; k += NP) {
+            const uint32_t r = w * 32 + k + sg;
+            if (r < nr) {
+                uint8_t* D = img + rowdst[r];
+                const uint32_t so = r * width;
+                uint32_t head = (4u - (rowdst[r] & 3u)) & 3u;
+                head = head < width ? head : width;
+                if (sl < head) D[sl] = in[so + sl];
+                const uint32_t nwords = (width - head) >> 2;
+                uint32_t* Dw = reinterpret_cast<uint32_t*>(D + head);
+                for (uint32_t q = sl; q < nwords; q += SUB) {
+                    const uint32_t b = so + head + 4u * q;
+                    Dw[q] = __funnelshift_r(in32[b >> 2], in32[(b >> 2) + 1], (b & 3u) * 8u);
+                }
+                const uint32_t fin = head + 4u * nwords;
+                if (sl < width - fin) D[fin + sl] = in[so + fin + sl];
+            }
+        }
+        __syncthreads();
+        // image runs -> global
+        for (uint32_t k = 0; k < segs.n; k++) {
+            if (!cnt[k]) continue;
+            const uint32_t i0 = ioff[k], i1 = i0 + cnt[k] * width;
+            const uint32_t a = (i0 + 15u) & ~15u, b = i1 & ~15u;
+            uint8_t* G = reinterpret_cast<uint8_t*>((uintptr_t)gaddr[k]) - i0;     // image offset x <-> G + x
+            if (a <= b) {
+                for (uint32_t x = a + 16u * tid; x < b; x += 16u * SR_THREADS)
+                    *reinterpret_cast<uint4*>(G + x) = *reinterpret_cast<const uint4*>(img + x);
+                if (tid < a - i0) G[i0 + tid] = img[i0 + tid];
+                if (tid < i1 - b) G[b + tid] = img[b + tid];
+            } else {
+                for (uint32_t x = i0 + tid; x < i1; x += SR_THREADS) G[x] = img[x];
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(SR_THREADS) k_scatter_items_by_pos(const T* __restrict__ in, uint64_t n, const uint32_t* __restrict__ pos,
                                                                     pp_segs segs, uint8_t* __restrict__ out) {
@@ -233,6 +322,29 @@ static int scatter_rows_impl(uqb_ctx* ctx, const uqb_array* table, const uqb_arr
     } else if (w == 1) {
         UQB_LAUNCH_B(ab, k_scatter_items_by_pos<uint8_t>, uqb_grid(ctx, n, SR_THREADS, 8), SR_THREADS, 0, (const uint8_t*)table->d, n, (const uint32_t*)pos->d, S, o);
     } else {
+        static const bool by_rows = [] { const char* e = getenv("UQB_SCATTER_ROWS"); return e && e[0] == '1'; }();
+        if (!by_rows) {
+            // contiguous runs per destination, regrouped in shared memory
+            const size_t in_bytes = ((size_t)SR_THREADS * w + 32 + 15) & ~(size_t)15;
+            const size_t smem = in_bytes + (size_t)SR_THREADS * w + 32 * (size_t)S.n + 64;
+            const unsigned per_sm = (unsigned)(200 * 1024 / (smem + 5 * 1024)) ? (unsigned)(200 * 1024 / (smem + 5 * 1024)) : 1u;
+            const uint64_t ntiles = (n + SR_THREADS - 1) / SR_THREADS, cap = (uint64_t)ctx->sm_count * (per_sm > 8 ? 8 : per_sm);
+            const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+            if (w <= 32) {
+                auto k_scatter_rows_runs_8 = k_scatter_rows_runs<8>;
+                UQB_CUDA(cudaFuncSetAttribute(k_scatter_rows_runs_8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                UQB_LAUNCH_B(ab, k_scatter_rows_runs_8, grid, SR_THREADS, smem, (const uint8_t*)table->d, n, w, (const uint32_t*)pos->d, S, o);
+            } else if (w <= 64) {
+                auto k_scatter_rows_runs_16 = k_scatter_rows_runs<16>;
+                UQB_CUDA(cudaFuncSetAttribute(k_scatter_rows_runs_16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                UQB_LAUNCH_B(ab, k_scatter_rows_runs_16, grid, SR_THREADS, smem, (const uint8_t*)table->d, n, w, (const uint32_t*)pos->d, S, o);
+            } else {
+                auto k_scatter_rows_runs_32 = k_scatter_rows_runs<32>;
+                UQB_CUDA(cudaFuncSetAttribute(k_scatter_rows_runs_32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                UQB_LAUNCH_B(ab, k_scatter_rows_runs_32, grid, SR_THREADS, smem, (const uint8_t*)table->d, n, w, (const uint32_t*)pos->d, S, o);
+            }
+            return 0;
+        }
         const size_t smem = (size_t)SR_THREADS * w + 32;
         const unsigned per_sm = (unsigned)(200 * 1024 / (smem + 3 * 1024)) ? (unsigned)(200 * 1024 / (smem + 3 * 1024)) : 1u;
         const uint64_t ntiles = (n + SR_THREADS - 1) / SR_THREADS, cap = (uint64_t)ctx->sm_count * (per_sm > 8 ? 8 : per_sm);

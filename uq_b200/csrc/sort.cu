@@ -188,7 +188,15 @@ __global__ void __launch_bounds__(ST) k_group_lcp(const uint8_t* __restrict__ ro
                 }
             }
         }
-        if (live && mine != GLCP_EQUAL) atomicMin(&glcp[g], mine);
+        // one atomic per warp when its rows share a group (a giant group would otherwise serialise millions of them), and
+        // none when the group's value is already as small
+        const uint32_t g0 = __shfl_sync(0xffffffffu, g, __ffs((int)todo) - 1);
+        if (__all_sync(0xffffffffu, !live || g == g0)) {
+            const uint32_t m = __reduce_min_sync(0xffffffffu, live ? mine : GLCP_EQUAL);
+            if (lane == 0 && m != GLCP_EQUAL && m < *((volatile uint32_t*)&glcp[g0])) atomicMin(&glcp[g0], m);
+        } else if (live && mine != GLCP_EQUAL && mine < *((volatile uint32_t*)&glcp[g])) {
+            atomicMin(&glcp[g], mine);
+        }
     }
 }
 
