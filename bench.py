@@ -168,6 +168,20 @@ def run_ours(args):
                 slot = int(1.3 * n * 128)
                 comm.window = multigpu.open_peer_window(dist, "cuda:%d" % local_rank, tstream, 3 * slot, slots=3)
                 exchange = "peer window (symmetric memory, %d x %.1f GB per rank): rows stored into the receivers' memory by uqb_scatter_rows_to" % (3, slot / 1e9)
+                # measured at N=2 (profiles/README.md): running the exchange on a side stream next to the sort of the previous
+                # table gains nothing - the stores compete with the sort for the memory system (183.6 / 187.3 ms against
+                # 182.3 ms serial) and the copy engines move peer data too slowly (187.8 ms) - so both stay opt-in
+                side = os.environ.get("UQB_MG_SIDE", "0")
+                if side == "dma":
+                    comm.side = torch.cuda.Stream(device=local_rank, priority=-1)
+                    comm.exchange_mode = "dma"
+                    exchange = ("peer window (symmetric memory, %d x %.1f GB per rank): rows grouped by destination in local HBM "
+                                "(uqb_scatter_rows_segmented), segments pushed into the receivers' memory by the copy engines on a "
+                                "side stream, under the sort of the previous table" % (3, slot / 1e9))
+                elif side == "stores":
+                    comm.side = torch.cuda.Stream(device=local_rank, priority=-1)
+                    comm.side_ctas = int(os.environ.get("UQB_MG_SIDE_CTAS", "2"))
+                    exchange += "; on a side stream (%d CTAs per SM) next to the partition / sort of the neighbouring tables" % comm.side_ctas
             except Exception as e:                       # no peer mapping on this box: NCCL all-to-all
                 comm.window = None
                 exchange = "nccl all_to_all (peer window unavailable: %s)" % str(e).splitlines()[0][:120]

@@ -38,6 +38,11 @@ int         uqb_version(void);
  * on it so that callers can time the path with events recorded on the same stream. */
 int         uqb_ctx_create(int device, void* stream, uqb_ctx** out);
 void        uqb_ctx_destroy(uqb_ctx* ctx);
+/* launches that follow go to `stream` (a cudaStream_t) instead; *previous receives the stream that was installed.
+ * Used for the side stream of a multi-GPU row exchange that runs next to the sort of the previous table: the caller
+ * orders the streams with its own events and keeps the arrays of the side-stream work alive until they are joined.
+ * max_ctas_per_sm > 0 caps the grid of the row-exchange kernels (NVLink bound) while the side stream is installed. */
+int         uqb_ctx_swap_stream(uqb_ctx* ctx, void* stream, uint32_t max_ctas_per_sm, void** previous);
 const char* uqb_last_error(const uqb_ctx* ctx);
 int         uqb_ctx_sync(uqb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */

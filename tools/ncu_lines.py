@@ -35,9 +35,13 @@ if lines is None:
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kregex, "--launch-skip", skip,
                       "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
-h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr = rows[h]
-body = [r for r in rows[h + 1:] if len(r) == len(hdr)]
+# the page holds one section per matching launch (the filters are not applied to an imported report): keep the
+# heaviest section
+heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+hdr = rows[heads[0]]
+ci = hdr.index("Instructions Executed")
+sections = [[r for r in rows[a + 1:b] if len(r) == len(hdr)] for a, b in zip(heads, heads[1:] + [len(rows)])]
+body = max(sections, key=lambda sec: sum(int(r[ci] or 0) for r in sec))
 ci, cs, cn = hdr.index("Instructions Executed"), hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Warp Stall Sampling (Not-issued Samples)")
 if len(body) != len(lines):
     print("warning: %d SASS rows in the report vs %d in the cubin (rebuilt since the capture?)" % (len(body), len(lines)), file=sys.stderr)

@@ -76,6 +76,7 @@ SIGNATURES = {
     "uqb_version": (C.c_int, []),
     "uqb_ctx_create": (C.c_int, [C.c_int, P, PP]),
     "uqb_ctx_destroy": (None, [P]),
+    "uqb_ctx_swap_stream": (C.c_int, [P, P, C.c_uint32, PP]),
     "uqb_last_error": (C.c_char_p, [P]),
     "uqb_ctx_sync": (C.c_int, [P]),
     "uqb_ctx_launch_count": (C.c_uint64, [P]),

@@ -313,14 +313,15 @@ static int scatter_rows_impl(uqb_ctx* ctx, const uqb_array* table, const uqb_arr
     if (n == 0) return 0;
     if ((reinterpret_cast<uintptr_t>(table->d) & 15u) != 0) return uqb_fail(ctx, "scatter_rows: the table must be 16-byte aligned");
     const uint64_t ab = n * (2ull * w + 4);
+    const unsigned iw = ctx->side_ctas_per_sm ? 2u * ctx->side_ctas_per_sm : 8u;      // waves of the item kernels
     if (w == 4) {
-        UQB_LAUNCH_B(ab, k_scatter_items_by_pos<uint32_t>, uqb_grid(ctx, n, SR_THREADS, 8), SR_THREADS, 0, (const uint32_t*)table->d, n, (const uint32_t*)pos->d, S, o);
+        UQB_LAUNCH_B(ab, k_scatter_items_by_pos<uint32_t>, uqb_grid(ctx, n, SR_THREADS, iw), SR_THREADS, 0, (const uint32_t*)table->d, n, (const uint32_t*)pos->d, S, o);
     } else if (w == 8) {
-        UQB_LAUNCH_B(ab, k_scatter_items_by_pos<uint64_t>, uqb_grid(ctx, n, SR_THREADS, 8), SR_THREADS, 0, (const uint64_t*)table->d, n, (const uint32_t*)pos->d, S, o);
+        UQB_LAUNCH_B(ab, k_scatter_items_by_pos<uint64_t>, uqb_grid(ctx, n, SR_THREADS, iw), SR_THREADS, 0, (const uint64_t*)table->d, n, (const uint32_t*)pos->d, S, o);
     } else if (w == 2) {
-        UQB_LAUNCH_B(ab, k_scatter_items_by_pos<uint16_t>, uqb_grid(ctx, n, SR_THREADS, 8), SR_THREADS, 0, (const uint16_t*)table->d, n, (const uint32_t*)pos->d, S, o);
+        UQB_LAUNCH_B(ab, k_scatter_items_by_pos<uint16_t>, uqb_grid(ctx, n, SR_THREADS, iw), SR_THREADS, 0, (const uint16_t*)table->d, n, (const uint32_t*)pos->d, S, o);
     } else if (w == 1) {
-        UQB_LAUNCH_B(ab, k_scatter_items_by_pos<uint8_t>, uqb_grid(ctx, n, SR_THREADS, 8), SR_THREADS, 0, (const uint8_t*)table->d, n, (const uint32_t*)pos->d, S, o);
+        UQB_LAUNCH_B(ab, k_scatter_items_by_pos<uint8_t>, uqb_grid(ctx, n, SR_THREADS, iw), SR_THREADS, 0, (const uint8_t*)table->d, n, (const uint32_t*)pos->d, S, o);
     } else {
         static const bool by_rows = [] { const char* e = getenv("UQB_SCATTER_ROWS"); return e && e[0] == '1'; }();
         if (!by_rows) {
@@ -328,7 +329,9 @@ static int scatter_rows_impl(uqb_ctx* ctx, const uqb_array* table, const uqb_arr
             const size_t in_bytes = ((size_t)SR_THREADS * w + 32 + 15) & ~(size_t)15;
             const size_t smem = in_bytes + (size_t)SR_THREADS * w + 32 * (size_t)S.n + 64;
             const unsigned per_sm = (unsigned)(200 * 1024 / (smem + 5 * 1024)) ? (unsigned)(200 * 1024 / (smem + 5 * 1024)) : 1u;
-            const uint64_t ntiles = (n + SR_THREADS - 1) / SR_THREADS, cap = (uint64_t)ctx->sm_count * (per_sm > 8 ? 8 : per_sm);
+            unsigned ctas = per_sm > 8 ? 8 : per_sm;
+            if (ctx->side_ctas_per_sm && ctas > ctx->side_ctas_per_sm) ctas = ctx->side_ctas_per_sm;
+            const uint64_t ntiles = (n + SR_THREADS - 1) / SR_THREADS, cap = (uint64_t)ctx->sm_count * ctas;
             const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
             if (w <= 32) {
                 auto k_scatter_rows_runs_8 = k_scatter_rows_runs<8>;

@@ -1,5 +1,6 @@
 """Thin object wrappers over the C ABI (include/uqb200.h).  No computation happens here: every method
 is one call into libuqb200.so; numpy is used only as host memory."""
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -49,6 +50,17 @@ class Context:
 
     def sync(self):
         self.check(self.lib.uqb_ctx_sync(self.h))
+
+    @contextlib.contextmanager
+    def on_stream(self, stream, max_ctas_per_sm=0):
+        """launches inside the block go to `stream` (raw cudaStream_t) instead of the context's stream; the caller orders
+        the two streams with events and keeps the arrays of that work alive until the streams are joined"""
+        prev = C.c_void_p()
+        self.check(self.lib.uqb_ctx_swap_stream(self.h, C.c_void_p(stream), int(max_ctas_per_sm), C.byref(prev)))
+        try:
+            yield
+        finally:
+            self.check(self.lib.uqb_ctx_swap_stream(self.h, prev, 0, None))
 
     @property
     def launches(self):

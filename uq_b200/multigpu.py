@@ -237,9 +237,10 @@ def open_peer_window(dist, device, stream, nbytes, slots=3):
     buf = symm_mem.empty(int(nbytes), dtype=torch.uint8, device=device)
     hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
 
-    def barrier():
-        if stream is not None:
-            with torch.cuda.stream(stream):
+    def barrier(on=None):
+        s = on if on is not None else stream
+        if s is not None:
+            with torch.cuda.stream(s):
                 hdl.barrier(channel=0)
         else:
             hdl.barrier(channel=0)
@@ -263,9 +264,44 @@ def _p2p_plan(comm, ctx, table, router, count_table):
 
 def _p2p_exchange(comm, ctx, table, router, send_counts, recv_counts, plan):
     base, addrs = plan
-    comm.window.barrier()                                # nobody reads what the slot held before
-    ctx.scatter_rows_to(table, router[1], send_counts, addrs)
-    return dict(p2p=True, recv=ctx.wrap(comm.window.ptrs[comm.rank] + base, sum(recv_counts), table.width))
+    recv = ctx.wrap(comm.window.ptrs[comm.rank] + base, sum(recv_counts), table.width)
+    side = getattr(comm, "side", None)
+    if side is None or comm.stream is None or _TRACE["on"]:
+        comm.window.barrier()                            # nobody reads what the slot held before
+        ctx.scatter_rows_to(table, router[1], send_counts, addrs)
+        return dict(p2p=True, recv=recv)
+    # The stores into the peers' memory are NVLink bound and need few SMs: they run on a side stream (high priority, a
+    # capped grid) next to whatever the context's stream does meanwhile - the partition of the next table, the sort of
+    # the previous one.  Both barriers of the exchange sit on the side stream; it starts after everything queued so far
+    # on the context's stream (rows and positions written, the slot's previous contents consumed), and
+    # exchange_rows_wait joins it back.  `keep`: what the side-stream kernel reads stays alive until then.
+    if comm.exchange_mode == "dma":
+        # Copy-engine form: one streaming pass groups the rows by destination in local HBM (context stream, HBM bound);
+        # the per-destination segments then leave as device-to-device copies on the side stream - no SM is involved, so
+        # the transfer runs under the sort of the previous table at full speed.
+        w = table.width
+        send_pad, soffs = ctx.scatter_rows_segmented(table, router[1], send_counts, 128)
+        src0 = send_pad.device_ptr.value or 0
+        side.wait_stream(comm.stream)
+        comm.window.barrier(side)
+        with ctx.on_stream(side.cuda_stream):
+            for k in range(comm.world):
+                d = (comm.rank + 1 + k) % comm.world         # every rank starts with another destination
+                nb = int(send_counts[d]) * w
+                if nb:
+                    view = ctx.wrap(addrs[d], nb, 1)
+                    ctx.copy_in(view, 0, src0 + int(soffs[d]), nb)
+                    view.free()
+        comm.window.barrier(side)                        # every rank's rows have landed ...
+        return dict(p2p=True, side=True, recv=recv, landed=side.record_event(), keep=(send_pad,), free_after=(send_pad,))
+    side.wait_stream(comm.stream)
+    comm.window.barrier(side)
+    with ctx.on_stream(side.cuda_stream, comm.side_ctas):
+        ctx.scatter_rows_to(table, router[1], send_counts, addrs)
+    comm.window.barrier(side)
+    # ... and the event marks that point of the side stream: the context's stream will wait for THIS exchange only, not
+    # for the next table's exchange that is queued behind it
+    return dict(p2p=True, side=True, recv=recv, landed=side.record_event(), keep=(table, router[1]))
 
 
 class Comm:
@@ -277,6 +313,9 @@ class Comm:
         never blocks around them; without it every exchange is bracketed by host synchronisations."""
         self.dist, self.device, self.stream = dist, device, stream
         self.window = None                               # PeerWindow: row exchanges as direct stores into the peers' memory
+        self.side = None                                 # torch.cuda.Stream for the peer-window stores (see _p2p_exchange)
+        self.side_ctas = 1                               # CTAs per SM of the exchange kernels on the side stream
+        self.exchange_mode = "stores"                    # "stores": uqb_scatter_rows_to; "dma": local grouping + copy engines
         self.rank = dist.get_rank() if dist else 0
         self.world = dist.get_world_size() if dist else 1
         # the small object collectives run over gloo next to NCCL: queued on the NCCL communicator they would wait
@@ -383,6 +422,12 @@ class Comm:
         return dict(work=work, send=send_pad, recv=recv_pad, roffs=roffs, recv_counts=list(recv_counts), width=w)
 
     def exchange_rows_wait(self, ctx, ex):
+        if ex.get("side"):
+            self.stream.wait_event(ex["landed"])
+            ex.pop("keep", None)
+            for a in ex.pop("free_after", ()):           # stream ordered: reused only after the join above
+                a.free()
+            return ex["recv"]
         if ex.get("p2p"):
             self.window.barrier()                        # every rank's rows have landed
             return ex["recv"]
@@ -642,6 +687,17 @@ def global_unique_end(ctx, comm, st):
     recv = st["recv"] if st["recv"] is not None else comm.exchange_rows_wait(ctx, st["ex"])
     _mark(ctx, comm, "gu.exchange_wait")
     router, send_counts, recv_counts, want_perm = st["router"], st["send_counts"], st["recv_counts"], st["want_perm"]
+    if want_perm and os.environ.get("UQB_MG_KEY_ROUNDTRIP") != "1":
+        # The sorted-on table: the records are going to follow their rows to this rank anyway (global_order), so the key of
+        # this rank's slice of the global order is the group id in SORTED order - no trip back to the record's rank and
+        # forth again.
+        perm_r, _, uniq_range, nr, key_sorted = ctx.sort_rows(recv, want_perm=True, want_uniq=True, want_key_sorted=True)
+        recv.free()
+        _mark(ctx, comm, "gu.sort")
+        counts = comm.all_gather_object(nr)
+        ctx.add_scalar_u32(key_sorted, sum(counts[:comm.rank]))
+        route = ("partition", router, send_counts, recv_counts, perm_r, st["count_table"])
+        return dict(key=None, key_sorted=key_sorted, uniq=uniq_range, n_unique=sum(counts), counts=counts, route=route)
     perm_r, key_r, uniq_range, nr = ctx.sort_rows(recv, want_perm=want_perm, want_key=True, want_uniq=True)
     recv.free()
     _mark(ctx, comm, "gu.sort")
@@ -931,6 +987,7 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
     keyed = {t: (t not in raw) for t in tables}
     uniq = {}
     payload = {}
+    in_order = {}                                   # arrays that are produced in the global order (no global_order trip)
     route = None
     for t in ('DNA', 'QUAL', 'QNAME'):
         if not keyed[t]:
@@ -947,7 +1004,10 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
             route = g['route']
         if keyed[t]:
             uniq[t] = (g['uniq'], g['n_unique'])
-            payload[t + '.key'] = g['key']
+            if g.get('key_sorted') is not None:     # already this rank's slice of the global order
+                in_order[t + '.key'] = g['key_sorted']
+            else:
+                payload[t + '.key'] = g['key']
             if t == 'QNAME':                        # unique rows back to typed columns (uq.py:842-847)
                 ucols = ctx.rows_to_columns(g['uniq'], [np.dtype(m['dtype']).itemsize for m in columns])
                 for c, meta in zip(ucols, columns):
@@ -957,7 +1017,9 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
                 add_table(t, g['uniq'], t)
         else:
             g['uniq'].free()
-            if not (t == sorted_on and route[0] == 'merge'):      # the merge route still needs the key
+            if g.get('key_sorted') is not None:
+                g['key_sorted'].free()
+            elif not (t == sorted_on and route[0] == 'merge'):      # the merge route still needs the key
                 g['key'].free()
 
     # software pipeline over the tables: while the rows of one table are on the wire (NCCL stream), the next table is
@@ -981,6 +1043,7 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
         for v in old.values():
             v.free()
         payload = moved
+    payload.update(in_order)
     # keys are narrowed to min_scalar_type(max(key)) of the WHOLE file (uq.py:790, 832)
     for t in ('DNA', 'QUAL', 'QNAME'):
         if keyed[t]:
