@@ -222,6 +222,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     launches0 = ctx.launches
+    hc0 = list(comm.host_collectives) if global_mode else None
     ctx.span_begin()
     for _ in range(args.steps):
         out_bytes, cfg = one_step()
@@ -229,6 +230,11 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop() if sampler else None
     launches = ctx.launches - launches0
+    host_coll = None
+    if global_mode:
+        host_coll = {"calls_per_step": (comm.host_collectives[0] - hc0[0]) / args.steps,
+                     "ms_per_step_rank0": round((comm.host_collectives[1] - hc0[1]) * 1e3 / args.steps, 2),
+                     "transport": "shared-memory board (one node)" if comm.board is not None else "gloo all_gather_object"}
     report = ctx.timing_report()
     ctx.timing(False)
     ms = max_over_ranks(ms)
@@ -397,7 +403,10 @@ def run_ours(args):
             line["parity_check"] = parity
         if global_mode:
             line["config"]["row_exchange"] = exchange
+            line["host_collectives"] = host_coll
         emit(line)
+    if global_mode:
+        comm.close()
     if dist is not None:
         dist.destroy_process_group()
 

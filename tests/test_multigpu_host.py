@@ -130,6 +130,42 @@ def test_object_collectives_over_gloo():
     assert recv == [0, 10]          # rank 0 receives send_counts[0] of rank 0 (=0) and of rank 1 (=10)
 
 
+def _board_worker(rank, world, port, q, use_board):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      UQB_MG_SHM="1" if use_board else "0")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = mg.Comm(dist, "cpu")
+    ok = (comm.board is not None) == use_board
+    for k in range(300):                                  # many rounds back to back: the two-slot protocol must never mix rounds
+        got = comm.all_gather_object((rank, k, b"x" * ((k * 37 + rank) % 5000)))
+        ok = ok and [g[:2] for g in got] == [(r, k) for r in range(world)] and all(len(g[2]) == (k * 37 + r) % 5000 for r, g in enumerate(got))
+    big = np.arange(400_000 + rank, dtype=np.int64)       # 3.2 MB: does not fit a slot -> the round falls back to gloo
+    got = comm.all_gather_object(big if rank == 1 else rank)
+    ok = ok and got[0] == 0 and len(got[1]) == 400_001
+    got = comm.all_gather_object({"after": rank})          # and the board is usable again afterwards
+    ok = ok and got == [{"after": r} for r in range(world)]
+    calls = comm.host_collectives[0]
+    comm.close()
+    q.put((rank, ok, calls))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_board", [True, False])
+def test_shared_memory_board_matches_gloo(use_board):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 3
+    procs = [ctx.Process(target=_board_worker, args=(r, world, port, q, use_board)) for r in range(world)]
+    for p in procs: p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs: p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    assert res == [(r, True, 302) for r in range(world)]
+
+
 # ---- partition-first sample sort: the host side of global_unique, emulated with numpy ---------------------------
 def _emu_partition(rows, split_keys):
     """contract of uqb_partition_rows: dest = number of splitter keys <= big-endian first 8 bytes; stable grouping"""
