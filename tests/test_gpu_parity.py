@@ -55,6 +55,32 @@ def test_split_empty_and_tiny(ctx):
         d.free()
 
 
+@pytest.mark.parametrize("shape", ["even", "dense_tail", "no_newline", "odd_size"])
+def test_split_single_pass_matches_numpy(ctx, shape):
+    """files of 1 MB and more take the one-pass newline scan (k_newline_scan1): its look-back numbering, the capacity
+    estimate from the head of the file, and the two-pass fallback when the tail is denser than the head"""
+    rng = np.random.default_rng(11)
+    if shape == "even":
+        data = rng.integers(0, 64, size=9_000_001, dtype=np.uint8)            # a newline every 64 bytes on average
+    elif shape == "dense_tail":
+        # 70 MB: the first 66 MB (all 4096 sampled tiles) hold few newlines, the tail is dense -> the estimate overflows
+        data = rng.integers(11, 255, size=70_000_000, dtype=np.uint8)
+        data[::5000] = 10
+        data[67_000_000:] = rng.integers(10, 12, size=3_000_000, dtype=np.uint8)      # 1.5 M newlines > the 1 M slack
+    elif shape == "no_newline":
+        data = rng.integers(11, 255, size=3_000_000, dtype=np.uint8)
+    else:
+        data = rng.integers(0, 32, size=4 * 16384 * 70 + 12345, dtype=np.uint8)
+        data[-1] = 10
+    raw = data.tobytes()
+    d = ctx.load_fastq(raw)
+    info = d.split()
+    ref = _line_offsets_ref(raw)
+    assert info.n_lines == len(ref) - 1
+    assert np.array_equal(d.line_offsets(), ref)
+    d.free()
+
+
 STAT_FIELDS = ["base_count", "qual_count", "base_single_qual", "last_count_mismatch", "first_lcp_eq", "first_lcs_eq",
                "first_short_prefix", "first_short_suffix"]
 STAT_SCALARS = ["dna_min", "dna_max", "bad_first_char", "bad_plus_record", "bad_len_record", "first_len", "last_len",

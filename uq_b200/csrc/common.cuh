@@ -115,6 +115,7 @@ int uqb_fail(uqb_ctx* ctx, const char* fmt, ...);
 int uqb_dalloc(uqb_ctx* ctx, void** p, size_t nbytes);            // stream-ordered
 int uqb_dfree(uqb_ctx* ctx, void* p, size_t nbytes);
 int uqb_new_array(uqb_ctx* ctx, uint64_t n, uint32_t width, uqb_array** out);
+int uqb_adopt_array(uqb_ctx* ctx, void* d, uint64_t n, uint32_t width, uqb_array** out);   // d: arena block of >= n * width + 64 bytes
 int uqb_pinned(uqb_ctx* ctx, size_t nbytes, void** out);          // ctx-owned scratch, grows
 int uqb_readback(uqb_ctx* ctx, void* host, const void* dev, size_t nbytes);   // D2H + sync
 
@@ -212,4 +213,5 @@ int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux, cons
 
 // rows (sort.cu)
 int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t width,
-                       uint32_t** d_perm, uint32_t** d_gid_sorted, uint64_t* n_unique, const uint64_t* key0 = nullptr);
+                       uint32_t** d_perm, uint32_t** d_gid_sorted, uint64_t* n_unique, const uint64_t* key0 = nullptr,
+                       uint64_t** sorted_keys = nullptr);

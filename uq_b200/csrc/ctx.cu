@@ -334,6 +334,18 @@ int uqb_new_array(uqb_ctx* ctx, uint64_t n, uint32_t width, uqb_array** out) {
     return 0;
 }
 
+// an arena block (at least n * width + 64 bytes) becomes an owned array
+int uqb_adopt_array(uqb_ctx* ctx, void* d, uint64_t n, uint32_t width, uqb_array** out) {
+    uqb_array* a = new (std::nothrow) uqb_array();
+    if (!a) return uqb_fail(ctx, "out of host memory");
+    a->n = n;
+    a->width = width;
+    a->owned = true;
+    a->d = d;
+    *out = a;
+    return 0;
+}
+
 int uqb_pinned(uqb_ctx* ctx, size_t nbytes, void** out) {
     if (ctx->pinned_bytes < nbytes) {
         if (ctx->pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }

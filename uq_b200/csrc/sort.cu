@@ -632,13 +632,17 @@ __global__ void __launch_bounds__(ST) k_iota_zero(uint32_t* __restrict__ perm, u
     gid[p] = 0;
 }
 
+// d_perm / d_gid_sorted: arena blocks of n + 16 words (the callers turn them into arrays without a copy).
+// sorted_keys (optional): for rows of up to 8 bytes the sorted round-0 keys ARE the sorted rows (big-endian, zero padded);
+// the buffer is handed over instead of being freed, and the unique table is cut out of it without touching the rows.
 int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t width,
-                       uint32_t** d_perm, uint32_t** d_gid_sorted, uint64_t* n_unique, const uint64_t* key0) {
+                       uint32_t** d_perm, uint32_t** d_gid_sorted, uint64_t* n_unique, const uint64_t* key0, uint64_t** sorted_keys) {
     *d_perm = nullptr; *d_gid_sorted = nullptr; *n_unique = 0;
+    if (sorted_keys) *sorted_keys = nullptr;
     if (n >= (1ull << 32)) return uqb_fail(ctx, "sort_rows: %llu rows exceed the 32-bit index range", (unsigned long long)n);
-    uint32_t *perm, *head, *excl;
-    UQB_TRY(uqb_dalloc_t(ctx, &perm, n));
-    UQB_TRY(uqb_dalloc_t(ctx, &excl, n));
+    uint32_t *perm = nullptr, *head, *excl;
+    UQB_TRY(uqb_dalloc_t(ctx, &excl, n + 16));
+    if (n == 0 || width == 0) UQB_TRY(uqb_dalloc_t(ctx, &perm, n + 16));
     if (n == 0) { *d_perm = perm; *d_gid_sorted = excl; return 0; }
     const unsigned nb = uqb_blocks(n, ST);
     if (width == 0) {
@@ -664,7 +668,9 @@ int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t w
         else if (!kf) UQB_LAUNCH_B(n * ((width < 8 ? width : 8) + 12), k_chunk0_keys, nb, ST, 0, rows, n, width, sb.key[0], sb.val[0]);
         UQB_TRY(uqb_radix_sort(ctx, &sb, n, zoff != nullptr, kf));
         UQB_LAUNCH(k_mark_heads, nb, ST, 0, sb.key[sb.cur], zoff ? sb.aux[sb.cur] : (const uint32_t*)nullptr, n, head);
-        UQB_CUDA(cudaMemcpyAsync(perm, sb.val[sb.cur], n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        perm = sb.val[sb.cur];                                 // the sorted values are the permutation: the buffer is kept
+        sb.val[sb.cur] = nullptr;
+        if (sorted_keys && width <= 8 && !zoff) { *sorted_keys = sb.key[sb.cur]; sb.key[sb.cur] = nullptr; }
         UQB_TRY(uqb_sortbuf_free(ctx, &sb));
     }
     // ---- refinement ----
@@ -839,6 +845,19 @@ __global__ void __launch_bounds__(ST) k_first_of_group(const uint32_t* __restric
     if (p == 0 || gid[p] != gid[p - 1]) first_row[gid[p]] = perm[p];
 }
 
+// rows of up to 8 bytes: unique row g = the leading `width` bytes of the (big-endian) sorted key at the first position of
+// group g.  Sequential reads, stores that advance with the positions.
+__global__ void __launch_bounds__(ST) k_uniq_from_keys(const uint64_t* __restrict__ skey, const uint32_t* __restrict__ gid, uint64_t n,
+                                                      uint32_t width, uint8_t* __restrict__ out) {
+    for (uint64_t p = (uint64_t)blockIdx.x * ST + threadIdx.x; p < n; p += (uint64_t)gridDim.x * ST) {
+        const uint32_t g = gid[p];
+        if (p && gid[p - 1] == g) continue;
+        const uint64_t k = skey[p];
+        uint8_t* o = out + (uint64_t)g * width;
+        for (uint32_t b = 0; b < width; b++) o[b] = (uint8_t)(k >> (56 - 8 * b));
+    }
+}
+
 // out[i][:] = table[idx[i]][:]; one warp per row: the index is read once per row, the row bytes are
 // contiguous loads and the output rows are contiguous stores
 __global__ void __launch_bounds__(ST) k_gather_rows(const uint8_t* __restrict__ table, uint32_t width, const uint32_t* __restrict__ idx,
@@ -955,7 +974,8 @@ extern "C" int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** p
     uint32_t *d_perm, *d_gid;
     uint64_t u = 0;
     const uint64_t n = table->n;
-    UQB_TRY(uqb_sort_rows_impl(ctx, (const uint8_t*)table->d, n, table->width, &d_perm, &d_gid, &u, table->key0));
+    uint64_t* skeys = nullptr;
+    UQB_TRY(uqb_sort_rows_impl(ctx, (const uint8_t*)table->d, n, table->width, &d_perm, &d_gid, &u, table->key0, uniq ? &skeys : nullptr));
     if (n_unique) *n_unique = u;
     const unsigned nb = uqb_blocks(n, ST);
     if (key) {
@@ -964,7 +984,10 @@ extern "C" int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** p
     }
     if (uniq) {
         UQB_TRY(uqb_new_array(ctx, u, table->width, uniq));
-        if (n && table->width) {
+        if (skeys) {
+            UQB_LAUNCH_B(n * 12 + u * table->width, k_uniq_from_keys, uqb_grid(ctx, n, ST, 16), ST, 0, skeys, d_gid, n, table->width, (uint8_t*)(*uniq)->d);
+            UQB_TRY(uqb_dfree(ctx, skeys, n * 8));
+        } else if (n && table->width) {
             uint32_t* first_row;
             UQB_TRY(uqb_dalloc_t(ctx, &first_row, u));
             UQB_LAUNCH(k_first_of_group, nb, ST, 0, d_perm, d_gid, n, first_row);
@@ -972,16 +995,11 @@ extern "C" int uqb_sort_rows(uqb_ctx* ctx, const uqb_array* table, uqb_array** p
             UQB_TRY(uqb_dfree(ctx, first_row, u * 4));
         }
     }
-    if (key_sorted) {
-        UQB_TRY(uqb_new_array(ctx, n, 4, key_sorted));
-        if (n) UQB_CUDA(cudaMemcpyAsync((*key_sorted)->d, d_gid, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    if (perm) {
-        UQB_TRY(uqb_new_array(ctx, n, 4, perm));
-        if (n) UQB_CUDA(cudaMemcpyAsync((*perm)->d, d_perm, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    UQB_TRY(uqb_dfree(ctx, d_perm, n * 4));
-    UQB_TRY(uqb_dfree(ctx, d_gid, n * 4));
+    // the two work arrays become the results (no copies)
+    if (key_sorted) UQB_TRY(uqb_adopt_array(ctx, d_gid, n, 4, key_sorted));
+    else UQB_TRY(uqb_dfree(ctx, d_gid, n * 4));
+    if (perm) UQB_TRY(uqb_adopt_array(ctx, d_perm, n, 4, perm));
+    else UQB_TRY(uqb_dfree(ctx, d_perm, n * 4));
     return 0;
 }
 
