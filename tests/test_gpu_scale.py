@@ -32,6 +32,23 @@ def _dec(cfg, st):
     return d
 
 
+def test_scatter_u32_through_l2_windows(ctx):
+    """out[idx[j]] = src[j] above 25 M items goes through the window-regrouped scatter (k_pairs_hist / k_pairs_regroup /
+    k_pairs_apply, the kernels behind every `.key` member of the 100 M-read encode): 30 M items over four 32 MB windows"""
+    n = 30_000_007
+    rng = np.random.default_rng(5)
+    idx = rng.permutation(n).astype(np.uint32)
+    src = rng.integers(0, 1 << 32, size=n, dtype=np.uint32)
+    d_idx, d_src = ctx.upload(idx), ctx.upload(src)
+    out = ctx.scatter_u32(d_src, d_idx)
+    got = out.download(np.uint32)
+    want = np.empty(n, np.uint32)
+    want[idx] = src
+    assert np.array_equal(got, want)
+    for a in (d_idx, d_src, out):
+        a.free()
+
+
 def test_config1_shape_tables_equal_closed_form(ctx):
     """1 M x 100 bp, raw tables: packed DNA / QUAL rows bit-exact vs the vectorised oracle."""
     from oracle import uq_vec as vec

@@ -210,6 +210,8 @@ int uqb_sortbuf_alloc(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool with_aux);
 int uqb_sortbuf_free(uqb_ctx* ctx, uqb_sortbuf* sb);
 // key_first != nullptr: the input of the first pass is (key_first[i], i) - buffer 0 of sb is scratch then
 int uqb_radix_sort(uqb_ctx* ctx, uqb_sortbuf* sb, uint64_t n, bool use_aux, const uint64_t* key_first = nullptr);
+// out[idx[p]] = val[p] through destination windows that fit the L2 (idx: a permutation of 0..n-1)
+int uqb_scatter_pairs_u32(uqb_ctx* ctx, const uint32_t* idx, const uint32_t* val, uint64_t n, uint32_t* out);
 
 // rows (sort.cu)
 int uqb_sort_rows_impl(uqb_ctx* ctx, const uint8_t* rows, uint64_t n, uint32_t width,

@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_units(const uint8_t
 // quality counters reach about 200 between two flushes.
 #define H3_STAGES 3
 struct h3_smem {
+    alignas(128) uint8_t front_pad[128];                      // the name copy reads the word in front of a tile's first byte
     alignas(128) uint8_t bytes[H3_STAGES][TL_CAP + 32];
     uint32_t loff[H3_STAGES][4 * TL_R + 4];
     alignas(8) uint64_t full[H3_STAGES];
@@ -420,18 +421,20 @@ __global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_pipe(const uint8_t*
     // issues the bulk copy.  full[s] therefore takes one arrival per warp plus the copy's transaction count.
     constexpr uint32_t OPW = (4 * TL_R + 1 + H2_THREADS / 32 - 1) / (H2_THREADS / 32);        // offsets per warp: 17
     uint64_t pend_off = 0, pend_b0 = 0, pend_b1 = 0;      // loads in flight for the tile that is being prepared
-    auto tile_first = [&](uint32_t k) { return r_begin + ((uint64_t)blockIdx.x + (uint64_t)k * gridDim.x) * TL_R; };
-    auto tile_nrec = [&](uint32_t k) { const uint64_t r0 = tile_first(k); return (uint32_t)(n_reads - r0 < TL_R ? n_reads - r0 : TL_R); };
-    auto prep_load = [&](uint32_t k) {                    // start the loads for tile k
-        const uint64_t* lo = line_off + 4 * tile_first(k);
-        const uint32_t nrec = tile_nrec(k), i = wid * OPW + lane;
-        if (lane < OPW && i <= 4 * nrec) pend_off = __ldg(lo + i);
+    // tile k of this CTA starts at record r_begin + (blockIdx.x + k * gridDim.x) * TL_R; the loop below carries that record
+    // number, the buffer index k % 3 and the barrier parity (k / 3) & 1 along instead of recomputing them per call
+    const uint64_t rstride = (uint64_t)gridDim.x * TL_R;
+    const uint32_t my_off = wid * OPW + lane;
+    auto nrec_at = [&](uint64_t r0) { return (uint32_t)(n_reads - r0 < TL_R ? n_reads - r0 : TL_R); };
+    auto prep_load = [&](uint64_t r0, uint32_t nrec) {    // start the loads for the tile at r0
+        const uint64_t* lo = line_off + 4 * r0;
+        if (lane < OPW && my_off <= 4 * nrec) pend_off = __ldg(lo + my_off);
         if (producer && lane == 0) { pend_b0 = __ldg(lo); pend_b1 = __ldg(lo + 4 * nrec); }
     };
-    auto prep_store = [&](uint32_t k) {                   // finish them: offsets into the buffer, bulk copy, arrivals
-        const uint32_t st = k % H3_STAGES;
-        if (k >= H3_STAGES) mbar_wait(&S->empty[st], ((k / H3_STAGES) - 1u) & 1u);        // every warp has left the previous tile of this buffer
-        const uint32_t nrec = tile_nrec(k), i = wid * OPW + lane;
+    // finish them: offsets into buffer st, bulk copy, arrivals.  wait_empty: the buffer held an earlier tile (parity given)
+    auto prep_store = [&](uint32_t nrec, uint32_t st, bool wait_empty, uint32_t empty_par) {
+        if (wait_empty) mbar_wait(&S->empty[st], empty_par);                              // every warp has left the previous tile of this buffer
+        const uint32_t i = my_off;
         if (lane < OPW && i <= 4 * nrec) S->loff[st][i] = (uint32_t)pend_off;
         if (producer) {
             const uint64_t b0 = __shfl_sync(0xffffffffu, pend_b0, 0), b1 = __shfl_sync(0xffffffffu, pend_b1, 0);
@@ -456,32 +459,44 @@ __global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_pipe(const uint8_t*
         }
     };
 
-    for (uint32_t k = 0; k < K && k < H3_STAGES - 1; k++) { prep_load(k); prep_store(k); }
+    {
+        uint64_t r0p = r_begin + (uint64_t)blockIdx.x * TL_R;
+        for (uint32_t k = 0; k < K && k < H3_STAGES - 1; k++, r0p += rstride) { const uint32_t nr = nrec_at(r0p); prep_load(r0p, nr); prep_store(nr, k, false, 0u); }
+    }
     uint32_t F = 1, next_flush = 1;
+    uint64_t r0 = r_begin + (uint64_t)blockIdx.x * TL_R;   // first record of tile k
+    uint32_t st = 0, par = 0;                              // k % 3, (k / 3) & 1
     for (uint32_t k = 0; k < K; k++) {
-        const uint32_t st = k % H3_STAGES;
         const bool ahead = k + H3_STAGES - 1 < K;
-        if (ahead) prep_load(k + H3_STAGES - 1);
-        mbar_wait(&S->full[st], (k / H3_STAGES) & 1u);
-        const uint64_t r0 = tile_first(k);
-        const uint32_t nrec = tile_nrec(k);
-        if (S->ok[st] && names) {                      // every thread, whatever its own line: 8 lanes copy one name
+        // tile k + 2: buffer (st + 2) % 3; it follows tile k - 1 there, whose round was (k - 1) / 3
+        const uint64_t r0a = r0 + 2 * rstride;
+        const uint32_t nrec_a = ahead ? nrec_at(r0a) : 0u;
+        const uint32_t st_a = st ? st - 1u : 2u;
+        const uint32_t par_a = st ? par : par ^ 1u;        // parity of round (k - 1) / 3
+        if (ahead) prep_load(r0a, nrec_a);
+        mbar_wait(&S->full[st], par);
+        const uint32_t nrec = nrec_at(r0);
+        if (S->ok[st] && names && wid < TL_R / 8) {        // warps 0..15: four lanes copy one name, 16 bytes each
             const uint32_t bytes_a = smem_u32(S->bytes[st]);
             const uint32_t* loff = S->loff[st];
             const uint32_t base32 = loff[0] & ~15u;
-            const uint32_t nr = 4u * wid + (lane >> 3), sl = lane & 7u;
+            const uint32_t nr = 8u * wid + (lane >> 2);
             if (nr < nrec) {
                 const uint32_t n0 = loff[4 * nr] - base32, nlen = loff[4 * nr + 1] - base32 - n0 - 1u;
                 if (nlen + 1u > name_pitch || nlen > 255u) {
-                    if (sl == 0) atomicOr(&S->C.oor, 2u);
+                    if ((lane & 3u) == 0) atomicOr(&S->C.oor, 2u);
                 } else {
-                    uint32_t* dst = reinterpret_cast<uint32_t*>(names + (r0 + nr) * name_pitch);
-                    const uint32_t nwords = (nlen + 4u) >> 2;                  // words that hold the length byte and the text
-                    for (uint32_t q = sl; q < nwords; q += 8) {
-                        // image bytes 4 q .. 4 q + 3: byte 0 is the length, byte b > 0 is text byte b - 1
-                        const uint32_t at = n0 + (q ? 4u * q - 1u : 0u), al = bytes_a + (at & ~3u);
-                        const uint32_t x = __funnelshift_r(lds_u32(al), lds_u32(al + 4u), (at & 3u) * 8u);
-                        dst[q] = q ? x : ((x << 8) | nlen);
+                    uint4* dst = reinterpret_cast<uint4*>(names + (r0 + nr) * name_pitch);
+                    // image byte 0 is the length, byte b > 0 is text byte b - 1: chunk c = image bytes 16 c .. 16 c + 15 starts one
+                    // byte in front of text byte 16 c (for c = 0 that is the byte before the name, replaced by the length)
+                    for (uint32_t c = lane & 3u; 16u * c <= nlen; c += 4) {
+                        const uint32_t at = n0 + 16u * c - 1u, al = bytes_a + (at & ~3u), sh = (at & 3u) * 8u;
+                        const uint32_t x0 = lds_u32(al), x1 = lds_u32(al + 4u), x2 = lds_u32(al + 8u), x3 = lds_u32(al + 12u), x4 = lds_u32(al + 16u);
+                        uint4 v;
+                        v.x = __funnelshift_r(x0, x1, sh); v.y = __funnelshift_r(x1, x2, sh);
+                        v.z = __funnelshift_r(x2, x3, sh); v.w = __funnelshift_r(x3, x4, sh);
+                        if (c == 0) v.x = (v.x & 0xFFFFFF00u) | nlen;
+                        dst[c] = v;
                     }
                 }
             }
@@ -520,7 +535,9 @@ __global__ void __launch_bounds__(H2_THREADS, 1) k_pair_hist_pipe(const uint8_t*
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&S->empty[st]);
-        if (ahead) prep_store(k + H3_STAGES - 1);
+        if (ahead) prep_store(nrec_a, st_a, k >= 1, par_a);
+        r0 += rstride;
+        if (++st == H3_STAGES) { st = 0; par ^= 1u; }
         if (k + 1 == next_flush || k + 1 == K) {
             // ---- the CTA meets: counter columns -> CTA histograms, hints ----
             const unsigned wq = __reduce_max_sync(0xffffffffu, isq ? qsym : 0u);

@@ -295,6 +295,142 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const uint64_t*
     }
 }
 
+// ---- out[idx[p]] = val[p] for arrays much larger than the L2 --------------------------------------
+// A plain scatter of 4-byte items over 400 MB costs a sector fill and a write-back per element.  Here the (idx, val) pairs
+// are first grouped by destination WINDOW (idx >> wshift: 32 MB of `out` per window) with one counting pass and one
+// regrouping pass (tile-local order inside a window is free: idx is a permutation, no two pairs meet), then applied in
+// that order: the stores of a window meet in the L2 and leave as full lines.  Three sequential sweeps over 8 bytes per
+// pair instead of one sweep per window.
+#define PW_THREADS 512
+#define PW_ITEMS (PR_TILE / PW_THREADS)
+
+__global__ void __launch_bounds__(PW_THREADS) k_pairs_hist(const uint32_t* __restrict__ idx, uint64_t n, uint32_t wshift, uint32_t nwin,
+                                                          uint32_t* __restrict__ ghist, uint32_t nblk) {
+    __shared__ uint32_t hist[256];
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t tile0 = (uint64_t)blockIdx.x * PR_TILE;
+#pragma unroll
+    for (int j = 0; j < PW_ITEMS; j++) {
+        const uint64_t i = tile0 + (uint64_t)j * PW_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&hist[__ldg(idx + i) >> wshift], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < nwin) ghist[(uint64_t)threadIdx.x * nblk + blockIdx.x] = hist[threadIdx.x];
+}
+
+struct pw_stage {
+    uint32_t cnt[256], dstart[256], gbase[256], wtot[8];
+    uint32_t idx[PR_TILE], val[PR_TILE];
+};
+
+__global__ void __launch_bounds__(PW_THREADS) k_pairs_regroup(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ val, uint64_t n,
+                                                             uint32_t wshift, uint32_t nwin, const uint32_t* __restrict__ goff, uint32_t nblk,
+                                                             uint32_t* __restrict__ idx_out, uint32_t* __restrict__ val_out) {
+    extern __shared__ __align__(16) uint8_t pw_raw[];
+    pw_stage* S = reinterpret_cast<pw_stage*>(pw_raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    if (tid < 256) S->cnt[tid] = 0;
+    __syncthreads();
+    const uint64_t tile0 = (uint64_t)blockIdx.x * PR_TILE;
+    const uint32_t ntile = (uint32_t)((n - tile0 < PR_TILE) ? (n - tile0) : PR_TILE);
+    uint32_t ix[PW_ITEMS], vx[PW_ITEMS], rk[PW_ITEMS];
+#pragma unroll
+    for (int j = 0; j < PW_ITEMS; j++) {
+        const uint64_t i = tile0 + (uint64_t)j * PW_THREADS + tid;
+        ix[j] = 0; vx[j] = 0; rk[j] = 0;
+        if (i < n) { ix[j] = __ldg(idx + i); vx[j] = __ldg(val + i); }
+    }
+#pragma unroll
+    for (int j = 0; j < PW_ITEMS; j++) {
+        const uint64_t i = tile0 + (uint64_t)j * PW_THREADS + tid;
+        // warp-aggregated: the lanes of one window take consecutive places behind one shared-memory atomic
+        const uint32_t d = i < n ? (ix[j] >> wshift) : 0xFFFFFFFFu;
+        const unsigned m = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (i < n && (int)lane == leader) base = atomicAdd(&S->cnt[d], (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        rk[j] = base + __popc(m & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    uint32_t tot = 0, incl = 0;
+    if (tid < 256) {
+        tot = tid < nwin ? S->cnt[tid] : 0u;
+        incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) S->wtot[w] = incl;
+    }
+    __syncthreads();
+    if (tid < 256) {
+        uint32_t wb = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) if ((unsigned)i < w) wb += S->wtot[i];
+        const uint32_t start = wb + incl - tot;
+        S->dstart[tid] = start;
+        if (tid < nwin) S->gbase[tid] = goff[(uint64_t)tid * nblk + blockIdx.x] - start;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PW_ITEMS; j++) {
+        const uint64_t i = tile0 + (uint64_t)j * PW_THREADS + tid;
+        if (i < n) {
+            const uint32_t slot = S->dstart[ix[j] >> wshift] + rk[j];
+            S->idx[slot] = ix[j];
+            S->val[slot] = vx[j];
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < ntile; i += PW_THREADS) {
+        const uint32_t x = S->idx[i];
+        const uint32_t pos = S->gbase[x >> wshift] + i;
+        idx_out[pos] = x;
+        val_out[pos] = S->val[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pairs_apply(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ val, uint64_t n,
+                                                    uint32_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * 256 * 4;
+    for (uint64_t p0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 4; p0 < n; p0 += stride) {
+        if (p0 + 4 <= n) {
+            const uint4 d = __ldg(reinterpret_cast<const uint4*>(idx + p0));
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(val + p0));
+            out[d.x] = v.x; out[d.y] = v.y; out[d.z] = v.z; out[d.w] = v.w;
+        } else {
+            for (uint64_t p = p0; p < n; p++) out[idx[p]] = val[p];
+        }
+    }
+}
+
+// out[idx[p]] = val[p]; idx must be a permutation of 0..n-1 (n < 2^32).  Small arrays are scattered directly.
+int uqb_scatter_pairs_u32(uqb_ctx* ctx, const uint32_t* idx, const uint32_t* val, uint64_t n, uint32_t* out) {
+    if (n == 0) return 0;
+    static const uint32_t wshift0 = [] { const char* e = getenv("UQB_PAIR_WSHIFT"); return e ? (uint32_t)atoi(e) : 23u; }();
+    uint32_t wshift = wshift0;                                     // 2^23 entries = 32 MB of `out` per window
+    while (((n + (1ull << wshift) - 1) >> wshift) > 256) wshift++;
+    const uint32_t nwin = (uint32_t)((n + (1ull << wshift) - 1) >> wshift);
+    const uint32_t nblk = (uint32_t)((n + PR_TILE - 1) / PR_TILE);
+    uint32_t *ghist, *idx2, *val2;
+    const uint64_t hist_n = (uint64_t)nwin * nblk;
+    UQB_TRY(uqb_dalloc_t(ctx, &ghist, hist_n));
+    UQB_TRY(uqb_dalloc_t(ctx, &idx2, n + 16));
+    UQB_TRY(uqb_dalloc_t(ctx, &val2, n + 16));
+    UQB_LAUNCH_B(n * 4, k_pairs_hist, nblk, PW_THREADS, 0, idx, n, wshift, nwin, ghist, nblk);
+    UQB_TRY(uqb_scan_u32(ctx, ghist, ghist, hist_n, nullptr));
+    UQB_CUDA(cudaFuncSetAttribute(k_pairs_regroup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pw_stage)));
+    UQB_LAUNCH_B(n * 16, k_pairs_regroup, nblk, PW_THREADS, sizeof(pw_stage), idx, val, n, wshift, nwin, ghist, nblk, idx2, val2);
+    UQB_LAUNCH_B(n * 12, k_pairs_apply, uqb_grid(ctx, n, 256 * 4, 4), 256, 0, idx2, val2, n, out);
+    UQB_TRY(uqb_dfree(ctx, ghist, 0));
+    UQB_TRY(uqb_dfree(ctx, idx2, 0));
+    UQB_TRY(uqb_dfree(ctx, val2, 0));
+    return 0;
+}
+
 // ---- one sweep per digit -------------------------------------------------------------------------
 // The three-kernel pass above reads the keys twice (histogram, scatter) and runs a 3-launch scan over 256 x tiles
 // counters in between.  k_radix_onesweep does a whole pass in one launch (Adinets & Merrill's Onesweep):

@@ -833,6 +833,8 @@ static int scatter_key(uqb_ctx* ctx, const uint32_t* perm, const uint32_t* gid, 
         UQB_LAUNCH_B(n * 12, k_scatter_key, uqb_blocks(n, ST), ST, 0, perm, gid, n, key);
         return 0;
     }
+    static const bool sweeps = [] { const char* e = getenv("UQB_SCATTER_SWEEPS"); return e && e[0] == '1'; }();
+    if (!sweeps) return uqb_scatter_pairs_u32(ctx, perm, gid, n, key);      // regrouped by window first: 3 sweeps instead of one per window
     const uint32_t nwin = (uint32_t)((n + (1ull << wshift) - 1) >> wshift);
     UQB_LAUNCH_B(n * 12, k_scatter_key_windows, uqb_grid(ctx, n, ST * 4, 4), ST, 0, perm, gid, n, wshift, nwin, key);
     return 0;
@@ -1336,6 +1338,7 @@ __global__ void __launch_bounds__(ST) k_scatter_u32(const uint32_t* __restrict__
 extern "C" int uqb_scatter_u32(uqb_ctx* ctx, const uqb_array* src, const uqb_array* idx, uqb_array** out) {
     if (src->width != 4 || idx->width != 4 || src->n != idx->n) return uqb_fail(ctx, "scatter_u32: two uint32 arrays of one length expected");
     UQB_TRY(uqb_new_array(ctx, src->n, 4, out));
+    if (src->n > (3ull << 23)) return uqb_scatter_pairs_u32(ctx, (const uint32_t*)idx->d, (const uint32_t*)src->d, src->n, (uint32_t*)(*out)->d);
     if (src->n) UQB_LAUNCH_B(src->n * 12, k_scatter_u32, uqb_grid(ctx, src->n, ST, 16), ST, 0, (const uint32_t*)src->d, (const uint32_t*)idx->d, src->n,
                              (uint32_t*)(*out)->d);
     return 0;
