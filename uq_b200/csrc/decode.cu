@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(DC) k_decode_write(const dec_params* __restric
 #define DT_THREADS 256
 #define DT_TEXT_CAP (28 * 1024)
 #define DT_IN_CAP (24 * 1024)
+#define DT_FIX_CAP 512
 
 template <int BITS>
 __device__ __forceinline__ void extract_chunk16(const uint32_t* __restrict__ words, uint32_t gbit, uint32_t (&code)[16]) {
@@ -307,6 +308,9 @@ struct dt_smem {
     uint8_t base_char[256];
     uint16_t qual_lut[256];             // quality character | (restored base + 1) << 8
     uint32_t toff[DT_R + 1];            // text offset of every record relative to the staged range
+    uint16_t sel_lut[256];              // four 2-bit codes (one byte of the DNA bit string) -> PRMT selector of their four characters
+    uint32_t fix_n;                     // N restorations of this tile: (text offset << 8) | base character
+    uint32_t fix[DT_FIX_CAP];
 };
 
 __global__ void __launch_bounds__(DT_THREADS) k_decode_tiles(const dec_params* __restrict__ Pp, const uint8_t* __restrict__ dna,
@@ -320,7 +324,14 @@ __global__ void __launch_bounds__(DT_THREADS) k_decode_tiles(const dec_params* _
         S->base_char[i] = P.base_char[i];
         const int rb = P.qual_to_base[i];
         S->qual_lut[i] = (uint16_t)(P.qual_char[i] | ((rb >= 0 ? (unsigned)rb + 1u : 0u) << 8));
+        S->sel_lut[i] = (uint16_t)(((i >> 6) & 3u) | (((i >> 4) & 3u) << 4) | (((i >> 2) & 3u) << 8) | ((i & 3u) << 12));
     }
+    // Two bits per base (the usual case): the characters of four positions are ONE byte permute of the 4-entry alphabet held
+    // in a register, selected by a byte of the bit string, and leave as aligned 32-bit words.  The DNA lines are then written
+    // by work items of their own (16 positions that start at a 4-byte aligned text address); the bases that a quality code
+    // restores (N with its own quality, uq.py:1036) are rare and patched in afterwards from a per-tile list.
+    const bool fast_dna = P.bb == 2u;
+    const uint32_t tbl = (uint32_t)P.base_char[0] | ((uint32_t)P.base_char[1] << 8) | ((uint32_t)P.base_char[2] << 16) | ((uint32_t)P.base_char[3] << 24);
     const uint32_t L = P.dna_max, wd = P.wd, wq = P.wq;
     const uint32_t pad_d = 8 * wd - P.bb * L, pad_q = 8 * wq - P.bq * L;
     const uint32_t words_d = (DT_R * wd + 3) / 4 + 4;                     // QUAL words start behind the DNA words
@@ -332,7 +343,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_decode_tiles(const dec_params* _
         const uint32_t nrec = (uint32_t)(r1 - r0);
         const uint64_t o0 = rec_off[r0], o1 = r1 < n ? rec_off[r1] : total;
         const uint64_t a0 = o0 & ~15ull;
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the bulk store of the previous tile has read its text
+        if (tid == 0) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); S->fix_n = 0; }   // the bulk store of the previous tile has read its text
         __syncthreads();                                                   // previous tile fully stored
         if (o1 - a0 > DT_TEXT_CAP) { if (tid == 0) atomicOr(fallback, 1u); continue; }
         // ---- packed rows -> shared memory (big-endian words) ----
@@ -356,9 +367,37 @@ __global__ void __launch_bounds__(DT_THREADS) k_decode_tiles(const dec_params* _
         // ---- work items: chunks of 16 positions (record index fastest), then one QNAME line per item ----
         const uint32_t nsymitems = nrec * chunks;
         const uint32_t ncol = P.ncols ? P.ncols : 1u;
-        for (uint32_t item = tid; item < nsymitems + nrec * ncol; item += DT_THREADS) {
+        const uint32_t cmax = L / 16;                                       // full DNA chunks a line can hold
+        const uint32_t ndnaitems = fast_dna ? nrec * (cmax + 1u) : 0u;      // + one item per record for the unaligned head and the tail
+        for (uint32_t item = tid; item < nsymitems + ndnaitems + nrec * ncol; item += DT_THREADS) {
+            if (item >= nsymitems && item < nsymitems + ndnaitems) {
+                const uint32_t di = item - nsymitems, c = di / nrec, i = di - c * nrec;
+                const uint32_t hl = S->toff[i + 1] - S->toff[i] - 2u * L - 4u;
+                const uint32_t line = S->toff[i] + hl;                      // text offset of the DNA line
+                uint32_t h = (4u - (line & 3u)) & 3u;                       // positions in front of the first aligned word
+                if (h > L) h = L;
+                const uint32_t nfull = (L - h) / 16;
+                const uint32_t bit0 = (i * wd) * 8u + pad_d;
+                if (c < cmax) {
+                    if (c < nfull) {
+                        const uint32_t p = h + 16u * c, g = bit0 + 2u * p;
+                        const uint32_t x = __funnelshift_l(S->in_d[(g >> 5) + 1], S->in_d[g >> 5], g & 31u);   // 16 codes, first one on top
+                        uint32_t* o = reinterpret_cast<uint32_t*>(S->text + line + p);
+#pragma unroll
+                        for (int m = 0; m < 4; m++) o[m] = __byte_perm(tbl, 0u, S->sel_lut[(x >> (24 - 8 * m)) & 255u]);
+                    }
+                } else {
+                    for (uint32_t p = 0; p < L; p++) {
+                        if (p == h) { p += 16u * nfull; if (p >= L) break; }
+                        const uint32_t g = bit0 + 2u * p;
+                        const uint32_t code = (S->in_d[g >> 5] >> (30u - (g & 31u))) & 3u;
+                        S->text[line + p] = (uint8_t)(tbl >> (8u * code));
+                    }
+                }
+                continue;
+            }
             if (item >= nsymitems) {
-                const uint32_t qi = item - nsymitems, c = qi / nrec, i = qi - c * nrec;       // record index fastest
+                const uint32_t qi = item - nsymitems - ndnaitems, c = qi / nrec, i = qi - c * nrec;       // record index fastest
                 uint8_t* w = S->text + S->toff[i];
                 if (P.ncols == 0) {
                     qname_write(P, r0 + i, w);
@@ -374,11 +413,26 @@ __global__ void __launch_bounds__(DT_THREADS) k_decode_tiles(const dec_params* _
             const uint32_t c = item / nrec, i = item - c * nrec;
             const uint32_t p0 = c * 16, nsym = (p0 + 16 <= L) ? 16u : L - p0;
             uint32_t cd[16], cq[16];
-            extract_chunk16_any(P.bb, S->in_d, (i * wd) * 8u + pad_d + p0 * P.bb, cd);
             extract_chunk16_any(P.bq, in_q, (i * wq) * 8u + pad_q + p0 * P.bq, cq);
             const uint32_t hl = S->toff[i + 1] - S->toff[i] - 2u * L - 4u;      // record length - (2 L + 4) = QNAME line length
-            uint8_t* od = S->text + S->toff[i] + hl + p0;
+            const uint32_t od_off = S->toff[i] + hl + p0;
+            uint8_t* od = S->text + od_off;
             uint8_t* oq = od + L + 3;
+            if (fast_dna) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    if ((uint32_t)k < nsym) {
+                        const uint32_t ql = S->qual_lut[cq[k]];
+                        oq[k] = (uint8_t)ql;
+                        if (ql >> 8) {                                          // qual_N (uq.py:1036): patched in after the DNA items
+                            const uint32_t slot = atomicAdd(&S->fix_n, 1u);
+                            if (slot < DT_FIX_CAP) S->fix[slot] = ((od_off + (uint32_t)k) << 8) | ((ql >> 8) - 1u);
+                        }
+                    }
+                }
+                continue;
+            }
+            extract_chunk16_any(P.bb, S->in_d, (i * wd) * 8u + pad_d + p0 * P.bb, cd);
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 if ((uint32_t)k < nsym) {
@@ -389,6 +443,30 @@ __global__ void __launch_bounds__(DT_THREADS) k_decode_tiles(const dec_params* _
             }
         }
         __syncthreads();
+        if (fast_dna && S->fix_n) {                                         // uniform: written before the barrier
+            const uint32_t nf = S->fix_n;
+            if (nf <= DT_FIX_CAP) {
+                for (uint32_t j = tid; j < nf; j += DT_THREADS) { const uint32_t e = S->fix[j]; S->text[e >> 8] = (uint8_t)e; }
+            } else {
+                // more restorations than the list holds (reads full of N): walk the quality codes again
+                for (uint32_t item = tid; item < nsymitems; item += DT_THREADS) {
+                    const uint32_t c = item / nrec, i = item - c * nrec;
+                    const uint32_t p0 = c * 16, nsym = (p0 + 16 <= L) ? 16u : L - p0;
+                    uint32_t cq[16];
+                    extract_chunk16_any(P.bq, in_q, (i * wq) * 8u + pad_q + p0 * P.bq, cq);
+                    const uint32_t hl = S->toff[i + 1] - S->toff[i] - 2u * L - 4u;
+                    uint8_t* od = S->text + S->toff[i] + hl + p0;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        if ((uint32_t)k < nsym) {
+                            const uint32_t ql = S->qual_lut[cq[k]];
+                            if (ql >> 8) od[k] = (uint8_t)((ql >> 8) - 1u);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
         // ---- text out: aligned 16-byte units inside [o0, o1), bytes at the two edges ----
         {
             const uint32_t lo = (uint32_t)(o0 - a0), hi = (uint32_t)(o1 - a0);

@@ -47,13 +47,14 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
-// 0xFF in every byte j of a word whose unit-relative position 4 * k + j lies in [lo, hi)
-__device__ __forceinline__ uint32_t h2_bytemask(int lo, int hi) {
-    lo = lo < 0 ? 0 : (lo > 4 ? 4 : lo);
-    hi = hi < 0 ? 0 : (hi > 4 ? 4 : hi);
-    if (hi <= lo) return 0u;
-    const unsigned long long ones = (1ull << (8 * hi)) - 1ull;
-    return (uint32_t)((ones >> (8 * lo)) << (8 * lo));
+// bit b of the result = byte b of the 16-byte unit lies in [lo, hi) (both may lie outside 0..16)
+__device__ __forceinline__ uint32_t h2_unitmask(int lo, int hi) {
+    const uint32_t l = lo < 0 ? 0u : (uint32_t)lo, h = hi > 16 ? 16u : (uint32_t)hi;
+    return h > l ? (((1u << h) - 1u) & ~((1u << l) - 1u)) : 0u;
+}
+// four mask bits -> 0xFF in the bytes whose bit is set (the partial products of the multiply do not overlap)
+__device__ __forceinline__ uint32_t h2_nibble_bytes(uint32_t nib) {
+    return (((nib & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;
 }
 
 __device__ __forceinline__ unsigned h2_bytesum(unsigned x) {
@@ -137,13 +138,14 @@ __device__ __forceinline__ void h2_dna_unit(h2_core* S, const uint4 v, uint32_t 
         bad[k] = ex ^ w[k];
     }
     if (lo > 0 || hi < 16) {                                             // edge unit: bytes outside the line count as zeroed
+        const uint32_t vb = h2_unitmask(lo, hi);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const unsigned vm = h2_bytemask(lo - 4 * k, hi - 4 * k);
+            const unsigned vm = h2_nibble_bytes(vb >> (4 * k));
             bad[k] &= vm;
             t[k] &= vm;
-            A.zeroed += 4u - (__popc(vm) >> 3);
         }
+        A.zeroed += 16u - __popc(vb);
     }
     if (bad[0] | bad[1] | bad[2] | bad[3]) {
         // offender map: bit 8 j + k <-> byte j of word k
@@ -178,9 +180,10 @@ __device__ __forceinline__ bool h2_qual_unit(const uint4 v, int lo, int hi, uint
     unsigned w[4] = {v.x, v.y, v.z, v.w};
     unsigned bad = 0;
     if (lo > 0 || hi < 16) {
+        const uint32_t vb = h2_unitmask(lo, hi);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const unsigned vm = h2_bytemask(lo - 4 * k, hi - 4 * k);
+            const unsigned vm = h2_nibble_bytes(vb >> (4 * k));
             const unsigned chk = (w[k] & vm) | (0x21212121u & ~vm);
             bad |= ((chk | (chk + 0x01010101u)) | ~((chk & 0x7F7F7F7Fu) + 0x5F5F5F5Fu)) & 0x80808080u;
             w[k] = (w[k] & vm) | (0x7F7F7F7Fu & ~vm);                    // masked-out bytes go to the spare row
