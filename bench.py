@@ -261,12 +261,17 @@ def run_ours(args):
                 "share_of_step": round(top_ms / (ms * 1.0), 4), "algorithmic_bytes_per_launch": top_bytes / max(top_cnt, 1)}
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture (same workload, per launch)
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_full_100m_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_full_100m_summary.json")) as f:
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+            def nbytes(txt):
+                v, u = txt.split()
+                return float(v) * unit[u]
             for rec in json.load(f):
-                if rec["kernel"].replace("void ", "").split("<")[0] == top_name.split("<")[0] and n == 100_000_000:
-                    gb = float(rec["dram__bytes_read.sum"].split()[0]) + float(rec["dram__bytes_write.sum"].split()[0])
-                    roofline["traffic"] = gb * 1e9
-                    roofline["traffic_source"] = "profiles/r01_ncu_full_100m_summary.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+                base = rec["kernel"].replace("void ", "").split("<")[0]        # the timer names template instances base_variant
+                if (top_name.split("<")[0] == base or top_name.startswith(base + "_")) and n == 100_000_000:
+                    roofline["traffic"] = nbytes(rec["dram__bytes_read.sum"]) + nbytes(rec["dram__bytes_write.sum"])
+                    roofline["traffic_source"] = "profiles/r02_ncu_full_100m_summary.json (dram__bytes_read.sum + dram__bytes_write.sum)"
                     break
     except Exception:
         pass

@@ -5,6 +5,7 @@
 #   3. ncu --set full of the heaviest kernels at full size                            -> gpurun_out/r02_full_*.ncu-rep
 # Numbers printed under ncu are never bench values.
 set -x
+[ "$1" = "captureonly" ] || {
 python tools/profile_phases.py > gpurun_out/r02_phases.json 2> gpurun_out/r02_phases.err
 python tools/profile_phases.py 50000000 QNAME casava 100 > gpurun_out/r02_config3.json 2> gpurun_out/r02_config3.err
 python tools/profile_phases.py 20000000 None illumina 100 2.2 > gpurun_out/r02_config4_p22.json 2> gpurun_out/r02_config4_p22.err
@@ -13,6 +14,7 @@ python tools/profile_decode.py > gpurun_out/r02_decode.json 2> gpurun_out/r02_de
 python tools/profile_testfeed.py > gpurun_out/r02_testfeed.json 2> gpurun_out/r02_testfeed.err
 python tools/profile_sort_adversarial.py > gpurun_out/r02_sort_adversarial.json 2> gpurun_out/r02_sort_adversarial.err
 python tools/bench_layouts.py > gpurun_out/r02_layouts.json 2> gpurun_out/r02_layouts.err
+}
 [ "$1" = "nocapture" ] && exit 0
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r02_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-decode > gpurun_out/r02_launches.log 2>&1

@@ -1171,7 +1171,7 @@ def encode_sharded(ctx, comm, fq, sort=None, raw=None, pattern=None, pad=False, 
 def assemble(comm, res):
     """Gather every rank's host slices on rank 0 and put them at their place in the global members -> members dict
     (name -> ndarray as numpy.save would receive it) on rank 0, None elsewhere.  Test / small-file helper: the container
-    writer (container.ShardedWriter) lets every rank write its slices at their byte offsets of the tar instead."""
+    writer (write_container_sharded below) lets every rank write its slices at their byte offsets of the tar instead."""
     parts = comm.all_gather_object((res.describe(), res.download()))
     if comm.rank != 0:
         return None
