@@ -250,12 +250,54 @@ __global__ void __launch_bounds__(PKT_THREADS) k_pack_tiles(const uint8_t* __res
     const uint32_t pad_d = wd * 8u - L * bb, pad_q = wq * 8u - L * bq;
     const uint32_t fullc = L / 16, tailn = L % 16;
     const uint64_t ntiles = (n_reads + TL_R - 1) / TL_R;
+    // item -> (record, chunk) without an integer division: i = item / fullc through a 32-bit reciprocal (exact for the
+    // item counts of a tile: item < 2^16, 2 <= fullc < 2^10; fullc = 1 needs none)
+    const uint32_t fullc_rcp = fullc ? (uint32_t)((0x100000000ull + fullc - 1) / fullc) : 0u;
     unsigned phase = 0;
+    // The line offsets of the NEXT tile are loaded while this one is packed (three per thread, plus the byte bounds), so that
+    // the tile load is one exposed round trip - the bulk copy - instead of two dependent ones.
+    constexpr int OPT = (4 * TL_R + 1 + PKT_THREADS - 1) / PKT_THREADS;
+    uint64_t pre_off[OPT], pre_b0 = 0, pre_b1 = 0;
+    auto prefetch = [&](uint64_t t) {
+        const uint64_t r0 = t * TL_R, r1 = (r0 + TL_R < n_reads) ? r0 + TL_R : n_reads;
+        const uint32_t nrec = (uint32_t)(r1 - r0);
+        pre_b0 = __ldg(line_off + 4 * r0); pre_b1 = __ldg(line_off + 4 * r1);
+#pragma unroll
+        for (int k = 0; k < OPT; k++) {
+            const uint32_t i = tid + k * PKT_THREADS;
+            pre_off[k] = i <= 4 * nrec ? __ldg(line_off + 4 * r0 + i) : 0ull;
+        }
+    };
+    if (blockIdx.x < ntiles) prefetch(blockIdx.x);
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint64_t r0 = t * TL_R, r1 = (r0 + TL_R < n_reads) ? r0 + TL_R : n_reads;
-        uint64_t a0;
-        const uint32_t nrec = tile_load(T, d, n_bytes, line_off, r0, r1, phase, &a0);
-        if (!nrec) { if (tid == 0) atomicOr(fallback, 1u); continue; }
+        // ---- tile_load (tile.cuh) with the prefetched offsets ----
+        __syncthreads();                                     // every thread is done with the previous tile
+        const uint32_t nrec = (uint32_t)(r1 - r0);
+        const uint64_t b0 = pre_b0, b1 = pre_b1, a0 = b0 & ~15ull;
+        const bool fits = b1 - a0 <= TL_CAP;
+        if (fits) {
+            uint64_t a1 = (b1 + 15) & ~15ull;
+            const uint64_t lim = n_bytes & ~15ull;
+            if (a1 > lim) a1 = lim;
+            if (a1 < a0) a1 = a0;
+            const uint32_t bulk = (uint32_t)(a1 - a0);
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&T->bar, bulk);
+                if (bulk) bulk_g2s(T->bytes, d + a0, bulk, &T->bar);
+            }
+#pragma unroll
+            for (int k = 0; k < OPT; k++) {
+                const uint32_t i = tid + k * PKT_THREADS;
+                if (i <= 4 * nrec) T->loff[i] = (uint32_t)(pre_off[k] - a0);
+            }
+            for (uint64_t q = a1 + tid; q < b1; q += PKT_THREADS) T->bytes[q - a0] = d[q];
+        }
+        if (t + gridDim.x < ntiles) prefetch(t + gridDim.x);   // in flight during the wait and the whole tile
+        if (!fits) { if (tid == 0) atomicOr(fallback, 1u); continue; }
+        mbar_wait(&T->bar, phase);
+        __syncthreads();
         phase ^= 1u;
         for (uint32_t i = tid; i < words_d; i += PKT_THREADS) stage_d[i] = 0;
         for (uint32_t i = tid; i < words_q; i += PKT_THREADS) stage_q[i] = 0;
@@ -265,7 +307,7 @@ __global__ void __launch_bounds__(PKT_THREADS) k_pack_tiles(const uint8_t* __res
         const uint32_t items_full = nrec * fullc, items = items_full + (tailn ? nrec : 0u);
         for (uint32_t item = tid; item < items; item += PKT_THREADS) {
             uint32_t i, c, nsym;
-            if (item < items_full) { i = item / fullc; c = item - i * fullc; nsym = 16; }
+            if (item < items_full) { i = fullc > 1u ? __umulhi(item, fullc_rcp) : item; c = item - i * fullc; nsym = 16; }
             else { i = item - items_full; c = fullc; nsym = tailn; }
             const uint32_t o1 = T->loff[4 * i + 1], o2 = T->loff[4 * i + 2], o3 = T->loff[4 * i + 3];
             if (o2 - o1 - 1 != L) { atomicOr(fallback, 2u); continue; }      // not a fixed-length file after all
