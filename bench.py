@@ -19,8 +19,9 @@ layout, ending with every output array resident in HBM in its final layout.
          on a bounded sample of the same FASTQ.
 
 Multi-GPU (torchrun, one process per GPU): rank r holds the contiguous read range [r n, (r+1) n) of ONE file and the
-ranks produce ONE global container (merged statistics, partition-first sample sort with an all-to-all of the packed
-rows over NVLink, global --sort order).  Weak scaling: n = 100 M reads per GPU.  Before the timed
+ranks produce ONE global container (merged statistics, partition-first sample sort whose rows are stored straight into
+the receivers' peer-mapped windows over NVLink - NCCL all-to-all where no window is available -, global --sort order;
+DESIGN.md section 6).  `--strong` divides ONE file of --reads reads over the ranks instead.  Weak scaling: n = 100 M reads per GPU.  Before the timed
 loop every N>1 run encodes a small file both ways (sharded over the ranks and whole on rank 0), compares every member
 and the config, decodes the container over the ranks, and reports the outcome as `parity_check`; a mismatch ends the
 run with a non-zero exit code.  `--multi shards` (independent container shards, no collective) is kept as a diagnostic.

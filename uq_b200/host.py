@@ -340,6 +340,15 @@ class DeviceMembers:
             a.free()
         self.items = {}
 
+    def __del__(self):
+        # members dropped without free() (an exception in the middle of run_mix): the queued device->host copies must
+        # finish before the garbage-collected arrays are recycled by the arena
+        try:
+            if self.items and self.sink is not None and self.ctx is not None and self.ctx.h:
+                self.ctx.copy_sync()
+        except Exception:
+            pass
+
 
 def table_ndarray(flat, n, width, pattern):
     """stream bytes of a laid-out table -> the ndarray object the reference hands to numpy.save (shape and memory

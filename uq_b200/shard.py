@@ -1,9 +1,8 @@
-"""Multi-GPU sharding of the encode path (one process per GPU).
-
-Round-1 scheme: reads shard naturally, so rank r encodes the contiguous read range
-[r * n, (r + 1) * n) into its own container shard; no data-path collective is needed.  The only
-cross-rank traffic is the timing/throughput reduction below.  `backend` is "nccl" on GPUs and "gloo" in
-the CPU tests."""
+"""Launch plumbing of the multi-GPU runs (one process per GPU): rank / world size from the torchrun environment, the
+read range of a rank under weak scaling, and the max / sum reductions of bench.py's timing contract (`backend` is "nccl"
+on GPUs and "gloo" in the CPU tests).  The data path of a multi-GPU encode - ONE global container from N ranks - is
+uq_b200/multigpu.py; `bench.py --multi shards` (independent container shards per rank, no data-path collective) uses only
+what is here."""
 import os
 
 
