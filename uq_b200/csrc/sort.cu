@@ -447,6 +447,9 @@ __global__ void __launch_bounds__(ST) k_small_groups_packed(const uint8_t* __res
             cur += 32;
         }
         while (cur < c1) {
+            // the row index of position cur + lane is requested together with the head flags: the rows can then be fetched
+            // as soon as the window is known (two dependent round trips per window instead of three)
+            const uint32_t r_spec = cur + lane < n ? perm[cur + lane] : 0u;
             const unsigned h1 = __ballot_sync(0xffffffffu, cur + lane < n ? head[cur + lane] != 0u : true);             // bit 0 is set
             const unsigned h2 = __ballot_sync(0xffffffffu, cur + 32 + lane < n ? head[cur + 32 + lane] != 0u : true);
             const unsigned hi = (h1 >> 1) | (h2 << 31);            // bit k: a group starts at cur + 1 + k
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(ST) k_small_groups_packed(const uint8_t* __res
             const unsigned live = cnt == 32u ? 0xffffffffu : ((1u << cnt) - 1u);
             const unsigned hm = h1 & live;
             if (hm == live) { cur += cnt; continue; }              // single rows only
-            const uint32_t r = lane < cnt ? perm[cur + lane] : 0u;
+            const uint32_t r = lane < cnt ? r_spec : 0u;
             const unsigned upto = (2u << lane) - 1u;               // lanes 0 .. lane
             const uint32_t gs = 31u - (uint32_t)__clz((int)(hm & upto));
             const unsigned above = hm & ~upto;
