@@ -54,6 +54,19 @@ def _rand_names(rng, style):
     return out
 
 
+def test_separator_class_that_changes_meaning_is_refused():
+    """uq.py:433-436 pastes the separators into a regex character class unescaped: ':-_' is a RANGE that takes in the
+    capitals.  A class that does not behave like the set it was meant to be is refused (Q11); a harmless one passes."""
+    bad = _fastq([b"@x%d:%d-%d_%d" % (i, i, i + 1, i + 2) for i in range(1, 30)])       # separators ':', '-', '_' in that order
+    st, n = emu_stats(bad)
+    with pytest.raises(host.UQError, match="Q11|unusual"):
+        host.derive_qname_layout(st, n)
+    ok = _fastq([b"@ab_%d-%d" % (i, 2 * i) for i in range(1, 30)])                       # class '_-' : the dash is last, a literal
+    st, n = emu_stats(ok)
+    prefix, suffix, seps = host.derive_qname_layout(st, n)
+    assert seps in ("-", "_-") and prefix.startswith("@ab")
+
+
 @pytest.mark.parametrize("style", [0, 1, 2, 3])
 def test_separator_logic_equals_sequential_reference(style):
     """The closed form derived from (first_lcp_eq, last_count_mismatch) reproduces the reference's

@@ -150,12 +150,19 @@ def derive_qname_layout(st, n_reads):
     if len(sep_count) == 0:
         raise UQError('ERROR: no QNAME separators (the reference crashes on such files, Q6)')
 
-    def order_seps(name):                          # uq.py:433-436
-        return ''.join(re.findall('([' + ''.join(sep_count) + ']+)', name[len(prefix):-1 - len(suffix)]))
+    def order_seps(name, cls=None):                # uq.py:433-436
+        return ''.join(re.findall('([' + (cls if cls is not None else ''.join(sep_count)) + ']+)', name[len(prefix):-1 - len(suffix)]))
     try:
         a, b = order_seps(last), order_seps(first)
     except re.error as e:
         raise UQError('ERROR: QNAME separators %r break the reference regex (Q11): %s' % (''.join(sep_count), e))
+    # The reference pastes the separator characters into a character class unescaped (in dict order): '-' between two
+    # others silently becomes a RANGE (':-_' takes in A-Z), a leading '^' negates the class.  Such a class is only accepted
+    # when it behaves like the set of characters it was meant to be; otherwise the file is refused (Q11).
+    if any(ch in '-^]\\' for ch in sep_count):
+        meant = ''.join(re.escape(ch) for ch in sep_count)
+        if (a, b) != (order_seps(last, meant), order_seps(first, meant)):
+            raise UQError('ERROR: QNAME separators %r change meaning inside the reference regex class (Q11)' % ''.join(sep_count))
     if a != b:                                     # uq.py:438-444
         raise UQError("ERROR: Sorry, the separators used in this file's QNAME/headers are so unusual/improbable that "
                       "I didn't think it was worth the time to write the code on how to deal with it, only identify it.")
