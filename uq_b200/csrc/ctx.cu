@@ -304,6 +304,16 @@ int uqb_dalloc(uqb_ctx* ctx, void** p, size_t nbytes) {
 
 int uqb_dfree(uqb_ctx* ctx, void* p, size_t /*nbytes*/) {
     if (!p) return 0;
+    // a block that an async device->host copy still reads (an array dropped without uqb_ctx_copy_sync, e.g. by an error
+    // path or a garbage collector) must not be recycled under the DMA engine: wait for the copy stream first
+    if (!ctx->copies_in_flight.empty()) {
+        for (const void* q : ctx->copies_in_flight)
+            if (q == p) {
+                if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+                ctx->copies_in_flight.clear();
+                break;
+            }
+    }
     uqb_arena& A = ctx->arena;
     const uint64_t off = (uint64_t)(uintptr_t)p - A.base;
     auto u = A.used.find(off);
@@ -467,12 +477,16 @@ extern "C" int uqb_array_download_async(uqb_ctx* ctx, const uqb_array* a, void* 
     UQB_CUDA(cudaEventRecord(ev, ctx->stream));
     UQB_CUDA(cudaStreamWaitEvent(cs, ev, 0));
     UQB_CUDA(cudaEventDestroy(ev));                      // released once the wait has consumed it
-    if (nbytes) UQB_CUDA(cudaMemcpyAsync(host, a->d, nbytes, cudaMemcpyDeviceToHost, cs));
+    if (nbytes) {
+        UQB_CUDA(cudaMemcpyAsync(host, a->d, nbytes, cudaMemcpyDeviceToHost, cs));
+        ctx->copies_in_flight.push_back(a->d);           // uqb_dfree waits for the copy before it recycles the block
+    }
     return 0;
 }
 
 extern "C" int uqb_ctx_copy_sync(uqb_ctx* ctx) {
     if (ctx->copy_stream) UQB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->copies_in_flight.clear();
     return 0;
 }
 

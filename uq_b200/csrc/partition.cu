@@ -213,7 +213,10 @@ __global__ void __launch_bounds__(SR_THREADS) k_scatter_rows_by_pos(const uint8_
 // unaligned 4-byte words: fine for local memory, but over NVLink (peer windows) that is a packet per sector - measured 240
 // GB/s against 770 GB/s for large aligned stores.
 #define SRR_MAXD 64
-template <int SUB>
+// TMA = true: the 16-byte aligned interior of every run leaves shared memory as ONE bulk store (cp.async.bulk.global.shared,
+// issued by the thread that owns the destination); the TMA unit does the address generation and keeps more bytes in flight
+// towards a peer than 16-byte stores of the SM do.
+template <int SUB, bool TMA>
 __global__ void __launch_bounds__(SR_THREADS) k_scatter_rows_runs(const uint8_t* __restrict__ rows, uint64_t n, uint32_t width,
                                                                  const uint32_t* __restrict__ pos, pp_segs segs, uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t srr_smem[];                 // [input tile | output image]
@@ -227,9 +230,11 @@ __global__ void __launch_bounds__(SR_THREADS) k_scatter_rows_runs(const uint8_t*
     uint8_t* img = srr_smem + in_bytes;
     const uint32_t* in32 = reinterpret_cast<const uint32_t*>(in);
     const uint64_t ntiles = (n + SR_THREADS - 1) / SR_THREADS;
+    bool bulk_pending = false;
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint64_t r0 = t * SR_THREADS;
         const uint32_t nr = (uint32_t)(n - r0 < SR_THREADS ? n - r0 : SR_THREADS);
+        if (TMA && bulk_pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); bulk_pending = false; }   // the image has been read
         __syncthreads();
         if (tid < segs.n) { cnt[tid] = 0; minpos[tid] = 0xFFFFFFFFu; }
         const uint4* src = reinterpret_cast<const uint4*>(rows + r0 * width);
@@ -277,14 +282,28 @@ __global__ void __launch_bounds__(SR_THREADS) k_scatter_rows_runs(const uint8_t*
         }
         __syncthreads();
         // image runs -> global
+        if (TMA && tid < segs.n && cnt[tid]) {
+            const uint32_t i0 = ioff[tid], i1 = i0 + cnt[tid] * width;
+            const uint32_t a = (i0 + 15u) & ~15u, b = i1 & ~15u;
+            if (a < b) {
+                uint8_t* G = reinterpret_cast<uint8_t*>((uintptr_t)gaddr[tid]) - i0;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(G + a),
+                             "r"((uint32_t)__cvta_generic_to_shared(img + a)), "r"(b - a)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                bulk_pending = true;
+            }
+        }
         for (uint32_t k = 0; k < segs.n; k++) {
             if (!cnt[k]) continue;
             const uint32_t i0 = ioff[k], i1 = i0 + cnt[k] * width;
             const uint32_t a = (i0 + 15u) & ~15u, b = i1 & ~15u;
             uint8_t* G = reinterpret_cast<uint8_t*>((uintptr_t)gaddr[k]) - i0;     // image offset x <-> G + x
             if (a <= b) {
-                for (uint32_t x = a + 16u * tid; x < b; x += 16u * SR_THREADS)
-                    *reinterpret_cast<uint4*>(G + x) = *reinterpret_cast<const uint4*>(img + x);
+                if (!TMA)
+                    for (uint32_t x = a + 16u * tid; x < b; x += 16u * SR_THREADS)
+                        *reinterpret_cast<uint4*>(G + x) = *reinterpret_cast<const uint4*>(img + x);
                 if (tid < a - i0) G[i0 + tid] = img[i0 + tid];
                 if (tid < i1 - b) G[b + tid] = img[b + tid];
             } else {
@@ -292,6 +311,7 @@ __global__ void __launch_bounds__(SR_THREADS) k_scatter_rows_runs(const uint8_t*
             }
         }
     }
+    if (TMA && bulk_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the last bulk stores have landed
 }
 
 template <typename T>
@@ -324,6 +344,7 @@ static int scatter_rows_impl(uqb_ctx* ctx, const uqb_array* table, const uqb_arr
         UQB_LAUNCH_B(ab, k_scatter_items_by_pos<uint8_t>, uqb_grid(ctx, n, SR_THREADS, iw), SR_THREADS, 0, (const uint8_t*)table->d, n, (const uint32_t*)pos->d, S, o);
     } else {
         static const bool by_rows = [] { const char* e = getenv("UQB_SCATTER_ROWS"); return e && e[0] == '1'; }();
+        static const bool tma = [] { const char* e = getenv("UQB_SCATTER_TMA"); return e && e[0] == '1'; }();
         if (!by_rows) {
             // contiguous runs per destination, regrouped in shared memory
             const size_t in_bytes = ((size_t)SR_THREADS * w + 32 + 15) & ~(size_t)15;
@@ -334,17 +355,26 @@ static int scatter_rows_impl(uqb_ctx* ctx, const uqb_array* table, const uqb_arr
             const uint64_t ntiles = (n + SR_THREADS - 1) / SR_THREADS, cap = (uint64_t)ctx->sm_count * ctas;
             const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
             if (w <= 32) {
-                auto k_scatter_rows_runs_8 = k_scatter_rows_runs<8>;
+                auto k_scatter_rows_runs_8 = k_scatter_rows_runs<8, false>;
+                auto k_scatter_rows_tma_8 = k_scatter_rows_runs<8, true>;
                 UQB_CUDA(cudaFuncSetAttribute(k_scatter_rows_runs_8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                UQB_LAUNCH_B(ab, k_scatter_rows_runs_8, grid, SR_THREADS, smem, (const uint8_t*)table->d, n, w, (const uint32_t*)pos->d, S, o);
+                UQB_CUDA(cudaFuncSetAttribute(k_scatter_rows_tma_8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (tma) UQB_LAUNCH_B(ab, k_scatter_rows_tma_8, grid, SR_THREADS, smem, (const uint8_t*)table->d, n, w, (const uint32_t*)pos->d, S, o);
+                else UQB_LAUNCH_B(ab, k_scatter_rows_runs_8, grid, SR_THREADS, smem, (const uint8_t*)table->d, n, w, (const uint32_t*)pos->d, S, o);
             } else if (w <= 64) {
-                auto k_scatter_rows_runs_16 = k_scatter_rows_runs<16>;
+                auto k_scatter_rows_runs_16 = k_scatter_rows_runs<16, false>;
+                auto k_scatter_rows_tma_16 = k_scatter_rows_runs<16, true>;
                 UQB_CUDA(cudaFuncSetAttribute(k_scatter_rows_runs_16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                UQB_LAUNCH_B(ab, k_scatter_rows_runs_16, grid, SR_THREADS, smem, (const uint8_t*)table->d, n, w, (const uint32_t*)pos->d, S, o);
+                UQB_CUDA(cudaFuncSetAttribute(k_scatter_rows_tma_16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (tma) UQB_LAUNCH_B(ab, k_scatter_rows_tma_16, grid, SR_THREADS, smem, (const uint8_t*)table->d, n, w, (const uint32_t*)pos->d, S, o);
+                else UQB_LAUNCH_B(ab, k_scatter_rows_runs_16, grid, SR_THREADS, smem, (const uint8_t*)table->d, n, w, (const uint32_t*)pos->d, S, o);
             } else {
-                auto k_scatter_rows_runs_32 = k_scatter_rows_runs<32>;
+                auto k_scatter_rows_runs_32 = k_scatter_rows_runs<32, false>;
+                auto k_scatter_rows_tma_32 = k_scatter_rows_runs<32, true>;
                 UQB_CUDA(cudaFuncSetAttribute(k_scatter_rows_runs_32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                UQB_LAUNCH_B(ab, k_scatter_rows_runs_32, grid, SR_THREADS, smem, (const uint8_t*)table->d, n, w, (const uint32_t*)pos->d, S, o);
+                UQB_CUDA(cudaFuncSetAttribute(k_scatter_rows_tma_32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (tma) UQB_LAUNCH_B(ab, k_scatter_rows_tma_32, grid, SR_THREADS, smem, (const uint8_t*)table->d, n, w, (const uint32_t*)pos->d, S, o);
+                else UQB_LAUNCH_B(ab, k_scatter_rows_runs_32, grid, SR_THREADS, smem, (const uint8_t*)table->d, n, w, (const uint32_t*)pos->d, S, o);
             }
             return 0;
         }
