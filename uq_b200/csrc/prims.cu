@@ -96,16 +96,42 @@ __global__ void __launch_bounds__(PR_THREADS) k_scan_apply(const uint32_t* in, T
     uint64_t base = (uint64_t)blockIdx.x * PR_TILE + (uint64_t)threadIdx.x * PR_ITEMS;
     uint32_t v[PR_ITEMS];
     Tout s = 0;
+    // full threads move their 16 items as 128-bit words (the radix passes scan 256 x tiles counters forty times per encode)
+    const bool full = base + PR_ITEMS <= n && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    if (full) {
+        const uint4* p = reinterpret_cast<const uint4*>(in + base);       // plain loads: `in` may alias `out`
 #pragma unroll
-    for (int i = 0; i < PR_ITEMS; i++) {
-        v[i] = (base + i < n) ? in[base + i] : 0u;
-        s += (Tout)v[i];
+        for (int i = 0; i < PR_ITEMS / 4; i++) {
+            const uint4 q = p[i];
+            v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+        }
+#pragma unroll
+        for (int i = 0; i < PR_ITEMS; i++) s += (Tout)v[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < PR_ITEMS; i++) {
+            v[i] = (base + i < n) ? in[base + i] : 0u;
+            s += (Tout)v[i];
+        }
     }
     Tout ex = block_exclusive_scan<Tout>(s, nullptr) + block_offsets[blockIdx.x];
+    if (full && sizeof(Tout) == 4) {
+        uint4* o = reinterpret_cast<uint4*>(out + base);
 #pragma unroll
-    for (int i = 0; i < PR_ITEMS; i++) {
-        if (base + i < n) out[base + i] = ex;
-        ex += (Tout)v[i];
+        for (int i = 0; i < PR_ITEMS / 4; i++) {
+            uint4 q;
+            q.x = (uint32_t)ex; ex += (Tout)v[4 * i];
+            q.y = (uint32_t)ex; ex += (Tout)v[4 * i + 1];
+            q.z = (uint32_t)ex; ex += (Tout)v[4 * i + 2];
+            q.w = (uint32_t)ex; ex += (Tout)v[4 * i + 3];
+            o[i] = q;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < PR_ITEMS; i++) {
+            if (base + i < n) out[base + i] = ex;
+            ex += (Tout)v[i];
+        }
     }
 }
 
